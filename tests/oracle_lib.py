@@ -1,0 +1,151 @@
+"""ctypes bindings of the CPU oracle (oracle/liboracle.so). Test infrastructure only."""
+from __future__ import annotations
+
+import ctypes as C
+import subprocess
+from pathlib import Path
+
+import numpy as np
+
+ROOT = Path(__file__).resolve().parents[1]
+ORACLE_DIR = ROOT / "oracle"
+_lib = None
+
+dp = C.POINTER(C.c_double)
+ip = C.POINTER(C.c_int)
+
+
+def _p(a):
+    return None if a is None else a.ctypes.data_as(dp)
+
+
+def _pi(a):
+    return None if a is None else a.ctypes.data_as(ip)
+
+
+def F(a):
+    """contiguous float64 copy"""
+    return np.ascontiguousarray(a, dtype=np.float64)
+
+
+def build_oracle(force=False):
+    so = ORACLE_DIR / "liboracle.so"
+    srcs = list(ORACLE_DIR.glob("*.hpp")) + list(ORACLE_DIR.glob("*.cpp")) + list(ORACLE_DIR.glob("*.inc"))
+    if force or not so.exists() or any(s.stat().st_mtime > so.stat().st_mtime for s in srcs):
+        subprocess.run(["make", "-C", str(ORACLE_DIR), "-s"], check=True)
+    return so
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        _lib = C.CDLL(str(build_oracle()))
+        _lib.orc_time_discretization.restype = C.c_int
+        _lib.orc_riccati.restype = C.c_int
+        _lib.orc_lu_projection.restype = C.c_int
+        _lib.orc_sqp_test_problem.restype = C.c_int
+    return _lib
+
+
+def time_discretization(t0, tf, dt, events):
+    ev = F(events)
+    cap = int((tf - t0) / dt) * 2 + 2 * len(ev) + 16
+    t = np.zeros(cap)
+    e = np.zeros(cap, dtype=np.int32)
+    n = lib().orc_time_discretization(C.c_double(t0), C.c_double(tf), C.c_double(dt), _p(ev), C.c_int(len(ev)), _p(t), _pi(e), C.c_int(cap))
+    assert n <= cap
+    return t[:n].copy(), e[:n].copy()
+
+
+def riccati(A, B, b, Q, S, R, q, r, dx0, nu=None, reg=1e-12):
+    """Padded stage arrays: A (N,nx,nx) etc. given as numpy arrays in math layout [k, row, col]."""
+    N, nx = A.shape[0], A.shape[1]
+    numax = B.shape[2]
+    nu = np.full(N, numax, dtype=np.int32) if nu is None else np.ascontiguousarray(nu, dtype=np.int32)
+    cm = lambda M: F(np.swapaxes(M, -1, -2))  # column-major per stage
+    dx = np.zeros((N + 1, nx))
+    du = np.zeros((N, numax))
+    P = np.zeros((N + 1, nx, nx))
+    p = np.zeros((N + 1, nx))
+    K = np.zeros((N, nx, numax))
+    kff = np.zeros((N, numax))
+    rc = lib().orc_riccati(C.c_int(N), C.c_int(nx), C.c_int(numax), _pi(nu), _p(cm(A)), _p(cm(B)), _p(F(b)), _p(cm(Q)), _p(cm(S)),
+                           _p(cm(R)), _p(F(q)), _p(F(r)), _p(F(dx0)), C.c_double(reg), _p(dx), _p(du), _p(P), _p(p), _p(K), _p(kff))
+    if rc != 0:
+        raise RuntimeError("oracle riccati failed")
+    return dict(dx=dx, du=du, P=np.swapaxes(P, 1, 2).copy(), p=p, K=np.swapaxes(K, 1, 2).copy(), k=kff)
+
+
+def lu_projection(Cm, D, e):
+    nc, nx = Cm.shape
+    nu = D.shape[1]
+    Pu = np.zeros((nu - nc, nu))
+    Px = np.zeros((nx, nu))
+    u0 = np.zeros(nu)
+    rank = lib().orc_lu_projection(C.c_int(nc), C.c_int(nx), C.c_int(nu), _p(F(Cm.T)), _p(F(D.T)), _p(F(e)), _p(Pu), _p(Px), _p(u0))
+    return Pu.T.copy(), Px.T.copy(), u0, rank
+
+
+def change_of_input_variables(A, B, b, Q, S, R, q, r, c, Pu, Px, u0):
+    nx, nu = B.shape
+    nut = Pu.shape[1]
+    cmA, cmB, cmQ, cmS, cmR = F(A.T), F(B.T), F(Q.T), F(S.T), F(R.T)
+    bb, qq, rr = F(b).copy(), F(q).copy(), F(r).copy()
+    cc = C.c_double(c)
+    Bt, St, Rt, rt = np.zeros((nut, nx)), np.zeros((nx, nut)), np.zeros((nut, nut)), np.zeros(nut)
+    lib().orc_change_of_input_variables(C.c_int(nx), C.c_int(nu), C.c_int(nut), _p(cmA), _p(cmB), _p(bb), _p(cmQ), _p(cmS), _p(cmR), _p(qq),
+                                        _p(rr), C.byref(cc), _p(F(Pu.T)), _p(F(Px.T)), _p(F(u0)), _p(Bt), _p(St), _p(Rt), _p(rt))
+    return dict(A=cmA.T.copy(), B=Bt.T.copy(), b=bb, Q=cmQ.T.copy(), S=St.T.copy(), R=Rt.T.copy(), q=qq, r=rt, c=cc.value)
+
+
+def rk4_sensitivity_linear(A, B, x, u, dt):
+    nx, nu = B.shape
+    Ad, Bd, xn, xv = np.zeros((nx, nx)), np.zeros((nu, nx)), np.zeros(nx), np.zeros(nx)
+    lib().orc_rk4_sensitivity_linear(C.c_int(nx), C.c_int(nu), _p(F(A.T)), _p(F(B.T)), _p(F(x)), _p(F(u)), C.c_double(dt), _p(Ad), _p(Bd),
+                                     _p(xn), _p(xv))
+    return Ad.T.copy(), Bd.T.copy(), xn, xv
+
+
+class _LqProblem(C.Structure):
+    _fields_ = [("kind", C.c_int), ("nx", C.c_int), ("nu", C.c_int), ("A", dp), ("B", dp), ("G", dp), ("Q", dp), ("R", dp), ("P", dp),
+                ("Qf", dp), ("Qe", dp), ("xRef", dp), ("uRef", dp), ("nModes", C.c_int), ("Cm", dp), ("Dm", dp), ("em", dp),
+                ("nEvents", C.c_int), ("eventTimes", dp), ("modeSequence", ip), ("t0", C.c_double), ("tf", C.c_double), ("x0", dp),
+                ("dt", C.c_double), ("sqpIteration", C.c_int)]
+
+
+def sqp_test_problem(kind, nx, nu, x0, t0, tf, dt, sqp_iteration, A=None, B=None, G=None, Q=None, R=None, P=None, Qf=None, Qe=None, xRef=None,
+                     uRef=None, Cm=None, Dm=None, em=None, event_times=(), mode_sequence=None):
+    keep = []
+
+    def cm(M):
+        if M is None:
+            return None
+        a = F(np.asarray(M).T)
+        keep.append(a)
+        return _p(a)
+
+    def v(x):
+        if x is None:
+            return None
+        a = F(x)
+        keep.append(a)
+        return _p(a)
+
+    ev = F(event_times)
+    ms = np.ascontiguousarray(mode_sequence if mode_sequence is not None else [-1] * (len(ev) + 1), dtype=np.int32)
+    nmodes = 0 if Cm is None else np.asarray(Cm).shape[0]
+    pr = _LqProblem(kind, nx, nu, cm(A), cm(B), cm(G), cm(Q), cm(R), cm(P), cm(Qf), cm(Qe), v(xRef), v(uRef), nmodes,
+                    v(None if Cm is None else np.asarray(Cm)), v(None if Dm is None else np.asarray(Dm)), v(em), len(ev), _p(ev), _pi(ms),
+                    t0, tf, v(x0), dt, sqp_iteration)
+    cap = int((tf - t0) / dt) * 2 + 2 * len(ev) + 16
+    times, events = np.zeros(cap), np.zeros(cap, dtype=np.int32)
+    x, u, K = np.zeros((cap, nx)), np.zeros((cap, nu)), np.zeros((cap, nx, nu))
+    log = np.zeros((64, 16))
+    nit = C.c_int(0)
+    n = lib().orc_sqp_test_problem(C.byref(pr), C.c_int(cap), _p(times), _pi(events), _p(x), _p(u), _p(K), C.c_int(64), _p(log), C.byref(nit))
+    assert n > 0, n
+    return dict(t=times[:n], event=events[:n], x=x[:n], u=u[: n - 1], K=np.swapaxes(K[: n - 1], 1, 2).copy(), log=log[: nit.value])
+
+
+LOG_FIELDS = ["base_merit", "base_cost", "base_dynSSE", "base_eqSSE", "merit", "cost", "dynSSE", "eqSSE", "stepSize", "stepType", "dx_norm",
+              "du_norm", "armijo", "convergence"]

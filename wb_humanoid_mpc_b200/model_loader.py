@@ -1,0 +1,430 @@
+"""Host-side loader: reference config files (URDF + task.info + reference.info + gait.info) -> flat model description.
+
+The reference builds its rigid-body model and OCP constants inside C++ objects
+(`createCustomPinocchioInterface`, humanoid_common_mpc/src/pinocchio_model/createPinocchioModel.cpp:144-182;
+`ModelSettings`, src/common/ModelSettings.cpp:110-185; `HumanoidCostConstraintFactory`,
+src/HumanoidCostConstraintFactory.cpp:77-245; `WBMpcInterface`, humanoid_wb_mpc/src/WBMpcInterface.cpp:69-199).
+A GPU cannot consume those objects, so this loader re-derives the same constants from the same
+files and emits one flat dictionary (see `build_wb_model`) that is (a) passed across the C ABI as
+`b200sqp_model_desc` and (b) stored as JSON so the GPU box needs neither the reference nor a URDF parser.
+
+Conventions reproduced from the reference / Pinocchio's URDF importer:
+  * joints not in `mpcModelJointNames` are welded (FIXED) and the child link inertia is folded
+    into the parent body (Pinocchio `appendBodyToJoint`), createPinocchioModel.cpp:156-164;
+  * joint order is a depth-first walk with children sorted by joint name (urdfdom stores joints in a
+    std::map), which yields the order listed in task.info `initialState` (task.info:119-186);
+  * the floating base is `JointModelComposite(Translation, SphericalZYX)` (createPinocchioModel.cpp:60-67);
+  * contact / collision frames are rigidly attached to the ankle-roll joint frame
+    (createPinocchioModel.cpp:76-131).
+"""
+from __future__ import annotations
+
+import json
+import math
+import re
+import xml.etree.ElementTree as ET
+from pathlib import Path
+
+import numpy as np
+
+# ----------------------------------------------------------------------------------------------
+# boost::property_tree INFO subset parser (loadData::loadPtreeValue / loadEigenMatrix / loadStdVector,
+# ocs2_core/include/ocs2_core/misc/LoadData.h)
+# ----------------------------------------------------------------------------------------------
+
+
+def _tokenize_info(text: str):
+    toks = []
+    for raw in text.splitlines():
+        line = raw.split(";")[0]  # ';' starts a comment
+        # '//' comments appear in the shipped task.info as well
+        line = line.split("//")[0]
+        for m in re.finditer(r'"[^"]*"|\{|\}|[^\s{}]+', line):
+            toks.append(m.group(0))
+        toks.append("\n")
+    return toks
+
+
+def parse_info(path: str | Path) -> dict:
+    """Parse a boost INFO file into nested dicts (leaf values stay strings)."""
+    toks = _tokenize_info(Path(path).read_text())
+    pos = 0
+
+    def parse_block():
+        nonlocal pos
+        node: dict = {}
+        while pos < len(toks):
+            t = toks[pos]
+            if t == "\n":
+                pos += 1
+                continue
+            if t == "}":
+                pos += 1
+                return node
+            key = t.strip('"')
+            pos += 1
+            val = None
+            # value on the same line?
+            if pos < len(toks) and toks[pos] not in ("\n", "{", "}"):
+                val = toks[pos].strip('"')
+                pos += 1
+                # swallow trailing tokens on the line (e.g. stray ';' less comments)
+                while pos < len(toks) and toks[pos] not in ("\n", "{", "}"):
+                    pos += 1
+            # skip newlines before a possible '{'
+            save = pos
+            while pos < len(toks) and toks[pos] == "\n":
+                pos += 1
+            if pos < len(toks) and toks[pos] == "{":
+                pos += 1
+                child = parse_block()
+                node[key] = child
+            else:
+                pos = save
+                node[key] = val
+        return node
+
+    return parse_block()
+
+
+def info_get(tree: dict, dotted: str, default=None):
+    node = tree
+    for k in dotted.split("."):
+        if not isinstance(node, dict) or k not in node:
+            if default is not None:
+                return default
+            raise KeyError(dotted)
+        node = node[k]
+    return node
+
+
+def info_float(tree, dotted, default=None) -> float:
+    v = info_get(tree, dotted, default)
+    return float(str(v).rstrip(";"))
+
+
+def info_matrix(tree: dict, name: str, rows: int, cols: int) -> np.ndarray:
+    """loadData::loadEigenMatrix: entries '(i,j) v', optional 'scaling', missing entries = 0."""
+    blk = tree[name]
+    out = np.zeros((rows, cols))
+    scaling = float(blk.get("scaling", 1.0))
+    for k, v in blk.items():
+        m = re.fullmatch(r"\((\d+),(\d+)\)", k)
+        if m:
+            out[int(m.group(1)), int(m.group(2))] = float(v)
+    return out * scaling
+
+
+def info_list(tree: dict, dotted: str) -> list[str]:
+    blk = info_get(tree, dotted)
+    items = []
+    for k, v in blk.items():
+        m = re.fullmatch(r"\[(\d+)\]", k)
+        if m:
+            items.append((int(m.group(1)), v))
+    return [v for _, v in sorted(items)]
+
+
+# ----------------------------------------------------------------------------------------------
+# URDF -> reduced kinematic tree
+# ----------------------------------------------------------------------------------------------
+
+
+def _rpy_to_R(rpy):
+    r, p, y = rpy
+    cr, sr, cp, sp, cy, sy = math.cos(r), math.sin(r), math.cos(p), math.sin(p), math.cos(y), math.sin(y)
+    Rx = np.array([[1, 0, 0], [0, cr, -sr], [0, sr, cr]])
+    Ry = np.array([[cp, 0, sp], [0, 1, 0], [-sp, 0, cp]])
+    Rz = np.array([[cy, -sy, 0], [sy, cy, 0], [0, 0, 1]])
+    return Rz @ Ry @ Rx
+
+
+def _vec(s, n=3):
+    v = [float(x) for x in s.split()]
+    assert len(v) == n
+    return np.array(v)
+
+
+class _Inertia:
+    """mass, com (in the frame it is expressed in), rotational inertia about the com (same axes)."""
+
+    def __init__(self, m=0.0, c=None, I=None):
+        self.m = m
+        self.c = np.zeros(3) if c is None else np.array(c, float)
+        self.I = np.zeros((3, 3)) if I is None else np.array(I, float)
+
+    def transformed(self, R, p):
+        """express in a parent frame: x_parent = R x + p"""
+        return _Inertia(self.m, R @ self.c + p, R @ self.I @ R.T)
+
+    def __add__(self, o):
+        m = self.m + o.m
+        if m == 0.0:
+            return _Inertia()
+        c = (self.m * self.c + o.m * o.c) / m
+
+        def shift(I, mm, d):  # parallel axis: about point c from com at c+d
+            return I + mm * (d @ d * np.eye(3) - np.outer(d, d))
+
+        I = shift(self.I, self.m, self.c - c) + shift(o.I, o.m, o.c - c)
+        return _Inertia(m, c, I)
+
+
+def parse_urdf(urdf_path: str | Path):
+    root = ET.parse(str(urdf_path)).getroot()
+    links = {}
+    for ln in root.findall("link"):
+        ine = ln.find("inertial")
+        if ine is None:
+            links[ln.get("name")] = _Inertia()
+            continue
+        org = ine.find("origin")
+        xyz = _vec(org.get("xyz", "0 0 0")) if org is not None else np.zeros(3)
+        rpy = _vec(org.get("rpy", "0 0 0")) if org is not None else np.zeros(3)
+        m = float(ine.find("mass").get("value"))
+        it = ine.find("inertia")
+        I = np.array(
+            [
+                [float(it.get("ixx")), float(it.get("ixy")), float(it.get("ixz"))],
+                [float(it.get("ixy")), float(it.get("iyy")), float(it.get("iyz"))],
+                [float(it.get("ixz")), float(it.get("iyz")), float(it.get("izz"))],
+            ]
+        )
+        R = _rpy_to_R(rpy)
+        links[ln.get("name")] = _Inertia(m, xyz, R @ I @ R.T)
+    joints = {}
+    for jn in root.findall("joint"):
+        org = jn.find("origin")
+        xyz = _vec(org.get("xyz", "0 0 0")) if org is not None else np.zeros(3)
+        rpy = _vec(org.get("rpy", "0 0 0")) if org is not None else np.zeros(3)
+        ax = jn.find("axis")
+        lim = jn.find("limit")
+        joints[jn.get("name")] = dict(
+            type=jn.get("type"),
+            parent=jn.find("parent").get("link"),
+            child=jn.find("child").get("link"),
+            R=_rpy_to_R(rpy),
+            p=xyz,
+            axis=_vec(ax.get("xyz")) if ax is not None else np.array([1.0, 0, 0]),
+            lower=float(lim.get("lower")) if lim is not None and lim.get("lower") else -math.inf,
+            upper=float(lim.get("upper")) if lim is not None and lim.get("upper") else math.inf,
+        )
+    return links, joints
+
+
+def reduce_tree(links, joints, fixed_joint_names):
+    """Weld fixed joints; return bodies in Pinocchio joint order.
+
+    bodies[0] is the floating base body; bodies[i>0] belongs to the i-th MPC joint.
+    """
+    child_links = {j["child"] for j in joints.values()}
+    roots = [l for l in links if l not in child_links]
+    assert len(roots) == 1, roots
+    root = roots[0]
+    by_parent: dict[str, list[str]] = {}
+    for name in sorted(joints):  # urdfdom keeps joints in a std::map -> alphabetical child order
+        by_parent.setdefault(joints[name]["parent"], []).append(name)
+
+    bodies = [dict(name="base", joint=None, parent=-1, R=np.eye(3), p=np.zeros(3), axis=None, inertia=_Inertia(), lower=0, upper=0)]
+    link_body = {}  # link -> (body index, R, p of link frame in that body's joint frame)
+
+    def visit(link, body_idx, R, p):
+        link_body[link] = (body_idx, R, p)
+        bodies[body_idx]["inertia"] = bodies[body_idx]["inertia"] + links[link].transformed(R, p)
+        for jname in by_parent.get(link, []):
+            j = joints[jname]
+            Rj, pj = R @ j["R"], R @ j["p"] + p
+            movable = j["type"] in ("revolute", "continuous") and jname not in fixed_joint_names
+            if j["type"] in ("floating", "prismatic", "planar") and jname not in fixed_joint_names:
+                raise ValueError(f"unsupported joint type {j['type']} for {jname}")
+            if movable:
+                bodies.append(
+                    dict(name=j["child"], joint=jname, parent=body_idx, R=Rj, p=pj, axis=j["axis"] / np.linalg.norm(j["axis"]),
+                         inertia=_Inertia(), lower=j["lower"], upper=j["upper"])
+                )
+                visit(j["child"], len(bodies) - 1, np.eye(3), np.zeros(3))
+            else:
+                visit(j["child"], body_idx, Rj, pj)
+
+    visit(root, 0, np.eye(3), np.zeros(3))
+    return bodies, link_body
+
+
+# ----------------------------------------------------------------------------------------------
+# Whole-body model description
+# ----------------------------------------------------------------------------------------------
+
+G1_REL = dict(
+    urdf="robot_models/unitree_g1/g1_description/urdf/g1_29dof.urdf",
+    task="robot_models/unitree_g1/g1_wb_mpc/config/mpc/task.info",
+    reference="robot_models/unitree_g1/g1_wb_mpc/config/command/reference.info",
+    gait="humanoid_nmpc/humanoid_common_mpc/config/command/gait.info",
+)
+
+
+def build_wb_model(urdf_path, task_path, reference_path=None, gait_path=None) -> dict:
+    """Flat whole-body (WB) model description. All matrices row-major nested lists."""
+    task = parse_info(task_path)
+    links, joints = parse_urdf(urdf_path)
+    fixed = set(info_list(task, "model_settings.fixedJointNames"))
+    bodies, _ = reduce_tree(links, joints, fixed)
+    nj = len(bodies) - 1
+    joint_names = [b["joint"] for b in bodies[1:]]
+    jidx = {n: i for i, n in enumerate(joint_names)}
+
+    contact_names = info_list(task, "model_settings.contactNames6DoF")
+    contact_parents = info_list(task, "model_settings.contactParentJointNames")
+    ct = np.array([info_float(task, f"contacts.contact_frame_translation.{a}") for a in "xyz"])
+    rect = {k: info_float(task, f"contacts.contact_rectangle.{k}") for k in ("x_max", "x_min", "y_max", "y_min")}
+
+    # frames: (name, body index, translation in the body's joint frame); rotation is identity for all of them
+    frames = []
+    for cname, pj in zip(contact_names, contact_parents):
+        b = jidx[pj] + 1
+        frames.append((cname, b, ct))
+        frames.append((cname + "_collision_p_1", b, ct + np.array([rect["x_max"] * 0.6, 0, 0])))
+        frames.append((cname + "_collision_p_2", b, ct + np.array([rect["x_min"] * 0.6, 0, 0])))
+    cc = "collision_constraint."
+    for key in ("foot.leftAnkleFrame", "foot.rightAnkleFrame", "knee.leftKneeFrame", "knee.rightKneeFrame"):
+        jn = info_get(task, cc + key)
+        frames.append((jn, jidx[jn] + 1, np.zeros(3)))
+
+    nx, nu = 2 * (6 + nj), 12 + nj
+    Q = info_matrix(task, "Q", nx, nx)
+    R = info_matrix(task, "R", nu, nu)
+    Qf = info_matrix(task, "Q_final", nx, nx) * info_float(task, "terminalCostScaling")
+    x_init = info_matrix(task, "initialState", nx, 1)[:, 0]
+
+    fc = "model_settings.foot_constraint."
+    w = "task_space_foot_cost_weights."
+    # EndEffectorDynamicsWeights::getWeights (humanoid_wb_mpc/src/cost/EndEffectorDynamicsCostHelpers.cpp:97-110)
+    # overwrites the velocity weights with the acceleration entries and leaves the acceleration weights at
+    # their defaults 0.01 (EndEffectorDynamicsCostHelpers.h:45-50).  Reproduced on purpose.
+    foot_w = np.concatenate(
+        [
+            [info_float(task, w + f"pos_{a}") for a in "xyz"],
+            [info_float(task, w + f"orientation_{a}") for a in "xyz"],
+            [info_float(task, w + f"lin_acceleration_{a}") for a in "xyz"],
+            [info_float(task, w + f"ang_acceleration_{a}") for a in "xyz"],
+            [0.01] * 3,
+            [0.01] * 3,
+        ]
+    )
+
+    model = dict(
+        name="g1_wb",
+        nj=nj,
+        nx=nx,
+        nu=nu,
+        gravity=9.81,
+        joint_names=joint_names,
+        parent=[b["parent"] for b in bodies],
+        joint_R=[b["R"].tolist() for b in bodies],
+        joint_p=[b["p"].tolist() for b in bodies],
+        joint_axis=[[0, 0, 0]] + [b["axis"].tolist() for b in bodies[1:]],
+        mass=[b["inertia"].m for b in bodies],
+        com=[b["inertia"].c.tolist() for b in bodies],
+        inertia=[b["inertia"].I.tolist() for b in bodies],
+        q_lower=[b["lower"] for b in bodies[1:]],
+        q_upper=[b["upper"] for b in bodies[1:]],
+        frame_names=[f[0] for f in frames],
+        frame_body=[f[1] for f in frames],
+        frame_p=[np.asarray(f[2]).tolist() for f in frames],
+        contact_frames=[0, 3],  # indices into frames of foot_l_contact / foot_r_contact
+        contact_rect=[rect["x_min"], rect["x_max"], rect["y_min"], rect["y_max"]],
+        Q_diag=np.diag(Q).tolist(),
+        R_diag=np.diag(R).tolist(),
+        Qf_diag=np.diag(Qf).tolist(),
+        x_init=x_init.tolist(),
+        foot_gains=dict(
+            pos_z=info_float(task, fc + "positionErrorGain_z"),
+            ori=info_float(task, fc + "orientationErrorGain"),
+            linvel_z=info_float(task, fc + "linearVelocityErrorGain_z"),
+            linvel_xy=info_float(task, fc + "linearVelocityErrorGain_xy"),
+            angvel=info_float(task, fc + "angularVelocityErrorGain"),
+            linacc_z=info_float(task, fc + "linearAccelerationErrorGain_z"),
+            linacc_xy=info_float(task, fc + "linearAccelerationErrorGain_xy"),
+            angacc=info_float(task, fc + "angularAccelerationErrorGain"),
+        ),
+        foot_cost_weights=foot_w.tolist(),
+        friction=dict(
+            mu_fric=info_float(task, "contacts.frictionForceConeSoftConstraint.frictionCoefficient"),
+            mu=info_float(task, "contacts.frictionForceConeSoftConstraint.mu"),
+            delta=info_float(task, "contacts.frictionForceConeSoftConstraint.delta"),
+            regularization=25.0,  # FrictionForceConeConstraint.h:66-69 defaults
+            hessian_shift=1e-6,
+        ),
+        moment_xy=dict(
+            mu=info_float(task, "contacts.contactMomentXYSoftConstraint.mu"),
+            delta=info_float(task, "contacts.contactMomentXYSoftConstraint.delta"),
+        ),
+        joint_limits=dict(mu=info_float(task, "jointLimits.mu"), delta=info_float(task, "jointLimits.delta")),
+        collision=dict(
+            mu=info_float(task, cc + "mu"),
+            delta=info_float(task, cc + "delta"),
+            r_foot=info_float(task, cc + "foot.footCollisionSphereRadius"),
+            r_knee=info_float(task, cc + "knee.kneeCollisionSphereRadius"),
+        ),
+        arm_swing_joints=[
+            jidx[info_get(task, "model_settings.armJointNames." + k)]
+            for k in ("left_shoulder_y", "right_shoulder_y", "left_elbow_y", "right_elbow_y")
+        ],
+        swing=dict(
+            liftOffVelocity=info_float(task, "swing_trajectory_config.liftOffVelocity"),
+            touchDownVelocity=info_float(task, "swing_trajectory_config.touchDownVelocity"),
+            swingHeight=info_float(task, "swing_trajectory_config.swingHeight"),
+            touchDownHeightOffset=info_float(task, "swing_trajectory_config.touchDownHeightOffset"),
+            swingTimeScale=info_float(task, "swing_trajectory_config.swingTimeScale"),
+            ipfLiftOffVelocity=info_float(task, "swing_trajectory_config.impactProximityFactorLiftOffVelocity"),
+            ipfTouchDownVelocity=info_float(task, "swing_trajectory_config.impactProximityFactorTouchDownVelocity"),
+            ipfMidPointValue=info_float(task, "swing_trajectory_config.impactProximityFactorMidPointValue"),
+        ),
+        sqp=dict(
+            dt=info_float(task, "multiple_shooting.dt"),
+            sqpIteration=int(info_float(task, "multiple_shooting.sqpIteration")),
+            deltaTol=info_float(task, "multiple_shooting.deltaTol"),
+            g_max=info_float(task, "multiple_shooting.g_max"),
+            g_min=info_float(task, "multiple_shooting.g_min"),
+            timeHorizon=info_float(task, "mpc.timeHorizon"),
+        ),
+    )
+    if reference_path is not None:
+        ref = parse_info(reference_path)
+        model["reference"] = dict(
+            defaultBaseHeight=info_float(ref, "defaultBaseHeight"),
+            defaultJointState=info_matrix(ref, "defaultJointState", nj, 1)[:, 0].tolist(),
+            targetDisplacementVelocity=info_float(ref, "targetDisplacementVelocity"),
+            targetRotationVelocity=info_float(ref, "targetRotationVelocity"),
+        )
+    if gait_path is not None:
+        g = parse_info(gait_path)
+        gaits = {}
+        for name in info_list(g, "list"):
+            if name in g:
+                gaits[name] = dict(
+                    modeSequence=info_list(g, name + ".modeSequence"),
+                    switchingTimes=[float(v) for v in info_list(g, name + ".switchingTimes")],
+                )
+        model["gaits"] = gaits
+    return model
+
+
+def build_g1_wb_from_reference(reference_root="/root/reference") -> dict:
+    r = Path(reference_root)
+    return build_wb_model(r / G1_REL["urdf"], r / G1_REL["task"], r / G1_REL["reference"], r / G1_REL["gait"])
+
+
+DATA_DIR = Path(__file__).resolve().parent / "data"
+
+
+def load_packaged_model(name="g1_wb") -> dict:
+    """Load the committed flat description (generated by tools/make_model_data.py)."""
+    return json.loads((DATA_DIR / f"{name}_model.json").read_text())
+
+
+if __name__ == "__main__":
+    import sys
+
+    m = build_g1_wb_from_reference(sys.argv[1] if len(sys.argv) > 1 else "/root/reference")
+    print(json.dumps({k: m[k] for k in ("nj", "nx", "nu", "joint_names", "parent")}, indent=1))
+    print("total mass", sum(m["mass"]))
