@@ -1,0 +1,168 @@
+/*
+ * b200sqp -- C ABI of the B200-native batched multiple-shooting SQP solver.
+ *
+ * This is the drop-in boundary for ONE hot path of manumerous/wb_humanoid_mpc: the SQP iteration
+ * ocs2::SqpSolver::runImpl (lib/ocs2_ros2/ocs2_sqp/ocs2_sqp/src/SqpSolver.cpp:193-284) for the Unitree G1
+ * whole-body optimal-control problem, batched over independent MPC instances.  Plain pointers and sizes only;
+ * no C++/torch types cross this boundary.  Every entry point names the reference interface it replaces.
+ *
+ * Conventions
+ *   - return 0 on success, a negative B200SQP_E* code on failure; nothing throws across the ABI;
+ *     b200sqp_last_error() returns a human-readable reason for the last failure on this thread.
+ *   - all matrices are column-major fp64 (Eigen's default, as in ocs2 VectorFunctionLinearApproximation /
+ *     ScalarFunctionQuadraticApproximation, ocs2_core/include/ocs2_core/Types.h:145-157,234-240).
+ *   - the caller owns every host buffer; a handle owns its device memory; one handle per GPU;
+ *     handles are thread-compatible (external synchronisation), like ocs2::SqpSolver (MPC_BASE.h:58).
+ *   - there is no CPU fallback: every entry point that computes fails with B200SQP_ENODEV without a CUDA device.
+ */
+#ifndef B200SQP_H
+#define B200SQP_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define B200SQP_OK 0
+#define B200SQP_EINVAL -1   /* bad argument / size mismatch (ocs2 throws std::runtime_error on size checks) */
+#define B200SQP_ENODEV -2   /* no CUDA device / CUDA runtime error */
+#define B200SQP_ENOMEM -3
+#define B200SQP_EQP -4      /* QP failed for at least one instance: "[SqpSolver] Failed to solve QP" (SqpSolver.cpp:306-308) */
+#define B200SQP_ESTATE -5   /* call order violated (e.g. solve before upload) */
+
+const char* b200sqp_last_error(void);
+/* library / build information, e.g. "b200sqp 0.1 sm_100a" */
+const char* b200sqp_version(void);
+
+/* ------------------------------------------------------------------------------------------------------------------
+ * (1) Batched QP sub-problem: replaces ocs2::HpipmInterface
+ *     (lib/ocs2_ros2/ocs2_sqp/hpipm_catkin/include/hpipm_catkin/HpipmInterface.h; src/HpipmInterface.cpp:92-455).
+ *
+ *     minimise  sum_k 1/2 [dx;du]'[Q S';S R][dx;du] + q'dx + r'du   s.t.  dx_{k+1} = A dx + B du + b,  dx_0 given
+ *
+ *     Stage arrays are padded to nu_max inputs; stage k of instance i uses the leading nu[i*N+k] columns/rows
+ *     (nu = 0 is the event-node shape of HpipmInterface test "noInputs", testHpipmInterface.cpp:208-256).
+ *       A [B][N][nx*nx]        B [B][N][nx*nu_max]      b [B][N][nx]
+ *       Q [B][N+1][nx*nx]      S [B][N][nu_max*nx] (leading dimension nu_max, = dfdux)
+ *       R [B][N][nu_max*nu_max]  q [B][N+1][nx]         r [B][N][nu_max]
+ * ------------------------------------------------------------------------------------------------------------------ */
+typedef struct b200sqp_qp_t* b200sqp_qp;
+
+/* HpipmInterface::HpipmInterface(OcpSize) / resize(): allocate device storage for `batch` problems of N stages. */
+int b200sqp_qp_create(int device, int batch, int N, int nx, int nu_max, b200sqp_qp* out);
+void b200sqp_qp_destroy(b200sqp_qp qp);
+
+/* HpipmInterface::solve(x0, dynamics, cost, nullptr, ...): host -> device copy of the LQ data. nu may be NULL (all nu_max). */
+int b200sqp_qp_upload(b200sqp_qp qp, const double* A, const double* B, const double* b, const double* Q, const double* S,
+                      const double* R, const double* q, const double* r, const int32_t* nu, const double* dx0);
+
+/* d_ocp_qp_ipm_solve for the unconstrained QP: one backward Riccati factorisation + forward substitution, all instances.
+ * reg_prim is added to the Hessian diagonals (hpipm_catkin HpipmInterfaceSettings.h:45-56, default 1e-12).
+ * Asynchronous on `stream` (a cudaStream_t, may be NULL). keep_P != 0 stores the cost-to-go for b200sqp_qp_download. */
+int b200sqp_qp_solve(b200sqp_qp qp, double reg_prim, int keep_P, void* stream);
+
+/* getStateSolution/getInputSolution, getRiccatiFeedback, getRiccatiFeedforward, getRiccatiCostToGo.
+ *   dx [B][N+1][nx], du [B][N][nu_max], K [B][N][nu_max*nx] (ld nu_max), k [B][N][nu_max], P [B][N+1][nx*nx], p [B][N+1][nx],
+ *   status [B] (0 ok, 1 = Cholesky failed / NaN -> hpipm_status != SUCCESS).  Any pointer may be NULL.  Synchronises. */
+int b200sqp_qp_download(b200sqp_qp qp, double* dx, double* du, double* K, double* k, double* P, double* p, int32_t* status);
+
+/* device-time of the last b200sqp_qp_solve in milliseconds (CUDA events on the launching stream) */
+int b200sqp_qp_last_ms(b200sqp_qp qp, float* ms);
+
+/* ------------------------------------------------------------------------------------------------------------------
+ * (2) Whole-body SQP solver: replaces ocs2::SqpSolver for the humanoid whole-body OCP
+ *     (SqpSolver.h:60-103; OCP wiring humanoid_nmpc/humanoid_wb_mpc/src/WBMpcInterface.cpp:131-199).
+ * ------------------------------------------------------------------------------------------------------------------ */
+#define B200SQP_MAX_BODIES 32
+#define B200SQP_MAX_FRAMES 16
+
+/* Model constants the reference keeps inside PinocchioInterface + ModelSettings + the cost/constraint objects;
+ * produced from URDF + task.info by wb_humanoid_mpc_b200/model_loader.py (or any caller that fills the arrays). */
+typedef struct b200sqp_model_desc {
+  int32_t nj;                                  /* actuated joints (23 for G1); nx = 2*(6+nj), nu = 12+nj */
+  int32_t parent[B200SQP_MAX_BODIES];          /* parent body of body i (body 0 = floating base, parent -1) */
+  double joint_R[B200SQP_MAX_BODIES][9];       /* row-major rotation of the joint frame in the parent body frame */
+  double joint_p[B200SQP_MAX_BODIES][3];
+  double joint_axis[B200SQP_MAX_BODIES][3];    /* revolute axis in the joint frame */
+  double mass[B200SQP_MAX_BODIES];
+  double com[B200SQP_MAX_BODIES][3];
+  double inertia[B200SQP_MAX_BODIES][9];       /* rotational inertia about the com, body axes, row-major */
+  double q_lower[B200SQP_MAX_BODIES], q_upper[B200SQP_MAX_BODIES]; /* index = joint (0-based) */
+  int32_t n_frames;                            /* operational frames: [0..2] left foot contact, p1, p2; [3..5] right; 6,7 ankles; 8,9 knees */
+  int32_t frame_body[B200SQP_MAX_FRAMES];
+  double frame_p[B200SQP_MAX_FRAMES][3];
+  double gravity;
+  double contact_rect[4];                      /* x_min, x_max, y_min, y_max (task.info contacts.contact_rectangle) */
+  double Q_diag[64], R_diag[48], Qf_diag[64];  /* StateInputQuadraticCost / terminal cost weights (task.info Q, R, Q_final*scaling) */
+  double foot_gain_pos_z, foot_gain_ori, foot_gain_linvel_z, foot_gain_linvel_xy, foot_gain_angvel, foot_gain_linacc_z,
+      foot_gain_linacc_xy, foot_gain_angacc;   /* model_settings.foot_constraint */
+  double foot_cost_w[18];                      /* EndEffectorDynamicsWeights::toVector() as actually loaded */
+  double fric_coeff, fric_mu, fric_delta, fric_reg, fric_hess_shift; /* FrictionForceConeConstraint + RelaxedBarrierPenalty */
+  double momxy_mu, momxy_delta;                /* ContactMomentXY relaxed barrier */
+  double jlim_mu, jlim_delta;                  /* JointLimitsSoftConstraint piecewise-polynomial barrier */
+  double coll_mu, coll_delta, coll_r_foot, coll_r_knee; /* FootCollisionConstraint */
+  int32_t arm_swing_joint[4];                  /* l shoulder, r shoulder, l elbow, r elbow joint indices */
+} b200sqp_model_desc;
+
+/* sqp::Settings fields the hot path reads (ocs2_sqp/include/ocs2_sqp/SqpSettings.h:40-87) */
+typedef struct b200sqp_settings {
+  int32_t sqp_iteration;       /* sqpIteration */
+  double delta_tol, cost_tol;  /* deltaTol, costTol */
+  double alpha_decay, alpha_min, gamma_c, g_max, g_min, armijo_factor;
+  double reg_prim;             /* HPIPM reg_prim */
+  int32_t use_feedback_policy; /* useFeedbackPolicy: compute remapped K (toPrimalSolution, SqpSolver.cpp:331-344) */
+  int32_t global_step;         /* 0: per-instance line search (reference semantics); 1: one step size for the whole (multi-GPU) batch */
+} b200sqp_settings;
+void b200sqp_default_settings(b200sqp_settings* s);
+
+typedef struct b200sqp_solver_t* b200sqp_handle;
+
+/* SqpSolver::SqpSolver(settings, ocp, initializer) */
+int b200sqp_create(const b200sqp_model_desc* model, const b200sqp_settings* settings, int device, b200sqp_handle* out);
+void b200sqp_destroy(b200sqp_handle h);
+
+/* batch of `batch` instances with n_nodes shooting nodes each (N = n_nodes-1 intervals incl. event nodes) */
+int b200sqp_set_batch(b200sqp_handle h, int batch, int n_nodes);
+
+/* Per-instance inputs of one runImpl call, i.e. what SolverBase::preRun + initializeStateInputTrajectories produce on the host:
+ *   x0 [B][nx]; x_init [B][n_nodes][nx], u_init [B][n_nodes-1][nu] (warm start / WeightCompInitializer);
+ *   t_nodes [B][n_nodes]; node_event [B][n_nodes] (0 none, 1 PreEvent, 2 PostEvent: AnnotatedTime::Event);
+ *   contact_flags [B][n_nodes][2]; swing_ref [B][n_nodes][2][3] (swing-z position, velocity, acceleration);
+ *   impact_factor [B][n_nodes][2]; arm_phase [B][n_nodes] (sin(2 pi (phase-0.15)), SwitchedModelReferenceManager.cpp:110-135);
+ *   x_ref [B][n_nodes][nx] (TargetTrajectories::getDesiredState at node times). */
+int b200sqp_upload_instances(b200sqp_handle h, const double* x0, const double* x_init, const double* u_init, const double* t_nodes,
+                             const uint8_t* node_event, const uint8_t* contact_flags, const double* swing_ref,
+                             const double* impact_factor, const double* arm_phase, const double* x_ref);
+
+/* SqpSolver::runImpl for every instance; asynchronous on `stream`. */
+int b200sqp_solve(b200sqp_handle h, void* stream);
+
+/* per-instance iteration record: mirrors sqp::LogEntry / PerformanceIndex (SqpLogging.h, PerformanceIndex.h) */
+typedef struct b200sqp_iter_log {
+  double base_merit, base_cost, base_dyn_sse, base_eq_sse;
+  double merit, cost, dyn_sse, eq_sse;
+  double step_size, step_type, dx_norm, du_norm, armijo, convergence;
+  double pad[2];
+} b200sqp_iter_log;
+
+/* primalSolution / getRiccatiFeedback / getIterationsLog:
+ *   x [B][n_nodes][nx], u [B][n_nodes-1][nu], K [B][n_nodes-1][nu*nx] (remapped gains, may be NULL),
+ *   log [B][sqp_iteration], n_iter [B], status [B]. Synchronises. */
+int b200sqp_download(b200sqp_handle h, double* x, double* u, double* K, b200sqp_iter_log* log, int32_t* n_iter, int32_t* status);
+
+/* Stage blocks of the last LQ approximation, for block-level parity tests:
+ *   which = 0 raw (before projection): A [nx*nx] B [nx*nu] b [nx] Q S(nu x nx) R q r C(nc_max x nx) D(nc_max x nu) e nc
+ *   see b200sqp_stage_layout for offsets. */
+int b200sqp_download_stage_blocks(b200sqp_handle h, int which, double* out, int64_t out_doubles);
+int b200sqp_stage_doubles(b200sqp_handle h, int which, int64_t* per_node);
+
+/* SqpSolver::getBenchmarks(): device ms of {LQ approximation, solve QP, line search, compute controller} of the last solve */
+int b200sqp_get_stage_times(b200sqp_handle h, float ms[4]);
+/* number of kernel launches issued by the last b200sqp_solve */
+int b200sqp_get_launch_count(b200sqp_handle h, int64_t* launches);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* B200SQP_H */
