@@ -1,5 +1,6 @@
 // ORACLE (test infrastructure only) -- C entry points for the Python tests (ctypes) and bench.py's CPU-baseline leg.
 // Product code never links this library.
+#include <atomic>
 #include <cstring>
 #include <memory>
 

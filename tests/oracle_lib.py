@@ -149,3 +149,152 @@ def sqp_test_problem(kind, nx, nu, x0, t0, tf, dt, sqp_iteration, A=None, B=None
 
 LOG_FIELDS = ["base_merit", "base_cost", "base_dynSSE", "base_eqSSE", "merit", "cost", "dynSSE", "eqSSE", "stepSize", "stepType", "dx_norm",
               "du_norm", "armijo", "convergence"]
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# whole-body restatement
+# ------------------------------------------------------------------------------------------------------------------
+u8p = C.POINTER(C.c_uint8)
+
+
+class WbOracle:
+    """One whole-body OCP instance on the CPU oracle."""
+
+    def __init__(self, model: dict):
+        from wb_humanoid_mpc_b200 import abi
+
+        self.model = model
+        self.desc = abi.model_desc(model)
+        self.nx, self.nu, self.nj = model["nx"], model["nu"], model["nj"]
+        L = lib()
+        L.orc_wb_create.restype = C.c_void_p
+        L.orc_wb_total_mass.restype = C.c_double
+        L.orc_wb_cost.restype = C.c_double
+        L.orc_wb_cost_quad.restype = C.c_double
+        self.h = C.c_void_p(L.orc_wb_create(C.byref(self.desc)))
+        self.L = L
+        self.n_nodes = 0
+
+    def __del__(self):
+        try:
+            self.L.orc_wb_destroy(self.h)
+        except Exception:
+            pass
+
+    def set_nodes(self, contact, swing, impact, arm_phase, xref):
+        self.n_nodes = len(arm_phase)
+        self._nodes = [np.ascontiguousarray(contact, dtype=np.uint8), F(swing), F(impact), F(arm_phase), F(xref)]
+        c, s, i, a, x = self._nodes
+        self.L.orc_wb_set_nodes(self.h, C.c_int(self.n_nodes), c.ctypes.data_as(u8p), _p(s), _p(i), _p(a), _p(x))
+
+    def total_mass(self):
+        return self.L.orc_wb_total_mass(self.h)
+
+    def flow_map(self, x, u):
+        out = np.zeros(self.nx)
+        self.L.orc_wb_flow_map(self.h, _p(F(x)), _p(F(u)), _p(out))
+        return out
+
+    def base_accel_literal(self, x, u):
+        out = np.zeros(6)
+        self.L.orc_wb_base_accel_literal(self.h, _p(F(x)), _p(F(u)), _p(out))
+        return out
+
+    def crba_nle(self, x):
+        nv = 6 + self.nj
+        M, nle = np.zeros((nv, nv)), np.zeros(nv)
+        self.L.orc_wb_crba_nle(self.h, _p(F(x)), _p(M), _p(nle))
+        return M, nle
+
+    def rnea(self, q, v, a):
+        tau = np.zeros(6 + self.nj)
+        self.L.orc_wb_rnea(self.h, _p(F(q)), _p(F(v)), _p(F(a)), _p(tau))
+        return tau
+
+    def foot_state(self, x, u):
+        out = np.zeros((2, 27))
+        fp = np.zeros((self.desc.n_frames, 3))
+        self.L.orc_wb_foot_state(self.h, _p(F(x)), _p(F(u)), _p(out), _p(fp))
+        feet = []
+        for c in range(2):
+            o = out[c]
+            feet.append(dict(pos=o[0:3], oriErr=o[3:6], vlin=o[6:9], vang=o[9:12], alin=o[12:15], aang=o[15:18], R=o[18:27].reshape(3, 3)))
+        return feet, fp
+
+    def flow_map_lin(self, x, u):
+        f, A, B = np.zeros(self.nx), np.zeros((self.nx, self.nx)), np.zeros((self.nu, self.nx))
+        self.L.orc_wb_flow_map_lin(self.h, _p(F(x)), _p(F(u)), _p(f), _p(A), _p(B))
+        return f, A.T.copy(), B.T.copy()
+
+    def cost(self, k, x, u):
+        return self.L.orc_wb_cost(self.h, C.c_int(k), _p(F(x)), _p(F(u)))
+
+    def cost_quad(self, k, x, u):
+        nx, nu = self.nx, self.nu
+        Q, S, R, q, r = np.zeros((nx, nx)), np.zeros((nx, nu)), np.zeros((nu, nu)), np.zeros(nx), np.zeros(nu)
+        f = self.L.orc_wb_cost_quad(self.h, C.c_int(k), _p(F(x)), _p(F(u)), _p(Q), _p(S), _p(R), _p(q), _p(r))
+        return dict(f=f, Q=Q.T.copy(), S=S.T.copy(), R=R.T.copy(), q=q, r=r)
+
+    def eq_constraint_lin(self, k, x, u):
+        nx, nu = self.nx, self.nu
+        g, Cm, Dm = np.zeros(14), np.zeros((nx, 14)), np.zeros((nu, 14))
+        nc = self.L.orc_wb_eq_constraint_lin(self.h, C.c_int(k), _p(F(x)), _p(F(u)), _p(g), _p(Cm), _p(Dm), C.c_int(14))
+        return g[:nc].copy(), Cm.T[:nc].copy(), Dm.T[:nc].copy()
+
+    def eq_constraint(self, k, x, u):
+        g = np.zeros(14)
+        nc = self.L.orc_wb_eq_constraint(self.h, C.c_int(k), _p(F(x)), _p(F(u)), _p(g))
+        return g[:nc].copy()
+
+    def sqp(self, t_nodes, events, x0, x, u, settings, keep_raw=False):
+        n = len(t_nodes)
+        xs, us = F(x).copy(), F(u).copy()
+        log = np.zeros((64, 16))
+        nit = C.c_int(0)
+        ev = np.ascontiguousarray(events, dtype=np.uint8)
+        rc = self.L.orc_wb_sqp(self.h, C.c_int(n), _p(F(t_nodes)), ev.ctypes.data_as(u8p), _p(F(x0)), _p(xs), _p(us), C.byref(settings),
+                               C.c_int(int(keep_raw)), _p(log), C.c_int(64), C.byref(nit))
+        if rc != 0:
+            raise RuntimeError("oracle SQP failed")
+        dx, du = np.zeros((n, self.nx)), np.zeros((n - 1, self.nu))
+        K = np.zeros((n - 1, self.nx, self.nu))
+        nut = np.zeros(n - 1, dtype=np.int32)
+        self.L.orc_wb_last_qp(self.h, _p(dx), _p(du), _p(K), _pi(nut))
+        return dict(x=xs, u=us, log=log[: nit.value], dx=dx, du=du, K=np.swapaxes(K, 1, 2).copy(), nut=nut)
+
+    def raw_per_node(self):
+        nx, nu = self.nx, self.nu
+        return 2 * nx * nx + 2 * nx * nu + nu * nu + 2 * nx + nu + 1 + 14 * (nx + nu + 1) + 1
+
+    def last_raw_blocks(self, n_nodes):
+        per = self.raw_per_node()
+        out = np.zeros((n_nodes - 1, per))
+        rc = self.L.orc_wb_last_raw_blocks(self.h, _p(out), C.c_longlong(per))
+        assert rc == 0, rc
+        return [unpack_raw_blocks(out[i], self.nx, self.nu) for i in range(n_nodes - 1)]
+
+
+def unpack_raw_blocks(p, nx, nu):
+    """Layout shared by the oracle (orc_wb_last_raw_blocks) and the CUDA path (b200sqp_download_stage_blocks which=0)."""
+    o = 0
+
+    def take(n):
+        nonlocal o
+        v = p[o:o + n]
+        o += n
+        return v
+
+    A = take(nx * nx).reshape(nx, nx).T
+    B = take(nx * nu).reshape(nu, nx).T
+    b = take(nx)
+    Q = take(nx * nx).reshape(nx, nx).T
+    S = take(nu * nx).reshape(nx, nu).T
+    R = take(nu * nu).reshape(nu, nu).T
+    q = take(nx)
+    r = take(nu)
+    c = take(1)[0]
+    Cm = take(14 * nx).reshape(nx, 14).T
+    Dm = take(14 * nu).reshape(nu, 14).T
+    e = take(14)
+    nc = int(round(take(1)[0]))
+    return dict(A=A, B=B, b=b, Q=Q, S=S, R=R, q=q, r=r, c=c, C=Cm[:nc], D=Dm[:nc], e=e[:nc], nc=nc)

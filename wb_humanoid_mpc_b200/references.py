@@ -1,0 +1,326 @@
+"""Host-side instance builder: what SolverBase::preRun + runImpl's bookkeeping hand to the LQ stage, as flat per-node arrays.
+
+Restates (paths relative to /root/reference/):
+  GaitSchedule                 humanoid_nmpc/humanoid_common_mpc/src/gait/GaitSchedule.cpp:46-139
+  ModeSchedule::modeAtTime     lib/ocs2_ros2/ocs2_core/src/reference/ModeSchedule.cpp:48-51
+  SwitchedModelReferenceManager::modifyReferences / getPhaseVariable / getContactFlags
+                               humanoid_nmpc/humanoid_common_mpc/src/reference_manager/SwitchedModelReferenceManager.cpp:54-154
+  SwingTrajectoryPlanner / SplineCpg / CubicSpline
+                               humanoid_nmpc/humanoid_common_mpc/src/swing_foot_planner/SwingTrajectoryPlanner.cpp:50-271,
+                               SplineCpg.cpp:38-63, CubicSpline.cpp:38-85
+  timeDiscretizationWithEvents lib/ocs2_ros2/ocs2_oc/src/oc_data/TimeDiscretization.cpp:40-114
+  commandedVelocityToTargetTrajectories
+                               humanoid_nmpc/humanoid_wb_mpc/src/command/WBMpcTargetTrajectoriesCalculator.cpp:82-136
+  WeightCompInitializer / initializeStateInputTrajectories (cold start)
+                               humanoid_nmpc/humanoid_common_mpc/src/initialization/WeightCompInitializer.cpp:66-70,
+                               lib/ocs2_ros2/ocs2_oc/src/multiple_shooting/Initialization.cpp:35-79
+These run on the host for every MPC instance (SURVEY.md §8(f)-1 lists moving them to the device as the next step).
+"""
+from __future__ import annotations
+
+import bisect
+import math
+from dataclasses import dataclass, field
+
+import numpy as np
+
+FLY, RF, LF, STANCE = 0, 1, 2, 3
+MODE_NAMES = {"FLY": FLY, "RF": RF, "LF": LF, "STANCE": STANCE}
+LIMIT_EPS, WEAK_EPS = 1e-6, 1e-9
+EV_NONE, EV_PRE, EV_POST = 0, 1, 2
+
+
+def mode_to_contacts(mode: int):
+    """modeNumber2StanceLeg: {left, right}"""
+    return [(False, False), (False, True), (True, False), (True, True)][mode]
+
+
+@dataclass
+class ModeSchedule:
+    event_times: list = field(default_factory=list)
+    mode_sequence: list = field(default_factory=lambda: [STANCE])
+
+    def mode_at(self, t: float) -> int:
+        return self.mode_sequence[bisect.bisect_left(self.event_times, t)]
+
+
+class GaitSchedule:
+    def __init__(self, init_events=(0.5,), init_modes=(STANCE, STANCE), template_modes=(STANCE,), template_times=(0.0, 0.5),
+                 phase_transition_stance_time=0.0):
+        self.ms = ModeSchedule(list(init_events), list(init_modes))
+        self.t_modes, self.t_times = list(template_modes), list(template_times)
+        self.ptst = phase_transition_stance_time
+
+    def insert_template(self, modes, times, start_time, final_time):
+        self.t_modes, self.t_times = list(modes), list(times)
+        ev, seq = self.ms.event_times, self.ms.mode_sequence
+        idx = bisect.bisect_left(ev, start_time)
+        if idx < len(ev):
+            del ev[idx:]
+            del seq[idx + 1:]
+        ptst = 0.0 if (seq and seq[-1] == STANCE) else self.ptst
+        if ptst > 0.0:
+            ev.append(start_time)
+            seq.append(STANCE)
+        self._tile(start_time + ptst, final_time)
+
+    def get_mode_schedule(self, lower, upper) -> ModeSchedule:
+        ev, seq = self.ms.event_times, self.ms.mode_sequence
+        idx = bisect.bisect_left(ev, lower)
+        if idx > 0:
+            del ev[: idx - 1]
+            del seq[: idx - 1]
+            seq[0] = STANCE
+        tiling_start = upper if not ev else ev[-1]
+        del ev[-1:]
+        del seq[-1:]
+        self._tile(tiling_start, upper)
+        return ModeSchedule(list(ev), list(seq))
+
+    def _tile(self, start, final):
+        ev, seq = self.ms.event_times, self.ms.mode_sequence
+        if not self.t_modes:
+            return
+        if ev and start <= ev[-1]:
+            raise RuntimeError("The initial time for template-tiling is not greater than the last event time.")
+        ev.append(start)
+        while ev[-1] < final:
+            for i, m in enumerate(self.t_modes):
+                seq.append(m)
+                ev.append(ev[-1] + (self.t_times[i + 1] - self.t_times[i]))
+        seq.append(STANCE)
+
+
+class CubicSpline:
+    def __init__(self, t0, p0, v0, t1, p1, v1):
+        self.t0, self.dt = t0, t1 - t0
+        dp, dv = p1 - p0, v1 - v0
+        self.c0 = p0
+        self.c1 = v0 * self.dt
+        self.c2 = -(3.0 * v0 + dv) * self.dt + 3.0 * dp
+        self.c3 = (2.0 * v0 + dv) * self.dt - 2.0 * dp
+
+    def pos(self, t):
+        tn = (t - self.t0) / self.dt
+        return self.c3 * tn ** 3 + self.c2 * tn ** 2 + self.c1 * tn + self.c0
+
+    def vel(self, t):
+        tn = (t - self.t0) / self.dt
+        return (3.0 * self.c3 * tn * tn + 2.0 * self.c2 * tn + self.c1) / self.dt
+
+    def acc(self, t):
+        tn = (t - self.t0) / self.dt
+        return (6.0 * self.c3 * tn + 2.0 * self.c2) / (self.dt * self.dt)
+
+
+class SplineCpg:
+    def __init__(self, lift, mid_height, touch):
+        (t0, p0, v0), (t1, p1, v1) = lift, touch
+        self.mid = (t0 + t1) / 2
+        self.left = CubicSpline(t0, p0, v0, self.mid, mid_height, 0.0)
+        self.right = CubicSpline(self.mid, mid_height, 0.0, t1, p1, v1)
+
+    def pos(self, t):
+        return self.left.pos(t) if t < self.mid else self.right.pos(t)
+
+    def vel(self, t):
+        return self.left.vel(t) if t < self.mid else self.right.vel(t)
+
+    def acc(self, t):
+        return self.left.acc(t) if t < self.mid else self.right.acc(t)
+
+
+class SwingTrajectoryPlanner:
+    def __init__(self, cfg: dict, n_feet=2):
+        self.c, self.n = cfg, n_feet
+
+    def update(self, ms: ModeSchedule, terrain_height=0.0):
+        c = self.c
+        modes, ev = ms.mode_sequence, ms.event_times
+        nph = len(modes)
+        lift_h, touch_h = terrain_height, terrain_height + c["touchDownHeightOffset"]
+        self.events = list(ev)
+        self.height, self.impact = [], []
+        for j in range(self.n):
+            flags = [mode_to_contacts(m)[j] for m in modes]
+            hs, ips = [], []
+            for p in range(nph):
+                if flags[p]:
+                    hs.append(SplineCpg((0.0, lift_h, 0.0), lift_h, (1.0, lift_h, 0.0)))
+                    ips.append(SplineCpg((0.0, 1.0, 0.0), 1.0, (1.0, 1.0, 0.0)))
+                    continue
+                start = next((ip for ip in range(p - 1, -1, -1) if flags[ip]), -1)
+                final = next((ip - 1 for ip in range(p + 1, nph) if flags[ip]), nph - 1)
+                if start < 0:
+                    raise RuntimeError(f"The time of take-off for the first swing of the EE with ID {j} is not defined.")
+                if final >= nph - 1:
+                    raise RuntimeError(f"The time of touch-down for the last swing of the EE with ID {j} is not defined.")
+                ts, tf = ev[start], ev[final]
+                prev_c, next_c = flags[p - 1], flags[p + 1]
+                mid_v = c["ipfMidPointValue"]
+                if prev_c and next_c:
+                    s = min(1.0, (tf - ts) / c["swingTimeScale"])
+                    hs.append(SplineCpg((ts, lift_h, s * c["liftOffVelocity"]), min(lift_h, touch_h) + s * c["swingHeight"],
+                                        (tf, touch_h, s * c["touchDownVelocity"])))
+                    ips.append(SplineCpg((ts, 1.0, s * c["ipfLiftOffVelocity"]), mid_v, (tf, 1.0, s * c["ipfTouchDownVelocity"])))
+                elif prev_c:
+                    mid = lift_h + c["swingHeight"]
+                    hs.append(SplineCpg((ts, lift_h, c["liftOffVelocity"]), mid, (tf, mid, 0.0)))
+                    ips.append(SplineCpg((ts, 1.0, c["ipfLiftOffVelocity"]), mid_v, (tf, mid_v, 0.0)))
+                elif next_c:
+                    mid = touch_h + c["swingHeight"]
+                    hs.append(SplineCpg((ts, mid, 0.0), mid, (tf, touch_h, c["touchDownVelocity"])))
+                    ips.append(SplineCpg((ts, mid_v, 0.0), mid_v, (tf, 1.0, c["ipfTouchDownVelocity"])))
+                else:
+                    mid = touch_h + c["swingHeight"]
+                    hs.append(SplineCpg((ts, mid, 0.0), mid, (tf, mid, 0.0)))
+                    ips.append(SplineCpg((ts, mid_v, 0.0), mid_v, (tf, mid_v, 0.0)))
+            self.height.append(hs)
+            self.impact.append(ips)
+
+    def _idx(self, t):
+        return bisect.bisect_left(self.events, t)
+
+    def z_ref(self, leg, t):
+        s = self.height[leg][self._idx(t)]
+        return s.pos(t), s.vel(t), s.acc(t)
+
+    def impact_factor(self, leg, t):
+        return self.impact[leg][self._idx(t)].pos(t)
+
+
+def phase_variable(ms: ModeSchedule, t: float) -> float:
+    ev = ms.event_times
+    it = bisect.bisect_right(ev, t)
+    nxt, prv = ev[it], ev[it - 1]
+    m = ms.mode_at(t)
+    if m == LF:
+        return 0.5 * (t - prv) / (nxt - prv)
+    if m == RF:
+        return 0.5 + 0.5 * (t - prv) / (nxt - prv)
+    return 0.5 if ms.mode_at(prv - 0.01) == LF else 0.0
+
+
+def time_discretization_with_events(t0, tf, dt, event_times, dt_min=10.0 * LIMIT_EPS):
+    td = [[t0, EV_NONE]]
+    nxt_idx = bisect.bisect_left(event_times, t0)
+    nxt = [t0, EV_NONE]
+    while td[-1][0] < tf:
+        nxt = [nxt[0] + dt, EV_NONE]
+        if nxt_idx < len(event_times) and nxt[0] >= event_times[nxt_idx]:
+            nxt = [event_times[nxt_idx], EV_PRE]
+            nxt_idx += 1
+        if nxt[0] >= tf:
+            nxt = [tf, EV_NONE]
+        if nxt[0] > td[-1][0] + dt_min:
+            td.append(list(nxt))
+        else:
+            td[-1] = list(nxt)
+    if td[0][1] == EV_PRE:
+        td[0][1] = EV_POST
+    out = []
+    for t, e in td:
+        out.append((t, e))
+        if e == EV_PRE:
+            out.append((t, EV_POST))
+    return np.array([t for t, _ in out]), np.array([e for _, e in out], dtype=np.uint8)
+
+
+def interval_start(t, e):
+    return t + (WEAK_EPS if e == EV_POST else 0.0)
+
+
+def velocity_command_targets(model: dict, t0, x0, cmd, horizon):
+    """3-knot TargetTrajectories for cmd = [v_x, v_y, pelvis height, yaw rate] (steady-state command filter)."""
+    nj = model["nj"]
+    nv = 6 + nj
+    pose = np.array(x0[:6], float)
+    pose[4] = pose[5] = 0.0
+    yaw = pose[3]
+    vg = np.array(cmd, float)
+    vg[0] = math.cos(yaw) * cmd[0] - math.sin(yaw) * cmd[1]
+    vg[1] = math.sin(yaw) * cmd[0] + math.cos(yaw) * cmd[1]
+    base_vel = np.array([vg[0], vg[1], 0.0, vg[3], 0.0, 0.0])
+    t_mid = 0.7 * horizon
+    bv = x0[nv:nv + 6]
+    avg = np.array([(bv[0] + vg[0]) / 2, (bv[1] + vg[1]) / 2, (bv[5] + vg[3]) / 2])
+    pose[2] = vg[2]
+
+    def integrate(p, av, h, dT):
+        q = p.copy()
+        q[0] += av[0] * dT
+        q[1] += av[1] * dT
+        q[2] = h
+        q[3] += av[2] * dT
+        q[4] = q[5] = 0.0
+        return q
+
+    mid = integrate(pose, avg, vg[2], t_mid)
+    fin = integrate(mid, np.array([vg[0], vg[1], vg[3]]), vg[2], horizon - t_mid)
+    joints = np.array(model["reference"]["defaultJointState"])
+    states = [np.concatenate([p, joints, base_vel, np.zeros(nj)]) for p in (pose, mid, fin)]
+    return np.array([t0, t0 + t_mid, t0 + horizon]), np.array(states)
+
+
+def interp_targets(times, states, t):
+    """LinearInterpolation::interpolate with clamping (TargetTrajectories::getDesiredState)"""
+    if t <= times[0]:
+        return states[0].copy()
+    if t >= times[-1]:
+        return states[-1].copy()
+    i = bisect.bisect_right(list(times), t) - 1
+    a = (times[i + 1] - t) / (times[i + 1] - times[i])
+    return a * states[i] + (1 - a) * states[i + 1]
+
+
+def weight_compensating_input(model: dict, contacts):
+    u = np.zeros(model["nu"])
+    ns = int(contacts[0]) + int(contacts[1])
+    if ns > 0:
+        fz = sum(model["mass"]) * 9.81 / ns
+        for c in range(2):
+            if contacts[c]:
+                u[6 * c + 2] = fz
+    return u
+
+
+def build_instance(model: dict, x0, t0=0.0, horizon=None, dt=None, gait="stance", gait_start=None, cmd=None):
+    """One MPC instance (cold start) -> dict of per-node arrays in the layout of b200sqp_upload_instances."""
+    sq = model["sqp"]
+    horizon = sq["timeHorizon"] if horizon is None else horizon
+    dt = sq["dt"] if dt is None else dt
+    tf = t0 + horizon
+    x0 = np.asarray(x0, float)
+    gs = GaitSchedule()
+    if gait != "stance":
+        g = model["gaits"][gait]
+        start = t0 if gait_start is None else gait_start
+        gs.insert_template([MODE_NAMES[m] for m in g["modeSequence"]], g["switchingTimes"], start, tf + horizon)
+    ms = gs.get_mode_schedule(t0 - horizon, tf + horizon)
+    planner = SwingTrajectoryPlanner(model["swing"])
+    planner.update(ms, 0.0)
+    t_nodes, events = time_discretization_with_events(t0, tf, dt, ms.event_times)
+    n = len(t_nodes)
+    cmd = [0.0, 0.0, model["reference"]["defaultBaseHeight"], 0.0] if cmd is None else list(cmd)
+    tt, ts = velocity_command_targets(model, t0, x0, cmd, horizon)
+    nx, nu = model["nx"], model["nu"]
+    contact = np.zeros((n, 2), dtype=np.uint8)
+    swing = np.zeros((n, 2, 3))
+    impact = np.ones((n, 2))
+    arm = np.zeros(n)
+    xref = np.zeros((n, nx))
+    u_init = np.zeros((n - 1, nu))
+    for i in range(n):
+        t = interval_start(t_nodes[i], events[i])
+        m = ms.mode_at(t)
+        contact[i] = mode_to_contacts(m)
+        for c in range(2):
+            swing[i, c] = planner.z_ref(c, t)
+            impact[i, c] = planner.impact_factor(c, t)
+        arm[i] = math.sin(2 * math.pi * (phase_variable(ms, t) - 0.15))
+        xref[i] = interp_targets(tt, ts, t)
+        if i < n - 1 and events[i] != EV_PRE:
+            u_init[i] = weight_compensating_input(model, contact[i])
+    x_init = np.tile(x0, (n, 1))
+    return dict(x0=x0, x_init=x_init, u_init=u_init, t_nodes=t_nodes, node_event=events, contact_flags=contact, swing_ref=swing,
+                impact_factor=impact, arm_phase=arm, x_ref=xref, mode_schedule=ms)
