@@ -1,0 +1,375 @@
+// K1/K3 building block: whole-body flow map xdot = f(x,u) and the analytic Jacobian of the base acceleration.
+//
+// Reference path: WBAccelDynamicsAD::systemFlowMap -> computeStateDerivative -> computeBaseAcceleration
+//   (humanoid_nmpc/humanoid_wb_mpc/src/dynamics/DynamicsHelperFunctions.cpp:51-134) with the block-diagonal base inertia
+//   inverse of humanoid_common_mpc/src/pinocchio_model/DynamicsHelperFunctions.cpp:196-218; the reference differentiates it
+//   with CppAD (ocs2_core/src/automatic_differentation/CppAdInterface.cpp:165-187).
+//
+// B200 formulation (not a port of Pinocchio/CppAD):
+//   * everything is expressed in pelvis coordinates about the pelvis origin, so the base pose enters only through
+//     v0 = (R'pdot, S thdot), a0 = (vl x wb + R'g, Sdot thdot) and the final rotations q̈_lin = R N_lin/m, q̈_ang = S^-1 Ic^-1 N_ang;
+//   * M_bj qdd_j + nle_b is one Newton-Euler sweep; composite quantities in a common frame are plain sums over subtrees;
+//   * d(total wrench)/d(q_k, qd_k, qdd_k) use the closed forms for single-DoF joints
+//       dF/dq_k = S_k x* fC_k + IC_k psidd_k + 2 BC_k psid_k,  dF/dqd_k = 2 IC_k psid_k + 2 BC_k S_k,  dF/dqdd_k = IC_k S_k
+//     (Singh, Russell, Wensing, "Efficient analytical derivatives of rigid-body dynamics using spatial vector algebra", RA-L 2022),
+//     so one tangent direction is O(1) work once the composites exist: one thread per column of the 6 x 93 Jacobian.
+// All functions are phase functions: every work item writes only its own outputs, phases are separated by a block barrier.
+#pragma once
+#include "wb_model.cuh"
+
+namespace b200sqp {
+
+struct Par {  // the calling thread's slice of a phase
+  int tid, nt;
+};
+
+// shared-memory workspace of one evaluation point (doubles)
+struct DynWs {
+  // base
+  double Rb[9], Sz[9], SzInv[9], v0[6], a0[6];
+  double dv0[9][6], da0[9][6], dRb[3][9], dSz[3][9];  // tangents w.r.t. th(3), pdot(3), thdot(3)
+  // bodies (pelvis coordinates)
+  double R[NB][9], p[NB][3], S[NB][6], v[NB][6], a[NB][6], psd[NB][6], psdd[NB][6];
+  double I[NB][36], Bm[NB][36], f[NB][6];
+  double IC[NB][36], BC[NB][36], fC[NB][6];
+  // finals
+  double pc[2][3], lf[2][3], lm[2][3];  // contact points, local contact force / moment
+  double N[6], IcInv[9], y[3], qddb[6];
+};
+
+HD void zyx(const D1* th, D1* R, D1* S) {
+  // Rz(th0) Ry(th1) Rx(th2) and the body-frame angular-velocity map of Pinocchio's JointModelSphericalZYX
+  const D1 c0{cos(th[0].v), -sin(th[0].v) * th[0].d}, s0{sin(th[0].v), cos(th[0].v) * th[0].d};
+  const D1 c1{cos(th[1].v), -sin(th[1].v) * th[1].d}, s1{sin(th[1].v), cos(th[1].v) * th[1].d};
+  const D1 c2{cos(th[2].v), -sin(th[2].v) * th[2].d}, s2{sin(th[2].v), cos(th[2].v) * th[2].d};
+  const D1 zero{0.0, 0.0}, one{1.0, 0.0};
+  R[0] = c0 * c1; R[1] = c0 * s1 * s2 - s0 * c2; R[2] = c0 * s1 * c2 + s0 * s2;
+  R[3] = s0 * c1; R[4] = s0 * s1 * s2 + c0 * c2; R[5] = s0 * s1 * c2 - c0 * s2;
+  R[6] = -s1;     R[7] = c1 * s2;                R[8] = c1 * c2;
+  S[0] = -s1;     S[1] = zero; S[2] = one;
+  S[3] = c1 * s2; S[4] = c2;   S[5] = zero;
+  S[6] = c1 * c2; S[7] = -s2;  S[8] = zero;
+}
+
+// Base kinematics with one tangent direction (dir in 0..8 = th, pdot, thdot; dir < 0: values only).
+HD void baseKinematics(const double* x, int dir, double g, D1* R, D1* S, D1* v0, D1* a0) {
+  D1 th[3], pd[3], td[3];
+#pragma unroll
+  for (int k = 0; k < 3; ++k) {
+    th[k] = D1{x[3 + k], dir == k ? 1.0 : 0.0};
+    pd[k] = D1{x[NV + k], dir == 3 + k ? 1.0 : 0.0};
+    td[k] = D1{x[NV + 3 + k], dir == 6 + k ? 1.0 : 0.0};
+  }
+  zyx(th, R, S);
+  // vl = R' pdot, wb = S thdot
+  const DV3 vl{R[0] * pd[0] + R[3] * pd[1] + R[6] * pd[2], R[1] * pd[0] + R[4] * pd[1] + R[7] * pd[2], R[2] * pd[0] + R[5] * pd[1] + R[8] * pd[2]};
+  const DV3 wb{S[0] * td[0] + S[1] * td[1] + S[2] * td[2], S[3] * td[0] + S[4] * td[1] + S[5] * td[2], S[6] * td[0] + S[7] * td[1] + S[8] * td[2]};
+  v0[0] = vl.x; v0[1] = vl.y; v0[2] = vl.z; v0[3] = wb.x; v0[4] = wb.y; v0[5] = wb.z;
+  // a0 = (vl x wb + R' g e_z, Sdot thdot)
+  const DV3 c = dcross(vl, wb);
+  a0[0] = c.x + g * R[6];
+  a0[1] = c.y + g * R[7];
+  a0[2] = c.z + g * R[8];
+  const D1 c1{cos(th[1].v), -sin(th[1].v) * th[1].d}, s1{sin(th[1].v), cos(th[1].v) * th[1].d};
+  const D1 c2{cos(th[2].v), -sin(th[2].v) * th[2].d}, s2{sin(th[2].v), cos(th[2].v) * th[2].d};
+  a0[3] = -(c1 * td[1] * td[0]);
+  a0[4] = (c1 * c2 * td[2] - s1 * s2 * td[1]) * td[0] - s2 * td[2] * td[1];
+  a0[5] = -((s1 * c2 * td[1] + c1 * s2 * td[2]) * td[0]) - c2 * td[2] * td[1];
+}
+
+HD void inv3(const double* A, double* Ai) {
+  const double c00 = A[4] * A[8] - A[5] * A[7], c01 = A[5] * A[6] - A[3] * A[8], c02 = A[3] * A[7] - A[4] * A[6];
+  const double det = A[0] * c00 + A[1] * c01 + A[2] * c02, id = 1.0 / det;
+  Ai[0] = c00 * id; Ai[1] = (A[2] * A[7] - A[1] * A[8]) * id; Ai[2] = (A[1] * A[5] - A[2] * A[4]) * id;
+  Ai[3] = c01 * id; Ai[4] = (A[0] * A[8] - A[2] * A[6]) * id; Ai[5] = (A[2] * A[3] - A[0] * A[5]) * id;
+  Ai[6] = c02 * id; Ai[7] = (A[1] * A[6] - A[0] * A[7]) * id; Ai[8] = (A[0] * A[4] - A[1] * A[3]) * id;
+}
+
+// ---- phase 1: base quantities (items 0..9) and chain kinematics (items 16..19) ------------------------------------------------
+// chains: 0 left leg, 1 right leg, 2 waist + left arm, 3 waist + right arm (waist recomputed in registers, written by chain 2 only)
+template <bool DERIV>
+HD void dynPhaseKinematics(Par P, const WbDeviceModel& m, const double* x, const double* u, DynWs& w) {
+  for (int it = P.tid; it < 20; it += P.nt) {
+    if (it == 0) {
+      D1 R[9], S[9], v0[6], a0[6];
+      baseKinematics(x, -1, m.gravity, R, S, v0, a0);
+      double Sv[9];
+      for (int k = 0; k < 9; ++k) {
+        w.Rb[k] = R[k].v;
+        w.Sz[k] = Sv[k] = S[k].v;
+      }
+      inv3(Sv, w.SzInv);
+      for (int k = 0; k < 6; ++k) {
+        w.v0[k] = v0[k].v;
+        w.a0[k] = a0[k].v;
+      }
+    } else if (it >= 1 && it <= 9) {
+      if (DERIV) {
+        const int dir = it - 1;
+        D1 R[9], S[9], v0[6], a0[6];
+        baseKinematics(x, dir, m.gravity, R, S, v0, a0);
+        for (int k = 0; k < 6; ++k) {
+          w.dv0[dir][k] = v0[k].d;
+          w.da0[dir][k] = a0[k].d;
+        }
+        if (dir < 3)
+          for (int k = 0; k < 9; ++k) {
+            w.dRb[dir][k] = R[k].d;
+            w.dSz[dir][k] = S[k].d;
+          }
+      }
+    } else if (it >= 16) {
+      const int ch = it - 16;
+      // values of the base needed by the recursion (recomputed locally to avoid a barrier)
+      D1 Rd[9], Sd[9], v0d[6], a0d[6];
+      baseKinematics(x, -1, m.gravity, Rd, Sd, v0d, a0d);
+      double Rl[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1};
+      V3 pl = mk(0, 0, 0);
+      V6 vl{mk(v0d[0].v, v0d[1].v, v0d[2].v), mk(v0d[3].v, v0d[4].v, v0d[5].v)};
+      V6 al{mk(a0d[0].v, a0d[1].v, a0d[2].v), mk(a0d[3].v, a0d[4].v, a0d[5].v)};
+      if (ch == 0) {  // body 0 entries
+        for (int k = 0; k < 9; ++k) w.R[0][k] = Rl[k];
+        st3(w.p[0], pl);
+        st6(w.v[0], vl);
+        st6(w.a[0], al);
+        for (int k = 0; k < 6; ++k) w.S[0][k] = w.psd[0][k] = w.psdd[0][k] = 0.0;
+      }
+      int first, last, own;
+      if (ch == 0) { first = 1; last = 6; own = 1; }
+      else if (ch == 1) { first = 7; last = 12; own = 7; }
+      else if (ch == 2) { first = 13; last = 19; own = 13; }
+      else { first = 13; last = 23; own = 20; }
+      for (int i = first; i <= last; ++i) {
+        if (ch == 3 && i >= 16 && i < 20) continue;  // skip the left arm on the right-arm chain
+        const double q = x[5 + i], qd = x[NV + 5 + i], qdd = u[12 + i - 1];
+        // joint rotation (Rodrigues) and placement
+        const double* ax = m.axis[i];
+        const double c = cos(q), s = sin(q), t = 1.0 - c;
+        const double Rq[9] = {t * ax[0] * ax[0] + c,         t * ax[0] * ax[1] - s * ax[2], t * ax[0] * ax[2] + s * ax[1],
+                              t * ax[0] * ax[1] + s * ax[2], t * ax[1] * ax[1] + c,         t * ax[1] * ax[2] - s * ax[0],
+                              t * ax[0] * ax[2] - s * ax[1], t * ax[1] * ax[2] + s * ax[0], t * ax[2] * ax[2] + c};
+        double Rj[9], Ri[9];
+        mm3(m.jR[i], Rq, Rj);
+        mm3(Rl, Rj, Ri);
+        const V3 pi = pl + mv(Rl, ld3(m.jp[i]));
+        const V3 om = mv(Ri, ld3(ax));
+        const V6 Si{cross(pi, om), om};
+        const V6 psd = mcross(vl, Si);
+        const V6 vi = vl + qd * Si;
+        const V6 ai = al + qdd * Si + qd * psd;
+        const V6 psdd = mcross(al, Si) + mcross(vl, psd);
+        if (i >= own) {
+          for (int k = 0; k < 9; ++k) w.R[i][k] = Ri[k];
+          st3(w.p[i], pi);
+          st6(w.S[i], Si);
+          st6(w.v[i], vi);
+          st6(w.a[i], ai);
+          st6(w.psd[i], psd);
+          st6(w.psdd[i], psdd);
+        }
+        for (int k = 0; k < 9; ++k) Rl[k] = Ri[k];
+        pl = pi;
+        vl = vi;
+        al = ai;
+      }
+    }
+  }
+}
+
+// ---- phase 2: per-body spatial inertia and force (items = bodies) --------------------------------------------------------------
+HD void dynPhaseInertia(Par P, const WbDeviceModel& m, DynWs& w) {
+  for (int i = P.tid; i < NB; i += P.nt) {
+    const double* R = w.R[i];
+    const V3 c = ld3(w.p[i]) + mv(R, ld3(m.com[i]));
+    double T[9], Ir[9];
+    // R Icom R'
+    for (int r = 0; r < 3; ++r)
+      for (int k = 0; k < 3; ++k) T[3 * r + k] = R[3 * r] * m.Icom[i][k] + R[3 * r + 1] * m.Icom[i][3 + k] + R[3 * r + 2] * m.Icom[i][6 + k];
+    for (int r = 0; r < 3; ++r)
+      for (int k = 0; k < 3; ++k) Ir[3 * r + k] = T[3 * r] * R[3 * k] + T[3 * r + 1] * R[3 * k + 1] + T[3 * r + 2] * R[3 * k + 2];
+    const double ms = m.mass[i];
+    const double C[9] = {0, -c.z, c.y, c.z, 0, -c.x, -c.y, c.x, 0};
+    double* I = w.I[i];
+    for (int r = 0; r < 3; ++r)
+      for (int k = 0; k < 3; ++k) {
+        double cc = C[3 * r] * C[k] + C[3 * r + 1] * C[3 + k] + C[3 * r + 2] * C[6 + k];
+        I[6 * r + k] = (r == k) ? ms : 0.0;
+        I[6 * r + 3 + k] = -ms * C[3 * r + k];
+        I[6 * (3 + r) + k] = ms * C[3 * r + k];
+        I[6 * (3 + r) + 3 + k] = Ir[3 * r + k] - ms * cc;
+      }
+    const V6 v = ld6(w.v[i]), a = ld6(w.a[i]);
+    const V6 h = m6v(I, v);
+    st6(w.f[i], m6v(I, a) + fcross(v, h));
+  }
+}
+
+// ---- phase 3: B_i = 1/2 [ (v x*) I - I (v x) + (I v) xbar* ]  (items = body x column) ------------------------------------------
+HD void dynPhaseBmat(Par P, DynWs& w) {
+  for (int it = P.tid; it < NB * 6; it += P.nt) {
+    const int i = it / 6, j = it % 6;
+    const double* I = w.I[i];
+    const V6 v = ld6(w.v[i]);
+    const V6 h = m6v(I, v);
+    const V6 e = basis6(j);
+    V6 Ie{mk(I[j], I[6 + j], I[12 + j]), mk(I[18 + j], I[24 + j], I[30 + j])};
+    const V6 col = 0.5 * (fcross(v, Ie) - m6v(I, mcross(v, e)) + fcross(e, h));
+    double o[6];
+    st6(o, col);
+    for (int r = 0; r < 6; ++r) w.Bm[i][6 * r + j] = o[r];
+  }
+}
+
+// ---- phase 4: composites = sums over subtrees (common coordinates) ------------------------------------------------------------------
+template <bool DERIV>
+HD void dynPhaseComposite(Par P, const WbDeviceModel& m, DynWs& w) {
+  const int per = DERIV ? 78 : 42;  // IC (36) [+ BC (36)] + fC (6)
+  for (int it = P.tid; it < NB * per; it += P.nt) {
+    const int i = it / per, e = it % per;
+    if (!DERIV && i != 0) continue;  // the value-only path needs only the root composite
+    const unsigned mask = m.subtree[i];
+    double s = 0.0;
+    if (e < 36) {
+      for (int j = i; j < NB; ++j)
+        if (mask >> j & 1u) s += w.I[j][e];
+      w.IC[i][e] = s;
+    } else if (DERIV && e < 72) {
+      for (int j = i; j < NB; ++j)
+        if (mask >> j & 1u) s += w.Bm[j][e - 36];
+      w.BC[i][e - 36] = s;
+    } else {
+      const int k = e - (DERIV ? 72 : 36);
+      for (int j = i; j < NB; ++j)
+        if (mask >> j & 1u) s += w.f[j][k];
+      w.fC[i][k] = s;
+    }
+  }
+}
+
+// ---- phase 5: net wrench, base acceleration (single item) ----------------------------------------------------------------------------
+HD void dynPhaseFinal(Par P, const WbDeviceModel& m, const double* u, DynWs& w) {
+  if (P.tid != 0) return;
+  V6 E{mk(0, 0, 0), mk(0, 0, 0)};
+  for (int c = 0; c < 2; ++c) {
+    const int b = m.frameBody[3 * c];
+    const V3 pc = ld3(w.p[b]) + mv(w.R[b], ld3(m.frameP[3 * c]));
+    const V3 lf = mtv(w.Rb, ld3(u + 6 * c)), lm = mtv(w.Rb, ld3(u + 6 * c + 3));
+    st3(w.pc[c], pc);
+    st3(w.lf[c], lf);
+    st3(w.lm[c], lm);
+    E.l = E.l + lf;
+    E.a = E.a + cross(pc, lf) + lm;
+  }
+  const V6 N = E - ld6(w.fC[0]);
+  st6(w.N, N);
+  double Ic[9];
+  for (int r = 0; r < 3; ++r)
+    for (int k = 0; k < 3; ++k) Ic[3 * r + k] = w.IC[0][6 * (3 + r) + 3 + k];
+  inv3(Ic, w.IcInv);
+  const V3 y = mv(w.IcInv, N.a);
+  st3(w.y, y);
+  st3(w.qddb, (1.0 / m.mtot) * mv(w.Rb, N.l));
+  st3(w.qddb + 3, mv(w.SzInv, y));
+}
+
+// xdot (58) from the workspace
+HD void dynWriteFlow(Par P, const double* x, const double* u, const DynWs& w, double* xdot) {
+  for (int i = P.tid; i < NX; i += P.nt) xdot[i] = (i < NV) ? x[NV + i] : (i < NV + 6 ? w.qddb[i - NV] : u[12 + i - NV - 6]);
+}
+
+// d(qdd_b)/dz column for direction d given the tangents of the net wrench / composite inertia / base rotations
+HD void baseAccTangent(const WbDeviceModel& m, const DynWs& w, V6 dN, const double* dIc, const double* dRb, const double* dSz, double* col) {
+  V3 lin = mv(w.Rb, dN.l);
+  if (dRb) lin = lin + mv(dRb, ld3(w.N));
+  st3(col, (1.0 / m.mtot) * lin);
+  V3 rhs = dN.a;
+  if (dIc) rhs = rhs - mv(dIc, ld3(w.y));
+  V3 dy = mv(w.IcInv, rhs);
+  if (dSz) dy = dy - mv(dSz, ld3(w.qddb + 3));
+  st3(col + 3, mv(w.SzInv, dy));
+}
+
+// ---- phase 6: G = d(qdd_b)/d[x;u]  (6 x 93, column-major with leading dimension 6; one item per column) ------------------------------
+HD void dynPhaseJacobian(Par P, const WbDeviceModel& m, const DynWs& w, double* G) {
+  for (int d = P.tid; d < NZ; d += P.nt) {
+    double* col = G + 6 * d;
+    if (d < 3) {  // base position: no dependence
+      for (int k = 0; k < 6; ++k) col[k] = 0.0;
+      continue;
+    }
+    V6 dN{mk(0, 0, 0), mk(0, 0, 0)};
+    if (d < 6 || (d >= NV && d < NV + 6)) {
+      // base directions: th (d-3), pdot (d-NV), thdot (d-NV-3)
+      const int dir = d < 6 ? d - 3 : 3 + (d - NV);
+      const V6 dv0 = ld6(w.dv0[dir]), da0 = ld6(w.da0[dir]);
+      const V6 v0 = ld6(w.v0);
+      const V6 dF = 2.0 * m6v(w.BC[0], dv0) + m6v(w.IC[0], mcross(v0, dv0) + da0);
+      dN = V6{-dF.l, -dF.a};
+      if (d < 6) {
+        const double* dR = w.dRb[dir];
+        for (int c = 0; c < 2; ++c) {
+          // local force/moment tangents: d(R') f
+          const V3 fw = mv(w.Rb, ld3(w.lf[c])), mw = mv(w.Rb, ld3(w.lm[c]));  // back to world values
+          const V3 dlf = mtv(dR, fw), dlm = mtv(dR, mw);
+          dN.l = dN.l + dlf;
+          dN.a = dN.a + cross(ld3(w.pc[c]), dlf) + dlm;
+        }
+        baseAccTangent(m, w, dN, nullptr, dR, w.dSz[dir], col);
+      } else {
+        baseAccTangent(m, w, dN, nullptr, nullptr, nullptr, col);
+      }
+    } else if (d < NV) {  // joint position q_k
+      const int k = d - 6 + 1;
+      const V6 S = ld6(w.S[k]);
+      const V6 dF = fcross(S, ld6(w.fC[k])) + m6v(w.IC[k], ld6(w.psdd[k])) + 2.0 * m6v(w.BC[k], ld6(w.psd[k]));
+      dN = V6{-dF.l, -dF.a};
+      for (int c = 0; c < 2; ++c) {
+        const int b = m.frameBody[3 * c];
+        if (m.subtree[k] >> b & 1u) {  // contact point moves with joint k
+          const V3 dp = cross(S.a, ld3(w.pc[c]) - ld3(w.p[k]));
+          dN.a = dN.a + cross(dp, ld3(w.lf[c]));
+        }
+      }
+      // d Ic = rot block of (S x* IC - IC S x)
+      const double* X = w.IC[k];
+      double dIc[9];
+      const double sx[9] = {0, -S.l.z, S.l.y, S.l.z, 0, -S.l.x, -S.l.y, S.l.x, 0};
+      const double wx[9] = {0, -S.a.z, S.a.y, S.a.z, 0, -S.a.x, -S.a.y, S.a.x, 0};
+      for (int r = 0; r < 3; ++r)
+        for (int cc = 0; cc < 3; ++cc) {
+          double s = 0.0;
+          for (int t = 0; t < 3; ++t) {
+            s += sx[3 * r + t] * X[6 * t + 3 + cc];            // [s]x M12
+            s += wx[3 * r + t] * X[6 * (3 + t) + 3 + cc];      // [w]x M22
+            s -= X[6 * (3 + r) + t] * sx[3 * t + cc];          // M21 [s]x
+            s -= X[6 * (3 + r) + 3 + t] * wx[3 * t + cc];      // M22 [w]x
+          }
+          dIc[3 * r + cc] = s;
+        }
+      baseAccTangent(m, w, dN, dIc, nullptr, nullptr, col);
+    } else if (d < NX) {  // joint velocity qd_k
+      const int k = d - NV - 6 + 1;
+      const V6 dF = 2.0 * (m6v(w.IC[k], ld6(w.psd[k])) + m6v(w.BC[k], ld6(w.S[k])));
+      dN = V6{-dF.l, -dF.a};
+      baseAccTangent(m, w, dN, nullptr, nullptr, nullptr, col);
+    } else if (d < NX + 12) {  // contact wrench components
+      const int c = (d - NX) / 6, j = (d - NX) % 6;
+      const V3 e = mk(j % 3 == 0, j % 3 == 1, j % 3 == 2);
+      const V3 le = mtv(w.Rb, e);
+      if (j < 3) {
+        dN.l = le;
+        dN.a = cross(ld3(w.pc[c]), le);
+      } else {
+        dN.a = le;
+      }
+      baseAccTangent(m, w, dN, nullptr, nullptr, nullptr, col);
+    } else {  // joint acceleration qdd_k
+      const int k = d - NX - 12 + 1;
+      const V6 dF = m6v(w.IC[k], ld6(w.S[k]));
+      dN = V6{-dF.l, -dF.a};
+      baseAccTangent(m, w, dN, nullptr, nullptr, nullptr, col);
+    }
+  }
+}
+
+}  // namespace b200sqp
