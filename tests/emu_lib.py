@@ -1,0 +1,66 @@
+"""ctypes bindings of the CPU development harness (tests/emu/libwbemu.so): the CUDA kernels' __host__ __device__ phase functions
+executed on the host.  Test infrastructure only -- never linked into or called by the product library."""
+from __future__ import annotations
+
+import ctypes as C
+import shutil
+import subprocess
+from pathlib import Path
+
+import numpy as np
+
+from oracle_lib import F, _p, unpack_raw_blocks
+
+ROOT = Path(__file__).resolve().parents[1]
+EMU = ROOT / "tests" / "emu"
+CSRC = ROOT / "wb_humanoid_mpc_b200" / "csrc"
+_lib = None
+
+
+def build(force=False):
+    so = EMU / "libwbemu.so"
+    srcs = list(EMU.glob("*.cu")) + list(EMU.glob("*.inc")) + list(CSRC.glob("*.cuh")) + list(CSRC.glob("*.inc"))
+    if force or not so.exists() or any(s.stat().st_mtime > so.stat().st_mtime for s in srcs):
+        nvcc = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
+        subprocess.run([nvcc, "-O2", "-std=c++17", "-DEMU_WITH_LQ", "-shared", "-Xcompiler", "-fPIC", "-Wno-deprecated-gpu-targets",
+                        "-diag-suppress", "177", "-o", str(so), str(EMU / "wb_emu.cu")], check=True)
+    return so
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        _lib = C.CDLL(str(build()))
+    return _lib
+
+
+class EmuNodeIn(C.Structure):
+    _fields_ = [("x", C.POINTER(C.c_double)), ("u", C.POINTER(C.c_double)), ("xnext", C.POINTER(C.c_double)), ("xref", C.POINTER(C.c_double)),
+                ("dt", C.c_double), ("contact", C.c_int * 2), ("swing", C.c_double * 6), ("impact", C.c_double * 2), ("armPhase", C.c_double)]
+
+
+def dyn(desc, x, u, deriv=True):
+    xd, G = np.zeros(58), np.zeros((93, 6))
+    rc = lib().emu_dyn(C.byref(desc), _p(F(x)), _p(F(u)), _p(xd), _p(G), C.c_int(int(deriv)))
+    assert rc == 0
+    return xd, G.T.copy()
+
+
+def lq_node(desc, x, u, xnext, xref, dt, contact, swing, impact, arm_phase):
+    NX, NU, NT = 58, 35, 23
+    xs, us, xn, xr = F(x), F(u), F(xnext), F(xref)
+    nin = EmuNodeIn(_p(xs), _p(us), _p(xn), _p(xr), dt, (C.c_int * 2)(*[int(c) for c in contact]), (C.c_double * 6)(*np.asarray(swing, float).reshape(6)),
+                    (C.c_double * 2)(*impact), arm_phase)
+    A, Bt, b = np.zeros((NX, NX)), np.zeros((NT, NX)), np.zeros(NX)
+    Q, St, Rt, q, rt = np.zeros((NX, NX)), np.zeros((NX, NT)), np.zeros((NT, NT)), np.zeros(NX), np.zeros(NT)
+    Pu, Px, u0 = np.zeros((NT, NU)), np.zeros((NX, NU)), np.zeros(NU)
+    nut = C.c_int(0)
+    perf = np.zeros(4)
+    per = 2 * NX * NX + 2 * NX * NU + NU * NU + 2 * NX + NU + 1 + 14 * (NX + NU + 1) + 1
+    raw = np.zeros(per)
+    rc = lib().emu_lq_node(C.byref(desc), C.byref(nin), _p(A), _p(Bt), _p(b), _p(Q), _p(St), _p(Rt), _p(q), _p(rt), _p(Pu), _p(Px), _p(u0),
+                           C.byref(nut), _p(perf), _p(raw))
+    assert rc == 0
+    n = nut.value
+    return dict(A=A.T.copy(), B=Bt.T[:, :n].copy(), b=b, Q=Q.T.copy(), S=St.T[:n].copy(), R=Rt.T[:n, :n].copy(), q=q, r=rt[:n].copy(),
+                Pu=Pu.T[:, :n].copy(), Px=Px.T.copy(), u0=u0, nut=n, perf=perf, raw=unpack_raw_blocks(raw, NX, NU))

@@ -1,0 +1,501 @@
+// K1: linear-quadratic approximation of one shooting node (dynamics, costs, constraints, projection), as phase functions.
+//
+// Replaces, per node, SqpSolver::setupQuadraticSubproblem's body (lib/ocs2_ros2/ocs2_sqp/ocs2_sqp/src/SqpSolver.cpp:346-431):
+//   multiple_shooting::setupIntermediateNode (ocs2_oc/src/multiple_shooting/Transcription.cpp:40-94)
+//     rk4SensitivityDiscretization (ocs2_core/src/integration/SensitivityIntegratorImpl.cpp:130-169)
+//     approximateCost (ocs2_oc/src/approximate_model/LinearQuadraticApproximator.cpp:181-209) * dt
+//     equalityConstraintPtr->getLinearApproximation
+//   computePerformanceIndex (PerformanceIndexComputation.cpp:40-58)
+//   projectTranscription (Transcription.cpp:96-123): luConstraintProjection + changeOfInputVariables
+// with the whole-body terms wired as in humanoid_nmpc/humanoid_wb_mpc/src/WBMpcInterface.cpp:131-199.
+//
+// Structure exploited (B200 formulation): the continuous Jacobian of xdot = [v; qdd_b(x,u); qdd_j] has only six dense rows, so
+// the RK4 sensitivity chain carries a 6 x 93 block per stage instead of 58 x 58 / 58 x 35 products.
+#pragma once
+#include "dense_par.cuh"
+#include "wb_feet.cuh"
+
+namespace b200sqp {
+
+constexpr int HLD = NZ;        // Hessian [Q S'; S R] stored as one 93 x 93 column-major block
+constexpr int JR_MAX = 18;     // weighted Gauss-Newton / penalty rows processed per group (lives in the G[1..3] slots)
+
+struct NodeIn {  // per-node inputs (see b200sqp_upload_instances)
+  const double *x, *u, *xnext, *xref;
+  double dt;
+  int event;          // AnnotatedTime::Event of this node
+  int contact[2];
+  double swing[2][3], impact[2], armPhase;
+  int terminal;
+};
+
+// shared-memory map of the LQ kernel (offsets in doubles)
+struct NodeOut {  // global-memory destinations of one node
+  double *A, *Bt, *b, *Q, *St, *Rt, *q, *rt;  // projected stage record in the QP layout (nx = 58, nu_max = 23)
+  double *Pu, *Px, *u0;                       // projection u = Pu ut + Px dx + u0
+  int* nut;
+  double* perf;                               // [dt*cost, dt*|b|^2, dt*|e|^2, projected cost offset]
+  double* raw;                                // optional raw (pre-projection) block dump, oracle layout; may be null
+};
+
+struct LqWs {
+  DynWs* dyn;      // R1 (later: LU, Pu, Px, u0)
+  double* G;       // R2: 4 x (6 x 93)  (later: JR rows)
+  double* JF;      // R3: 2 x (18 x 93) (later: T1 = S + R Px)
+  double* H;       // R4: 93 x 93       (first used as scratch for JFl, FP, DFP)
+  double* AB;      // R5: 58 x 93  [A | B]
+  double* CD;      // R6: 14 x 93 (ld 14) then e (14)
+  double* fs;      // 4 x 58 stage flows, then b (58)
+  double* FV;      // 2 x 18 foot values
+  double* vec;     // q-gradient (93), misc scalars
+  // aliases
+  double *JFl, *FP, *DFP, *JR, *LU, *Pu, *Px, *u0, *T1, *ev, *gq, *sc;
+  int* iw;         // small integer scratch (pivots), lives in vec tail
+};
+
+HD size_t lqWsDoubles() {
+  const size_t dynD = (sizeof(DynWs) + 7) / 8;
+  return dynD + 4 * 6 * NZ + 2 * FQ * NZ + static_cast<size_t>(NZ) * NZ + static_cast<size_t>(NX) * NZ + (NC_MAX * NZ + NC_MAX) + 6 * NX +
+         2 * FQ + (NZ + 256);
+}
+HD void lqWsMap(double* base, LqWs& s) {
+  const size_t dynD = (sizeof(DynWs) + 7) / 8;
+  s.dyn = reinterpret_cast<DynWs*>(base);
+  s.G = base + dynD;
+  s.JF = s.G + 4 * 6 * NZ;
+  s.H = s.JF + 2 * FQ * NZ;
+  s.AB = s.H + static_cast<size_t>(NZ) * NZ;
+  s.CD = s.AB + static_cast<size_t>(NX) * NZ;
+  s.fs = s.CD + NC_MAX * NZ + NC_MAX;
+  s.FV = s.fs + 6 * NX;
+  s.vec = s.FV + 2 * FQ;
+  s.ev = s.CD + NC_MAX * NZ;
+  s.gq = s.vec;            // 93
+  s.sc = s.vec + NZ;       // scalars: [0] cost, [1] nc, [2] nut, [3..] penalties
+  s.iw = reinterpret_cast<int*>(s.vec + NZ + 64);  // 96 doubles = 192 ints
+  // scratch inside AB before [A|B] is assembled
+  s.JFl = s.AB;                         // 2*36*18 = 1296
+  s.FP = s.AB + 2 * FLOC * FQ;          // 30
+  s.DFP = s.FP + 3 * NFRAMES;           // 10*15*3 = 450
+  // aliases of dead regions
+  s.JR = s.G + 6 * NZ;                  // JR_MAX x 93 (ld JR_MAX) = 1674 = the G[1..3] slots, free until the later RK stages
+  s.LU = base;                          // 14 x 35
+  s.Pu = base + NC_MAX * NU;            // 35 x 23
+  s.Px = s.Pu + NU * NUT_MAX;           // 35 x 58
+  s.u0 = s.Px + NU * NX;                // 35
+  s.T1 = s.JF;                          // 35 x 58 (2030 <= 3348)
+}
+
+HD void penRelaxed(double mu, double delta, double h, double& v, double& d1, double& d2) {
+  // RelaxedBarrierPenalty (ocs2_core/src/penalties/penalties/RelaxedBarrierPenalty.cpp:37-66)
+  if (h > delta) {
+    v = -mu * log(h);
+    d1 = -mu / h;
+    d2 = mu / (h * h);
+  } else {
+    const double dh = (h - 2.0 * delta) / delta;
+    v = mu * (-log(delta) + 0.5 * dh * dh - 0.5);
+    d1 = mu * ((h - 2.0 * delta) / (delta * delta));
+    d2 = mu / (delta * delta);
+  }
+}
+HD void penPwPoly(double mu, double delta, double h, double& v, double& d1, double& d2) {
+  // PieceWisePolynomialBarrierPenalty (.../PieceWisePolynomialBarrierPenalty.cpp:37-75)
+  if (h <= 0) {
+    v = mu * (0.5 * h * h - delta * h / 2 + delta * delta / 6);
+    d1 = mu * (h - delta / 2);
+    d2 = mu;
+  } else if (h < delta) {
+    v = mu * (-h * h * h / (6 * delta) + 0.5 * h * h - delta * h / 2 + delta * delta / 6);
+    d1 = mu * (-h * h / (2 * delta) + h - delta / 2);
+    d2 = mu * (-h / delta + 1);
+  } else {
+    v = d1 = d2 = 0.0;
+  }
+}
+
+// ---- RK4 sensitivity chain on the structured Jacobian ----------------------------------------------------------------------------------
+// Gr_s = Gq_s Xq_s + Gv_s Xv_s + Gu_s with  Xq_1 = e_q, Xv_1 = e_v,  Xq_s = e_q + c_s Xv_{s-1},  Xv_s = e_v + c_s [Gr_{s-1}; e_aj].
+// In place on G: after the call G[s] holds Gr_s (6 x 93, ld 6).  One item per (stage processed sequentially by the caller, column).
+HD double xvEntry(const double* GrPrev, double c, int row, int d) {  // Xv_s(row, d), rows = generalized velocities (29)
+  double e = (d == NV + row) ? 1.0 : 0.0;
+  if (c != 0.0) e += c * (row < 6 ? GrPrev[row + 6 * d] : ((d == NX + 12 + row - 6) ? 1.0 : 0.0));
+  return e;
+}
+HD void rkPhaseChainStage(Par P, int s, double dt, double* G, double* tmp /*6 x 93*/) {
+  // c_s for the stage point x_s = x + c_s k_{s-1}
+  const double c = (s == 1 || s == 2) ? 0.5 * dt : dt;      // s = 1,2,3 <-> RK stages 2,3,4
+  const double cp = (s == 1) ? 0.0 : (s == 2 ? 0.5 * dt : 0.5 * dt);  // c of the previous stage point (stage s-1)
+  const double* Gs = G + s * 6 * NZ;
+  const double* GrP = G + (s - 1) * 6 * NZ;                    // Gr_{s-1}
+  const double* GrPP = (s >= 2) ? G + (s - 2) * 6 * NZ : nullptr;  // Gr_{s-2}
+  for (int it = P.tid; it < 6 * NZ; it += P.nt) {
+    const int r = it % 6, d = it / 6;
+    double acc = (d >= NX) ? Gs[r + 6 * d] : 0.0;  // Gu_s
+    for (int k = 0; k < NV; ++k) {
+      // Xq_s(k, d) = e_q + c * Xv_{s-1}(k, d) ;  Xv_{s-1} = e_v + cp * [Gr_{s-2}; e_aj]
+      double xq = (d == k) ? 1.0 : 0.0;
+      xq += c * xvEntry(GrPP, (s >= 2) ? cp : 0.0, k, d);
+      const double xv = xvEntry(GrP, c, k, d);
+      if (xq != 0.0) acc = fma(Gs[r + 6 * k], xq, acc);
+      if (xv != 0.0) acc = fma(Gs[r + 6 * (NV + k)], xv, acc);
+    }
+    tmp[it] = acc;
+  }
+}
+
+// A = I + sum_s w_s dk_s/dx, B = sum_s w_s dk_s/du ; b = x + sum w_s k_s - xnext  (AB is 58 x 93 column-major, ld 58)
+HD void rkPhaseAssemble(Par P, double dt, const double* x, const double* xnext, const double* G, const double* fs, double* AB, double* b) {
+  const double w[4] = {dt / 6.0, dt / 3.0, dt / 3.0, dt / 6.0};
+  const double cs[4] = {0.0, 0.5 * dt, 0.5 * dt, dt};
+  for (int it = P.tid; it < NX * NZ; it += P.nt) {
+    const int r = it % NX, d = it / NX;
+    double acc = (r == d) ? 1.0 : 0.0;
+    if (r < NV) {
+      // position rows: sum_s w_s Xv_s(r, d)
+      for (int s = 0; s < 4; ++s) acc = fma(w[s], xvEntry(s > 0 ? G + (s - 1) * 6 * NZ : nullptr, cs[s], r, d), acc);
+    } else if (r < NV + 6) {
+      for (int s = 0; s < 4; ++s) acc = fma(w[s], G[s * 6 * NZ + (r - NV) + 6 * d], acc);
+    } else {
+      if (d == NX + 12 + (r - NV - 6)) acc += dt;
+    }
+    AB[it] = acc;
+  }
+  for (int r = P.tid; r < NX; r += P.nt) {
+    double acc = x[r];
+    for (int s = 0; s < 4; ++s) acc = fma(w[s], fs[s * NX + r], acc);
+    b[r] = acc - xnext[r];
+  }
+}
+
+// ---- equality constraints C dx + D du + e (collection order of WBMpcInterface.cpp:172-181) ----------------------------------------------
+HD int constraintRowCount(const NodeIn& n) { return (n.contact[0] ? 6 : 7) + (n.contact[1] ? 6 : 7); }
+HD void conPhaseAssemble(Par P, const WbDeviceModel& m, const NodeIn& n, const double* JF, const double* FV, double* CD, double* ev) {
+  const int nc = constraintRowCount(n);
+  for (int it = P.tid; it < nc * (NZ + 1); it += P.nt) {
+    const int r = it % nc, d = it / nc;  // d == NZ -> constant term
+    int c = 0, lr = r;
+    const int n0 = n.contact[0] ? 6 : 7;
+    if (r >= n0) {
+      c = 1;
+      lr = r - n0;
+    }
+    const double* J = JF + static_cast<size_t>(c * NZ + (d < NZ ? d : 0)) * FQ;
+    const double* F = FV + FQ * c;
+    double val;
+    if (n.contact[c]) {
+      // ZeroAccelerationConstraintCppAd: Ax [p; oriErr] + Av twist + Aa acc   (EndEffectorDynamicsAccelerationsConstraint.cpp:84-146)
+      const double Av = lr < 2 ? m.gLinVelXY : (lr == 2 ? m.gLinVelZ : m.gAngVel);
+      const double Aa = lr < 2 ? m.gLinAccXY : (lr == 2 ? m.gLinAccZ : m.gAngAcc);
+      const double Ax = lr == 2 ? m.gPosZ : (lr >= 3 ? m.gOri : 0.0);
+      const double* src = d < NZ ? J : F;
+      val = Ax * src[lr] + Av * src[6 + lr] + Aa * src[12 + lr];
+    } else if (lr < 6) {
+      // ZeroWrenchConstraint
+      val = d < NZ ? ((d == NX + 6 * c + lr) ? 1.0 : 0.0) : n.u[6 * c + lr];
+    } else {
+      // SwingLegVerticalConstraintCppAd (WBMpcPreComputation.cpp:92-103)
+      const double* src = d < NZ ? J : F;
+      val = m.gPosZ * src[2] + m.gLinVelZ * src[8] + m.gLinAccZ * src[14];
+      if (d == NZ) val += -m.gLinVelZ * n.swing[c][1] - m.gLinAccZ * n.swing[c][2] - m.gPosZ * n.swing[c][0];
+    }
+    if (d < NZ) CD[r + NC_MAX * d] = val;
+    else ev[r] = val;
+  }
+}
+
+// ---- costs ------------------------------------------------------------------------------------------------------------------------------------
+// phase A: zero H, diagonal terms, gradient of the quadratic tracking cost, joint limits, friction cone (items over 93 + a few)
+HD void costPhaseInit(Par P, const WbDeviceModel& m, const NodeIn& n, double* H, double* gq, double* sc) {
+  for (int it = P.tid; it < NZ * NZ; it += P.nt) H[it] = 0.0;
+  for (int i = P.tid; i < NZ; i += P.nt) gq[i] = 0.0;
+  if (P.tid == 0) sc[0] = 0.0;
+}
+HD void costPhaseDiagonal(Par P, const WbDeviceModel& m, const NodeIn& n, double* H, double* gq, double* pv /*partial values, 96*/) {
+  // friction-cone penalty derivative (needed for the Hessian shift on every diagonal entry)
+  double fricD1[2] = {0.0, 0.0};
+  for (int c = 0; c < 2; ++c)
+    if (n.contact[c]) {
+      const double* F = n.u + 6 * c;
+      const double h = m.fricCoeff * F[2] - sqrt(F[0] * F[0] + F[1] * F[1] + m.fricReg);
+      double v, d2;
+      penRelaxed(m.fricMu, m.fricDelta, h, v, fricD1[c], d2);
+    }
+  const double shift = -(fricD1[0] + fricD1[1]) * m.fricShift;
+  for (int i = P.tid; i < NZ; i += P.nt) {
+    double val = 0.0, g = 0.0, hd = shift;
+    if (i < NX) {
+      // StateInputQuadraticCost about xNominal (arm-swing reference evaluated at the current yaw, treated as constant)
+      double xn = n.xref[i];
+      if (i >= 6 && i < NV) {
+        const int j = i - 6;
+        const double yaw = n.x[3];
+        const double gc = n.armPhase * (cos(yaw) * n.xref[NV] + sin(yaw) * n.xref[NV + 1]);
+        if (j == m.armJoint[0] || j == m.armJoint[2]) xn += -0.15 * gc;
+        if (j == m.armJoint[1] || j == m.armJoint[3]) xn += 0.15 * gc;
+      }
+      const double dx = n.x[i] - xn;
+      val = 0.5 * m.Qd[i] * dx * dx;
+      g = m.Qd[i] * dx;
+      hd += m.Qd[i];
+      if (i >= 6 && i < NV) {  // JointLimitsSoftConstraint
+        const int j = i - 6;
+        double vu, d1u, d2u, vl, d1l, d2l;
+        penPwPoly(m.jlMu, m.jlDelta, m.qhi[j] - n.x[i], vu, d1u, d2u);
+        penPwPoly(m.jlMu, m.jlDelta, n.x[i] - m.qlo[j], vl, d1l, d2l);
+        val += vu + vl;
+        g += d1l - d1u;
+        hd += d2l + d2u;
+      }
+    } else {
+      const int j = i - NX;
+      double un = 0.0;
+      const int ns = n.contact[0] + n.contact[1];
+      if (ns > 0 && (j == 2 || j == 8) && n.contact[j / 6]) un = m.mtot * 9.81 / ns;
+      const double du = n.u[j] - un;
+      val = 0.5 * m.Rd[j] * du * du;
+      g = m.Rd[j] * du;
+      hd += m.Rd[j];
+    }
+    H[i + HLD * i] += hd;
+    gq[i] += g;
+    pv[i] = val;
+  }
+}
+// friction cone blocks (items = contacts): value, gradient, 3x3 Hessian block  (FrictionForceConeConstraint.cpp:145-224)
+HD void costPhaseFriction(Par P, const WbDeviceModel& m, const NodeIn& n, double* H, double* gq, double* pv) {
+  for (int c = P.tid; c < 2; c += P.nt) {
+    pv[NZ + c] = 0.0;
+    if (!n.contact[c]) continue;
+    const double* F = n.u + 6 * c;
+    const double Ft2 = F[0] * F[0] + F[1] * F[1] + m.fricReg, Ft = sqrt(Ft2), Ft32 = Ft * Ft2;
+    const double h = m.fricCoeff * F[2] - Ft;
+    double v, d1, d2;
+    penRelaxed(m.fricMu, m.fricDelta, h, v, d1, d2);
+    const double dh[3] = {-F[0] / Ft, -F[1] / Ft, m.fricCoeff};
+    const double ddh[9] = {-(F[1] * F[1] + m.fricReg) / Ft32, F[0] * F[1] / Ft32, 0, F[0] * F[1] / Ft32, -(F[0] * F[0] + m.fricReg) / Ft32, 0, 0, 0, 0};
+    pv[NZ + c] = v;
+    const int o = NX + 6 * c;
+    for (int i = 0; i < 3; ++i) {
+      gq[o + i] += d1 * dh[i];
+      for (int j = 0; j < 3; ++j) H[(o + i) + HLD * (o + j)] += d2 * dh[i] * dh[j] + d1 * ddh[3 * i + j];
+    }
+  }
+}
+
+// Row groups of the Gauss-Newton / penalty terms: group 0/1 = foot 0/1 (swing: 18 residual rows, stance: 4 moment rows), group 2 = collision.
+// Fills JR (ld JR_MAX, weighted rows), rowCoef (gradient coefficient per weighted row) and the value contribution; returns rows via sc.
+HD int groupRows(const NodeIn& n, int g) {
+  if (g < 2) return n.contact[g] ? 4 : FQ;
+  return (n.contact[0] && n.contact[1]) ? 0 : 16;
+}
+HD void collisionPair(int r, int& a, int& b, bool& knee) {
+  // FootCollisionConstraint.cpp:112-137 ; frames: 0 fl, 1 fl_p1, 2 fl_p2, 3 fr, 4 fr_p1, 5 fr_p2, 6 ankle_l, 7 ankle_r, 8 knee_l, 9 knee_r
+  const int A[16] = {1, 1, 2, 2, 0, 0, 3, 3, 0, 8, 0, 1, 2, 3, 4, 5};
+  const int B[16] = {4, 5, 4, 5, 4, 5, 1, 2, 3, 9, 7, 7, 7, 6, 6, 6};
+  a = A[r];
+  b = B[r];
+  knee = (r == 9);
+}
+HD void costPhaseRows(Par P, const WbDeviceModel& m, const NodeIn& n, int g, const double* JF, const double* FV, const DynWs& w, const double* FP,
+                      const double* DFP, double* JR, double* rowCoef, double* rowVal) {
+  const int nr = groupRows(n, g);
+  // row scalars first (one item per row), then the 93 entries of every row
+  for (int it = P.tid; it < nr * (NZ + 1); it += P.nt) {
+    const int r = it % nr, d = it / nr;
+    double wsq = 0.0, coef = 0.0, value = 0.0, entry = 0.0;
+    if (g < 2 && !n.contact[g]) {
+      // EndEffectorDynamicsFootCost residual rows (EndEffectorDynamicsFootCost.cpp:91-124): sqrtW * impact * [0, oriErr, v, w, a, alpha]
+      const double sw = m.footSqrtW[r] * n.impact[g];
+      const double res = (r < 3) ? 0.0 : sw * FV[FQ * g + r];
+      wsq = 1.0;
+      coef = res;
+      value = 0.5 * res * res;
+      if (d < NZ) entry = (r < 3) ? 0.0 : sw * JF[static_cast<size_t>(g * NZ + d) * FQ + r];
+    } else if (g < 2) {
+      // ContactMomentXYConstraintCppAd (ContactMomentXYConstraintCppAd.cpp:86-104) under a relaxed barrier
+      const int b = m.frameBody[3 * g];
+      double Rf[9];
+      mm3(w.Rb, w.R[b], Rf);
+      const V3 fw = ld3(n.u + 6 * g), mw = ld3(n.u + 6 * g + 3);
+      const V3 lf = mtv(Rf, fw), lm = mtv(Rf, mw);
+      // h_r = sm * lm[ax] + bound * lf.z
+      const int ax = r < 2 ? 0 : 1;
+      const double sm = (r == 0 || r == 3) ? 1.0 : -1.0;
+      const double bound = (r == 0) ? -m.rect[2] : (r == 1 ? m.rect[3] : (r == 2 ? -m.rect[0] : m.rect[1]));
+      const double lmv = ax == 0 ? lm.x : lm.y;
+      const double h = sm * lmv + bound * lf.z;
+      double v, d1, d2;
+      penRelaxed(m.momMu, m.momDelta, h, v, d1, d2);
+      wsq = sqrt(d2);
+      coef = d1 / wsq;
+      value = v;
+      if (d < NZ) {
+        double dh = 0.0;
+        // tangent of the foot rotation: dRf = [omega]x Rf  -> d(Rf' a) = -Rf'(omega x a)
+        V3 om = mk(0, 0, 0);
+        bool rot = false;
+        if (d >= 3 && d < 6) {
+          // world angular direction of th_k: columns of Rb Sz
+          const int k = d - 3;
+          om = mv(w.Rb, mk(w.Sz[k], w.Sz[3 + k], w.Sz[6 + k]));
+          rot = true;
+        } else if (d >= 6 && d < NV) {
+          const int kb = d - 6 + 1;
+          if (m.subtree[kb] >> b & 1u) {
+            om = mv(w.Rb, ld3(w.S[kb] + 3));
+            rot = true;
+          }
+        }
+        if (rot) {
+          const V3 dlf = -mtv(Rf, cross(om, fw)), dlm = -mtv(Rf, cross(om, mw));
+          dh = sm * (ax == 0 ? dlm.x : dlm.y) + bound * dlf.z;
+        } else if (d >= NX + 6 * g && d < NX + 6 * g + 6) {
+          const int j = d - NX - 6 * g;
+          const V3 col = mk(Rf[3 * (j % 3)], Rf[3 * (j % 3) + 1], Rf[3 * (j % 3) + 2]);  // Rf' e_j = row j of Rf
+          if (j < 3) dh = bound * col.z;
+          else dh = sm * (ax == 0 ? col.x : col.y);
+        }
+        entry = wsq * dh;
+      }
+    } else {
+      // FootCollisionConstraint under the piecewise-polynomial barrier
+      int a, b;
+      bool knee;
+      collisionPair(r, a, b, knee);
+      const V3 dv = ld3(FP + 3 * a) - ld3(FP + 3 * b);
+      const double dist = sqrt(dot(dv, dv));
+      const double h = dist - 2.0 * (knee ? m.rKnee : m.rFoot);
+      double v, d1, d2;
+      penPwPoly(m.collMu, m.collDelta, h, v, d1, d2);
+      value = v;
+      if (d2 > 0.0) {
+        wsq = sqrt(d2);
+        coef = d1 / wsq;
+        if (d < NZ) {
+          int dl = -1;
+          if (d >= 3 && d < 6) dl = d - 3;
+          else if (d >= 6 && d < 18) dl = 3 + (d - 6);
+          if (dl >= 0) {
+            const V3 t = ld3(DFP + (a * 15 + dl) * 3) - ld3(DFP + (b * 15 + dl) * 3);
+            entry = wsq * dot(dv, t) / dist;
+          }
+        }
+      }
+    }
+    if (d < NZ) JR[r + JR_MAX * d] = entry;
+    else {
+      rowCoef[r] = coef;
+      rowVal[r] = value;
+    }
+  }
+}
+// H += JR' JR ; gq += JR' coef     (items over the Hessian)
+HD void costPhaseAccumulate(Par P, int nr, const double* JR, const double* rowCoef, double* H, double* gq) {
+  if (nr == 0) return;
+  for (int it = P.tid; it < NZ * NZ; it += P.nt) {
+    const int i = it % NZ, j = it / NZ;
+    double acc = 0.0;
+    for (int r = 0; r < nr; ++r) acc = fma(JR[r + JR_MAX * i], JR[r + JR_MAX * j], acc);
+    H[it] += acc;
+  }
+  for (int i = P.tid; i < NZ; i += P.nt) {
+    double acc = 0.0;
+    for (int r = 0; r < nr; ++r) acc = fma(JR[r + JR_MAX * i], rowCoef[r], acc);
+    gq[i] += acc;
+  }
+}
+
+// ---- projection: Eigen::FullPivLU semantics (complete pivoting; particular solution with free variables = 0; kernel basis) ----------------
+// single work item (tid 0) does the pivot search bookkeeping; the elimination is spread over the block by the caller's phases.
+HD void luPhasePivot(Par P, int nc, int k, double* LU, int* rowOf, int* colOf, int* info) {
+  if (P.tid != 0) return;
+  int pi = k, pj = k;
+  double best = -1.0;
+  for (int j = k; j < NU; ++j)
+    for (int i = k; i < nc; ++i) {
+      const double a = fabs(LU[i + NC_MAX * j]);
+      if (a > best) {
+        best = a;
+        pi = i;
+        pj = j;
+      }
+    }
+  info[0] = pi;
+  info[1] = pj;
+  info[2] = (best > 0.0);
+}
+HD void luPhaseSwap(Par P, int nc, int k, double* LU, int* rowOf, int* colOf, const int* info) {
+  const int pi = info[0], pj = info[1];
+  // row swap then column swap, each element handled by one item
+  for (int j = P.tid; j < NU; j += P.nt)
+    if (pi != k) {
+      const double t = LU[k + NC_MAX * j];
+      LU[k + NC_MAX * j] = LU[pi + NC_MAX * j];
+      LU[pi + NC_MAX * j] = t;
+    }
+  if (P.tid == 0 && pi != k) {
+    const int t = rowOf[k];
+    rowOf[k] = rowOf[pi];
+    rowOf[pi] = t;
+  }
+}
+HD void luPhaseSwapCols(Par P, int nc, int k, double* LU, int* colOf, const int* info) {
+  const int pj = info[1];
+  for (int i = P.tid; i < nc; i += P.nt)
+    if (pj != k) {
+      const double t = LU[i + NC_MAX * k];
+      LU[i + NC_MAX * k] = LU[i + NC_MAX * pj];
+      LU[i + NC_MAX * pj] = t;
+    }
+  if (P.tid == 0 && pj != k) {
+    const int t = colOf[k];
+    colOf[k] = colOf[pj];
+    colOf[pj] = t;
+  }
+}
+HD void luPhaseScale(Par P, int nc, int k, double* LU) {
+  const double piv = LU[k + NC_MAX * k];
+  for (int i = k + 1 + P.tid; i < nc; i += P.nt) LU[i + NC_MAX * k] /= piv;
+}
+HD void luPhaseUpdate(Par P, int nc, int k, double* LU) {
+  const int rows = nc - k - 1, cols = NU - k - 1;
+  for (int it = P.tid; it < rows * cols; it += P.nt) {
+    const int i = k + 1 + it % rows, j = k + 1 + it / rows;
+    LU[i + NC_MAX * j] = fma(-LU[i + NC_MAX * k], LU[k + NC_MAX * j], LU[i + NC_MAX * j]);
+  }
+}
+// Px = -D^+ C (35 x 58), u0 = -D^+ e, Pu = kernel (35 x nut); one item per right-hand side / kernel column
+HD void luPhaseSolve(Par P, int nc, const double* LU, const int* rowOf, const int* colOf, const double* CD, const double* ev, double* Pu,
+                     double* Px, double* u0) {
+  const int nut = NU - nc;
+  for (int it = P.tid; it < NX + 1 + nut; it += P.nt) {
+    double y[NC_MAX];
+    if (it <= NX) {
+      // right-hand side column (permuted rows), forward then backward substitution on the leading nc x nc blocks
+      for (int i = 0; i < nc; ++i) y[i] = (it < NX) ? CD[rowOf[i] + NC_MAX * it] : ev[rowOf[i]];
+      for (int k = 0; k < nc; ++k)
+        for (int i = k + 1; i < nc; ++i) y[i] = fma(-LU[i + NC_MAX * k], y[k], y[i]);
+      for (int k = nc - 1; k >= 0; --k) {
+        y[k] /= LU[k + NC_MAX * k];
+        for (int i = 0; i < k; ++i) y[i] = fma(-LU[i + NC_MAX * k], y[k], y[i]);
+      }
+      double* out = (it < NX) ? Px + static_cast<size_t>(NU) * it : u0;
+      for (int i = 0; i < NU; ++i) out[i] = 0.0;
+      for (int i = 0; i < nc; ++i) out[colOf[i]] = -y[i];
+    } else {
+      const int kk = it - NX - 1;
+      for (int i = 0; i < nc; ++i) y[i] = -LU[i + NC_MAX * (nc + kk)];
+      for (int k = nc - 1; k >= 0; --k) {
+        y[k] /= LU[k + NC_MAX * k];
+        for (int i = 0; i < k; ++i) y[i] = fma(-LU[i + NC_MAX * k], y[k], y[i]);
+      }
+      double* out = Pu + static_cast<size_t>(NU) * kk;
+      for (int i = 0; i < NU; ++i) out[i] = 0.0;
+      for (int i = 0; i < nc; ++i) out[colOf[i]] = y[i];
+      out[colOf[nc + kk]] = 1.0;
+    }
+  }
+}
+
+}  // namespace b200sqp
