@@ -1,0 +1,64 @@
+"""Device-math check without a GPU: the __host__ __device__ phase functions of K1/K3 executed on the host by the development
+harness (tests/emu) against the oracle.  This validates the kernels' arithmetic and the barrier placement (work items of every
+phase are visited in reverse order); the GPU tests (-m gpu) validate the real launches through the C ABI."""
+import numpy as np
+import pytest
+
+import emu_lib as emu
+import oracle_lib as orc
+from test_oracle_wb import rand_input, rand_state
+from wb_humanoid_mpc_b200 import abi, model_loader
+
+
+@pytest.fixture(scope="module")
+def model():
+    return model_loader.load_packaged_model()
+
+
+@pytest.fixture(scope="module")
+def wb(model):
+    return orc.WbOracle(model)
+
+
+def rel(a, b):
+    return np.max(np.abs(a - b)) / max(1e-12, np.max(np.abs(b))) if b.size else 0.0
+
+
+def test_flow_map_and_base_acceleration_jacobian(model, wb):
+    rng = np.random.default_rng(0)
+    for _ in range(3):
+        x, u = rand_state(model, rng), rand_input(model, rng)
+        f, A, B = wb.flow_map_lin(x, u)
+        xd, G = emu.dyn(wb.desc, x, u, True)
+        assert np.max(np.abs(xd - f)) < 1e-12
+        assert rel(G, np.hstack([A[29:35], B[29:35]])) < 1e-11
+        xd2, _ = emu.dyn(wb.desc, x, u, False)
+        assert np.max(np.abs(xd2 - f)) < 1e-12
+
+
+@pytest.mark.parametrize("contact", [(1, 1), (1, 0), (0, 1), (0, 0)])
+def test_lq_node_blocks_and_projection(model, wb, contact):
+    rng = np.random.default_rng(sum(contact) + 3)
+    x, u = rand_state(model, rng, 0.5), rand_input(model, rng)
+    u[2] += 100
+    u[8] += 100
+    xn = x + rng.uniform(-0.01, 0.01, 58)
+    xref = np.array(model["x_init"])
+    xref[29:31] = [0.4, 0.1]
+    swing = np.array([[0.03, 0.2, -1.0], [0.05, -0.1, 0.5]])
+    impact, arm, dt = [0.7, 0.4], 0.3, 0.035
+    wb.set_nodes(np.array([contact, contact], dtype=np.uint8), np.stack([swing, swing]), np.array([impact, impact]), np.array([arm, arm]),
+                 np.stack([xref, xref]))
+    st = abi.default_settings(model, sqp_iteration=1)
+    wb.sqp(np.array([0.0, dt]), np.array([0, 0], dtype=np.uint8), x, np.stack([x, xn]), u[None], st, keep_raw=True)
+    raw = wb.last_raw_blocks(2)[0]
+    e = emu.lq_node(wb.desc, x, u, xn, xref, dt, contact, swing, impact, arm)
+    assert e["raw"]["nc"] == raw["nc"] and e["nut"] == 35 - raw["nc"]
+    for k in ["A", "B", "b", "Q", "S", "R", "q", "r", "C", "D", "e"]:
+        assert rel(e["raw"][k], raw[k]) < 1e-10, k
+    assert abs(e["raw"]["c"] - raw["c"]) < 1e-10 * max(1.0, abs(raw["c"]))
+    r = e["raw"]
+    assert np.abs(r["D"] @ e["Pu"]).max() < 1e-10 and np.abs(r["D"] @ e["Px"] + r["C"]).max() < 1e-9 and np.abs(r["D"] @ e["u0"] + r["e"]).max() < 1e-9
+    pr = orc.change_of_input_variables(r["A"], r["B"], r["b"], r["Q"], r["S"], r["R"], r["q"], r["r"], r["c"], e["Pu"], e["Px"], e["u0"])
+    for k in ["A", "B", "b", "Q", "S", "R", "q", "r"]:
+        assert rel(e[k], pr[k]) < 1e-10, k

@@ -170,10 +170,11 @@ HD void rkPhaseAssemble(Par P, double dt, const double* x, const double* xnext, 
 
 // ---- equality constraints C dx + D du + e (collection order of WBMpcInterface.cpp:172-181) ----------------------------------------------
 HD int constraintRowCount(const NodeIn& n) { return (n.contact[0] ? 6 : 7) + (n.contact[1] ? 6 : 7); }
-HD void conPhaseAssemble(Par P, const WbDeviceModel& m, const NodeIn& n, const double* JF, const double* FV, double* CD, double* ev) {
+HD void conPhaseAssemble(Par P, const WbDeviceModel& m, const NodeIn& n, const double* JF, const double* FV, double* CD, double* ev,
+                         bool valuesOnly = false) {
   const int nc = constraintRowCount(n);
-  for (int it = P.tid; it < nc * (NZ + 1); it += P.nt) {
-    const int r = it % nc, d = it / nc;  // d == NZ -> constant term
+  for (int it = P.tid; it < nc * (valuesOnly ? 1 : NZ + 1); it += P.nt) {
+    const int r = it % nc, d = valuesOnly ? NZ : it / nc;  // d == NZ -> constant term
     int c = 0, lr = r;
     const int n0 = n.contact[0] ? 6 : 7;
     if (r >= n0) {
@@ -211,6 +212,7 @@ HD void costPhaseInit(Par P, const WbDeviceModel& m, const NodeIn& n, double* H,
   for (int i = P.tid; i < NZ; i += P.nt) gq[i] = 0.0;
   if (P.tid == 0) sc[0] = 0.0;
 }
+template <bool DERIV = true>
 HD void costPhaseDiagonal(Par P, const WbDeviceModel& m, const NodeIn& n, double* H, double* gq, double* pv /*partial values, 96*/) {
   // friction-cone penalty derivative (needed for the Hessian shift on every diagonal entry)
   double fricD1[2] = {0.0, 0.0};
@@ -257,12 +259,15 @@ HD void costPhaseDiagonal(Par P, const WbDeviceModel& m, const NodeIn& n, double
       g = m.Rd[j] * du;
       hd += m.Rd[j];
     }
-    H[i + HLD * i] += hd;
-    gq[i] += g;
+    if (DERIV) {
+      H[i + HLD * i] += hd;
+      gq[i] += g;
+    }
     pv[i] = val;
   }
 }
 // friction cone blocks (items = contacts): value, gradient, 3x3 Hessian block  (FrictionForceConeConstraint.cpp:145-224)
+template <bool DERIV = true>
 HD void costPhaseFriction(Par P, const WbDeviceModel& m, const NodeIn& n, double* H, double* gq, double* pv) {
   for (int c = P.tid; c < 2; c += P.nt) {
     pv[NZ + c] = 0.0;
@@ -275,6 +280,7 @@ HD void costPhaseFriction(Par P, const WbDeviceModel& m, const NodeIn& n, double
     const double dh[3] = {-F[0] / Ft, -F[1] / Ft, m.fricCoeff};
     const double ddh[9] = {-(F[1] * F[1] + m.fricReg) / Ft32, F[0] * F[1] / Ft32, 0, F[0] * F[1] / Ft32, -(F[0] * F[0] + m.fricReg) / Ft32, 0, 0, 0, 0};
     pv[NZ + c] = v;
+    if (!DERIV) continue;
     const int o = NX + 6 * c;
     for (int i = 0; i < 3; ++i) {
       gq[o + i] += d1 * dh[i];
@@ -298,11 +304,11 @@ HD void collisionPair(int r, int& a, int& b, bool& knee) {
   knee = (r == 9);
 }
 HD void costPhaseRows(Par P, const WbDeviceModel& m, const NodeIn& n, int g, const double* JF, const double* FV, const DynWs& w, const double* FP,
-                      const double* DFP, double* JR, double* rowCoef, double* rowVal) {
+                      const double* DFP, double* JR, double* rowCoef, double* rowVal, bool valuesOnly = false) {
   const int nr = groupRows(n, g);
-  // row scalars first (one item per row), then the 93 entries of every row
-  for (int it = P.tid; it < nr * (NZ + 1); it += P.nt) {
-    const int r = it % nr, d = it / nr;
+  // one item per (row, entry); entry == NZ carries the row scalars
+  for (int it = P.tid; it < nr * (valuesOnly ? 1 : NZ + 1); it += P.nt) {
+    const int r = it % nr, d = valuesOnly ? NZ : it / nr;
     double wsq = 0.0, coef = 0.0, value = 0.0, entry = 0.0;
     if (g < 2 && !n.contact[g]) {
       // EndEffectorDynamicsFootCost residual rows (EndEffectorDynamicsFootCost.cpp:91-124): sqrtW * impact * [0, oriErr, v, w, a, alpha]
@@ -498,4 +504,28 @@ HD void luPhaseSolve(Par P, int nc, const double* LU, const int* rowOf, const in
   }
 }
 
+}  // namespace b200sqp
+
+namespace b200sqp {
+// workspace of the value-only rollout kernel (K3)
+struct RoWs {
+  DynWs* dyn;
+  double *fs, *xs, *FV, *FP, *pv, *rowCoef, *rowVal, *ev, *sc, *xa, *xna, *ua;
+};
+HD size_t roWsDoubles() { return (sizeof(DynWs) + 7) / 8 + 4 * NX + NX + 2 * FQ + 3 * NFRAMES + 96 + 2 * JR_MAX + NC_MAX + 8 + 2 * NX + NU + 5; }
+HD void roWsMap(double* base, RoWs& r) {
+  r.dyn = reinterpret_cast<DynWs*>(base);
+  r.fs = base + (sizeof(DynWs) + 7) / 8;
+  r.xs = r.fs + 4 * NX;
+  r.FV = r.xs + NX;
+  r.FP = r.FV + 2 * FQ;
+  r.pv = r.FP + 3 * NFRAMES;
+  r.rowCoef = r.pv + 96;
+  r.rowVal = r.rowCoef + JR_MAX;
+  r.ev = r.rowVal + JR_MAX;
+  r.sc = r.ev + NC_MAX;
+  r.xa = r.sc + 8;
+  r.xna = r.xa + NX;
+  r.ua = r.xna + NX;
+}
 }  // namespace b200sqp

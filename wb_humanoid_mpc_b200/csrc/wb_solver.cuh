@@ -1,0 +1,479 @@
+// Device kernels of the whole-body SQP iteration and the per-handle device state.
+//   K1 lq_kernel        one CTA per (instance, shooting node): LQ approximation + projection   (SqpSolver::setupQuadraticSubproblem)
+//   K2 riccati_kernel   riccati.cuh                                                            (HpipmInterface::solve)
+//   K4a remap_kernel    du = Pu dut + Px dx + u0, K = Pu Kt + Px, Armijo / norm partial sums    (remapProjectedInput/Gain, armijoDescentMetric)
+//   K3 rollout_kernel   one CTA per (instance, node): value-only RK4 defect, cost, constraints at x + alpha dx   (computePerformance)
+//   K4b reduce kernels  PerformanceIndex sums, FilterLinesearch::acceptStep, step application, checkConvergence
+#pragma once
+#include <cstdint>
+
+#include "riccati.cuh"
+#include "wb_host.cuh"
+#include "wb_lq.cuh"
+
+namespace b200sqp {
+
+constexpr int LQ_THREADS = 256;
+constexpr int RO_THREADS = 128;
+constexpr double kWeakEps = 1e-9;  // numeric_traits::weakEpsilon (ocs2_core/include/ocs2_core/NumericTraits.h:51)
+
+enum InstD { I_BASE_MERIT = 0, I_BASE_COST, I_BASE_DYN, I_BASE_EQ, I_ARMIJO, I_DXN, I_DUN, I_ALPHA, I_STEP, I_STEPTYPE, I_NEW_MERIT, I_NEW_COST,
+             I_NEW_DYN, I_NEW_EQ, I_ND = 16 };
+enum InstF { F_CONVERGED = 0, F_LSDONE, F_ITER, F_STATUS, F_CONVCODE, F_NF = 8 };
+
+struct WbDev {
+  int B, N;  // N intervals, N+1 nodes
+  const WbDeviceModel* model;
+  // instance inputs
+  double *x0, *x, *u, *t, *swing, *impact, *arm, *xref;
+  uint8_t *event, *contact;
+  // QP (nx = 58, nu_max = 23)
+  QpDeviceView qp;
+  double *Pu, *Px, *u0p;
+  double* du;     // remapped input step [B][N][35]
+  double* Kre;    // remapped gains [B][N][35*58] or null
+  double* perfNode;  // [B][N+1][4] baseline
+  double* lsNode;    // [B][N+1][4] trial / partial sums
+  double* inst;      // [B][I_ND]
+  int* flags;        // [B][F_NF]
+  int* pending;      // number of instances whose line search is still running
+  double* raw;       // optional [B][N][rawPer]
+  long long rawPer;
+  b200sqp_iter_log* log;  // [B][maxIter]
+  int maxIter;
+  b200sqp_settings st;
+};
+
+__device__ __forceinline__ void loadNode(const WbDev& d, int b, int k, NodeIn& n) {
+  const size_t node = static_cast<size_t>(b) * (d.N + 1) + k;
+  n.xref = d.xref + node * NX;
+  n.event = d.event[node];
+  n.terminal = (k == d.N);
+  n.contact[0] = d.contact[2 * node];
+  n.contact[1] = d.contact[2 * node + 1];
+  for (int c = 0; c < 2; ++c) {
+    for (int j = 0; j < 3; ++j) n.swing[c][j] = d.swing[(2 * node + c) * 3 + j];
+    n.impact[c] = d.impact[2 * node + c];
+  }
+  n.armPhase = d.arm[node];
+  n.dt = 0.0;
+  if (k < d.N) {
+    const double ts = d.t[node] + (d.event[node] == 2 ? kWeakEps : 0.0);
+    const double te = d.t[node + 1] - (d.event[node + 1] == 1 ? kWeakEps : 0.0);
+    n.dt = te - ts;
+  }
+}
+
+#define PHASE(...)                                   \
+  {                                                  \
+    const Par P{static_cast<int>(threadIdx.x), static_cast<int>(blockDim.x)}; \
+    __VA_ARGS__                                      \
+  }                                                  \
+  __syncthreads();
+
+__global__ void __launch_bounds__(LQ_THREADS, 1) lq_kernel(WbDev d) {
+  extern __shared__ double smem[];
+  const int k = blockIdx.x, b = blockIdx.y;
+  if (d.flags[b * F_NF + F_CONVERGED]) return;
+  const WbDeviceModel& m = *d.model;
+  const int N = d.N;
+  const size_t node = static_cast<size_t>(b) * (N + 1) + k, stage = static_cast<size_t>(b) * N + k;
+  NodeIn n;
+  loadNode(d, b, k, n);
+  n.x = d.x + node * NX;
+  double* perf = d.perfNode + node * 4;
+  if (k == N) {
+    // setupTerminalNode: final cost 1/2 (x - xref)' Qf (x - xref)   (Transcription.cpp:125-154, HumanoidCostConstraintFactory.cpp:218-228)
+    double* Q = const_cast<double*>(d.qp.Q) + node * NX * NX;
+    double* q = const_cast<double*>(d.qp.q) + node * NX;
+    for (int i = threadIdx.x; i < NX * NX; i += blockDim.x) Q[i] = (i % NX == i / NX) ? m.Qfd[i % NX] : 0.0;
+    double part = 0.0;
+    for (int i = threadIdx.x; i < NX; i += blockDim.x) {
+      const double dx = n.x[i] - n.xref[i];
+      q[i] = m.Qfd[i] * dx;
+      part += 0.5 * m.Qfd[i] * dx * dx;
+    }
+    smem[threadIdx.x] = part;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      double c = 0.0;
+      for (int i = 0; i < blockDim.x; ++i) c += smem[i];
+      perf[0] = c;
+      perf[1] = perf[2] = perf[3] = 0.0;
+    }
+    return;
+  }
+  n.u = d.u + stage * NU;
+  n.xnext = d.x + (node + 1) * NX;
+  NodeOut out;
+  out.A = d.qp.A ? const_cast<double*>(d.qp.A) + stage * NX * NX : nullptr;
+  out.Bt = const_cast<double*>(d.qp.Bm) + stage * NX * NUT_MAX;
+  out.b = const_cast<double*>(d.qp.b) + stage * NX;
+  out.Q = const_cast<double*>(d.qp.Q) + node * NX * NX;
+  out.St = const_cast<double*>(d.qp.S) + stage * NUT_MAX * NX;
+  out.Rt = const_cast<double*>(d.qp.R) + stage * NUT_MAX * NUT_MAX;
+  out.q = const_cast<double*>(d.qp.q) + node * NX;
+  out.rt = const_cast<double*>(d.qp.r) + stage * NUT_MAX;
+  out.Pu = d.Pu + stage * NU * NUT_MAX;
+  out.Px = d.Px + stage * NU * NX;
+  out.u0 = d.u0p + stage * NU;
+  out.nut = const_cast<int*>(d.qp.nu) + stage;
+  out.perf = perf;
+  out.raw = d.raw ? d.raw + stage * d.rawPer : nullptr;
+  if (n.event == 1) {
+    // setupEventNode: identity jump map, no cost, no input (Transcription.cpp:156-192)
+    double part = 0.0;
+    for (int i = threadIdx.x; i < NX * NX; i += blockDim.x) {
+      out.A[i] = (i % NX == i / NX) ? 1.0 : 0.0;
+      out.Q[i] = 0.0;
+    }
+    for (int i = threadIdx.x; i < NX; i += blockDim.x) {
+      const double df = n.x[i] - n.xnext[i];
+      out.b[i] = df;
+      out.q[i] = 0.0;
+      part += df * df;
+    }
+    smem[threadIdx.x] = part;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      double c = 0.0;
+      for (int i = 0; i < blockDim.x; ++i) c += smem[i];
+      perf[0] = 0.0;
+      perf[1] = c;
+      perf[2] = perf[3] = 0.0;
+      *out.nut = 0;
+    }
+    if (out.raw) {
+      for (long long i = threadIdx.x; i < d.rawPer; i += blockDim.x) out.raw[i] = 0.0;
+      __syncthreads();
+      for (int i = threadIdx.x; i < NX; i += blockDim.x) {
+        out.raw[i + NX * i] = 1.0;
+        out.raw[NX * NX + NX * NU + i] = n.x[i] - n.xnext[i];
+      }
+    }
+    return;
+  }
+  LqWs s;
+  lqWsMap(smem, s);
+#include "wb_node_body.inc"
+}
+
+// ---- K4a: remap the projected QP solution, Armijo metric and norms (one CTA per (instance, stage)) --------------------------------------------
+__global__ void __launch_bounds__(128) remap_kernel(WbDev d) {
+  const int k = blockIdx.x, b = blockIdx.y;
+  if (d.flags[b * F_NF + F_CONVERGED]) return;
+  const int N = d.N;
+  const size_t node = static_cast<size_t>(b) * (N + 1) + k, stage = static_cast<size_t>(b) * N + k;
+  __shared__ double red[128][3];
+  const int nut = d.qp.nu[stage];
+  const double* dx = d.qp.dx + node * NX;
+  const double* dut = d.qp.du + stage * NUT_MAX;
+  double* du = d.du + stage * NU;
+  double arm = 0.0, dxn = 0.0, dun = 0.0;
+  for (int i = threadIdx.x; i < NU; i += blockDim.x) {
+    double s = 0.0;
+    if (nut > 0) {
+      // remapProjectedInput (ocs2_oc/src/multiple_shooting/Helpers.cpp:38-48)
+      s = d.u0p[stage * NU + i];
+      const double* Pu = d.Pu + stage * NU * NUT_MAX;
+      const double* Px = d.Px + stage * NU * NX;
+      for (int j = 0; j < nut; ++j) s = fma(Pu[i + NU * j], dut[j], s);
+      for (int j = 0; j < NX; ++j) s = fma(Px[i + NU * j], dx[j], s);
+    }
+    du[i] = s;
+    dun = fma(s, s, dun);
+  }
+  for (int i = threadIdx.x; i < NX; i += blockDim.x) {
+    arm = fma(d.qp.q[node * NX + i], dx[i], arm);
+    dxn = fma(dx[i], dx[i], dxn);
+    if (k == N - 1) {  // terminal node terms
+      const double dxe = d.qp.dx[(node + 1) * NX + i];
+      arm = fma(d.qp.q[(node + 1) * NX + i], dxe, arm);
+      dxn = fma(dxe, dxe, dxn);
+    }
+  }
+  for (int i = threadIdx.x; i < nut; i += blockDim.x) arm = fma(d.qp.r[stage * NUT_MAX + i], dut[i], arm);
+  if (d.Kre && nut > 0) {
+    // remapProjectedGain (Helpers.cpp:50-58): K = Pu Kt + Px
+    const double* Pu = d.Pu + stage * NU * NUT_MAX;
+    const double* Px = d.Px + stage * NU * NX;
+    const double* Kt = d.qp.K + stage * NUT_MAX * NX;
+    double* Ko = d.Kre + stage * NU * NX;
+    for (int it = threadIdx.x; it < NU * NX; it += blockDim.x) {
+      const int i = it % NU, j = it / NU;
+      double s = Px[it];
+      for (int l = 0; l < nut; ++l) s = fma(Pu[i + NU * l], Kt[l + NUT_MAX * j], s);
+      Ko[it] = s;
+    }
+  } else if (d.Kre) {
+    for (int it = threadIdx.x; it < NU * NX; it += blockDim.x) d.Kre[stage * NU * NX + it] = 0.0;
+  }
+  red[threadIdx.x][0] = arm;
+  red[threadIdx.x][1] = dxn;
+  red[threadIdx.x][2] = dun;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double a = 0, x2 = 0, u2 = 0;
+    for (int i = 0; i < blockDim.x; ++i) {
+      a += red[i][0];
+      x2 += red[i][1];
+      u2 += red[i][2];
+    }
+    double* o = d.lsNode + node * 4;
+    o[0] = a;
+    o[1] = x2;
+    o[2] = u2;
+  }
+}
+
+// ---- K4b: per-instance reductions and line-search logic (one CTA per instance) ------------------------------------------------------------
+__device__ __forceinline__ double blockSum(double v, double* sh) {
+  sh[threadIdx.x] = v;
+  __syncthreads();
+  for (int s = blockDim.x / 2; s > 0; s >>= 1) {
+    if (threadIdx.x < s) sh[threadIdx.x] += sh[threadIdx.x + s];
+    __syncthreads();
+  }
+  const double r = sh[0];
+  __syncthreads();
+  return r;
+}
+
+// mode 0: baseline PerformanceIndex from perfNode (after K1).  mode 1: Armijo/norm sums from lsNode (after remap) + line-search init.
+__global__ void __launch_bounds__(128) prep_kernel(WbDev d, int mode) {
+  const int b = blockIdx.x;
+  if (d.flags[b * F_NF + F_CONVERGED]) return;
+  __shared__ double sh[128];
+  const int N = d.N;
+  const double* src = (mode == 0 ? d.perfNode : d.lsNode) + static_cast<size_t>(b) * (N + 1) * 4;
+  double a0 = 0, a1 = 0, a2 = 0;
+  const int cnt = (mode == 0) ? N + 1 : N;
+  for (int k = threadIdx.x; k < cnt; k += blockDim.x) {
+    a0 += src[4 * k];
+    a1 += src[4 * k + 1];
+    a2 += src[4 * k + 2];
+  }
+  double x0d = 0.0;
+  if (mode == 0)
+    for (int i = threadIdx.x; i < NX; i += blockDim.x) {
+      const double df = d.x0[b * NX + i] - d.x[static_cast<size_t>(b) * (N + 1) * NX + i];
+      x0d = fma(df, df, x0d);
+    }
+  a0 = blockSum(a0, sh);
+  a1 = blockSum(a1, sh);
+  a2 = blockSum(a2, sh);
+  x0d = blockSum(x0d, sh);
+  if (mode == 0) {
+    // delta_x0 = initState - x[0]  (SqpSolver.cpp:236)
+    for (int i = threadIdx.x; i < NX; i += blockDim.x)
+      const_cast<double*>(d.qp.dx0)[b * NX + i] = d.x0[b * NX + i] - d.x[static_cast<size_t>(b) * (N + 1) * NX + i];
+  }
+  if (threadIdx.x == 0) {
+    double* in = d.inst + b * I_ND;
+    if (mode == 0) {
+      in[I_BASE_COST] = a0;
+      in[I_BASE_DYN] = a1 + x0d;
+      in[I_BASE_EQ] = a2;
+      in[I_BASE_MERIT] = a0;  // merit = cost + Lagrangians (both zero here)
+    } else {
+      in[I_ARMIJO] = a0;
+      in[I_DXN] = sqrt(a1);
+      in[I_DUN] = sqrt(a2);
+      in[I_ALPHA] = 1.0;
+      in[I_STEP] = 0.0;
+      d.flags[b * F_NF + F_LSDONE] = 0;
+      if (d.qp.status[b]) {  // QP failed: no step, report through status
+        d.flags[b * F_NF + F_STATUS] = 1;
+      }
+    }
+  }
+}
+
+__global__ void __launch_bounds__(RO_THREADS) rollout_kernel(WbDev d) {
+  extern __shared__ double smem[];
+  const int k = blockIdx.x, b = blockIdx.y;
+  if (d.flags[b * F_NF + F_CONVERGED] || d.flags[b * F_NF + F_LSDONE]) return;
+  const WbDeviceModel& m = *d.model;
+  const int N = d.N;
+  const size_t node = static_cast<size_t>(b) * (N + 1) + k, stage = static_cast<size_t>(b) * N + k;
+  const double alpha = d.inst[b * I_ND + I_ALPHA];
+  RoWs r;
+  roWsMap(smem, r);
+  NodeIn n;
+  loadNode(d, b, k, n);
+  double* perfOut = d.lsNode + node * 4;
+  for (int i = threadIdx.x; i < NX; i += blockDim.x) {
+    r.xa[i] = fma(alpha, d.qp.dx[node * NX + i], d.x[node * NX + i]);
+    if (k < N) r.xna[i] = fma(alpha, d.qp.dx[(node + 1) * NX + i], d.x[(node + 1) * NX + i]);
+  }
+  if (k < N)
+    for (int i = threadIdx.x; i < NU; i += blockDim.x) r.ua[i] = fma(alpha, d.du[stage * NU + i], d.u[stage * NU + i]);
+  __syncthreads();
+  n.x = r.xa;
+  n.u = r.ua;
+  n.xnext = r.xna;
+  if (k == N || n.event == 1) {
+    double part = 0.0;
+    for (int i = threadIdx.x; i < NX; i += blockDim.x) {
+      if (k == N) {
+        const double dx = r.xa[i] - n.xref[i];
+        part += 0.5 * m.Qfd[i] * dx * dx;
+      } else {
+        const double df = r.xa[i] - r.xna[i];
+        part += df * df;
+      }
+    }
+    r.pv[threadIdx.x] = 0.0;
+    __syncthreads();
+    double* red = r.fs;  // 4*58 >= 128 doubles
+    red[threadIdx.x] = part;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      double c = 0.0;
+      for (int i = 0; i < blockDim.x; ++i) c += red[i];
+      perfOut[0] = (k == N) ? c : 0.0;
+      perfOut[1] = (k == N) ? 0.0 : c;
+      perfOut[2] = 0.0;
+    }
+    return;
+  }
+#include "wb_rollout_body.inc"
+}
+
+// FilterLinesearch::acceptStep + takeStep bookkeeping + checkConvergence for one instance (SqpSolver.cpp:484-602, FilterLinesearch.cpp:34-57)
+__global__ void __launch_bounds__(256) accept_kernel(WbDev d) {
+  const int b = blockIdx.x;
+  int* fl = d.flags + b * F_NF;
+  if (fl[F_CONVERGED] || fl[F_LSDONE]) return;
+  __shared__ double sh[256];
+  __shared__ int decision;  // 0 continue, 1 accepted, 2 give up (zero step)
+  const int N = d.N;
+  double* in = d.inst + b * I_ND;
+  const double alpha = in[I_ALPHA];
+  const double* src = d.lsNode + static_cast<size_t>(b) * (N + 1) * 4;
+  double a0 = 0, a1 = 0, a2 = 0;
+  for (int k = threadIdx.x; k <= N; k += blockDim.x) {
+    a0 += src[4 * k];
+    a1 += src[4 * k + 1];
+    a2 += src[4 * k + 2];
+  }
+  double x0d = 0.0;
+  for (int i = threadIdx.x; i < NX; i += blockDim.x) {
+    // initState - xNew[0] with xNew[0] = x[0] + alpha (initState - x[0])
+    const double df = (1.0 - alpha) * d.qp.dx0[b * NX + i];
+    x0d = fma(df, df, x0d);
+  }
+  a0 = blockSum(a0, sh);
+  a1 = blockSum(a1, sh);
+  a2 = blockSum(a2, sh);
+  x0d = blockSum(x0d, sh);
+  const b200sqp_settings& st = d.st;
+  if (threadIdx.x == 0) {
+    const double cost = a0, dyn = a1 + x0d, eq = a2, merit = a0;
+    const double g0 = sqrt(in[I_BASE_DYN] + in[I_BASE_EQ]), g1 = sqrt(dyn + eq);
+    const double arm = alpha * in[I_ARMIJO];
+    bool acc;
+    int type;
+    if (fl[F_STATUS]) {  // QP failure: never accept
+      acc = false;
+      type = 0;
+    } else if (g1 > st.g_max) {
+      acc = g1 < (1.0 - st.gamma_c) * g0;
+      type = 1;  // CONSTRAINT
+    } else if (g1 < st.g_min && g0 < st.g_min && arm < 0.0) {
+      acc = merit < in[I_BASE_MERIT] + st.armijo_factor * arm;
+      type = 3;  // COST
+    } else {
+      acc = merit < in[I_BASE_MERIT] - st.gamma_c * g0 || g1 < (1.0 - st.gamma_c) * g0;
+      type = 2;  // DUAL
+    }
+    int dec = 0;
+    if (acc) {
+      dec = 1;
+      in[I_STEP] = alpha;
+      in[I_STEPTYPE] = type;
+      in[I_NEW_MERIT] = merit;
+      in[I_NEW_COST] = cost;
+      in[I_NEW_DYN] = dyn;
+      in[I_NEW_EQ] = eq;
+    } else {
+      const double next = alpha * st.alpha_decay;
+      if (fl[F_STATUS] || (next * in[I_DXN] < st.delta_tol && next * in[I_DUN] < st.delta_tol) || !(next >= st.alpha_min)) {
+        dec = 2;
+        in[I_STEP] = 0.0;
+        in[I_STEPTYPE] = 4;  // ZERO
+        in[I_NEW_MERIT] = in[I_BASE_MERIT];
+        in[I_NEW_COST] = in[I_BASE_COST];
+        in[I_NEW_DYN] = in[I_BASE_DYN];
+        in[I_NEW_EQ] = in[I_BASE_EQ];
+      } else {
+        in[I_ALPHA] = next;
+      }
+    }
+    decision = dec;
+  }
+  __syncthreads();
+  if (decision == 0) return;
+  if (decision == 1) {  // x <- x + alpha dx, u <- u + alpha du
+    for (size_t i = threadIdx.x; i < static_cast<size_t>(N + 1) * NX; i += blockDim.x) {
+      const size_t g = static_cast<size_t>(b) * (N + 1) * NX + i;
+      d.x[g] = fma(alpha, d.qp.dx[g], d.x[g]);
+    }
+    for (size_t i = threadIdx.x; i < static_cast<size_t>(N) * NU; i += blockDim.x) {
+      const size_t g = static_cast<size_t>(b) * N * NU + i;
+      d.u[g] = fma(alpha, d.du[g], d.u[g]);
+    }
+  }
+  if (threadIdx.x == 0) {
+    fl[F_LSDONE] = 1;
+    atomicSub(d.pending, 1);
+    const int iter = fl[F_ITER];
+    const double step = in[I_STEP];
+    const double dxn = step * in[I_DXN], dun = step * in[I_DUN];
+    // checkConvergence (SqpSolver.cpp:583-602)
+    int conv = 0;
+    if (iter + 1 >= st.sqp_iteration) conv = 1;  // ITERATIONS
+    else if (step < st.alpha_min) conv = 2;        // STEPSIZE
+    else if (fabs(in[I_NEW_MERIT] - in[I_BASE_MERIT]) < st.cost_tol && sqrt(in[I_NEW_DYN] + in[I_NEW_EQ]) < st.g_min) conv = 3;  // METRICS
+    else if (dxn < st.delta_tol && dun < st.delta_tol) conv = 4;  // PRIMAL
+    if (iter < d.maxIter) {
+      b200sqp_iter_log& L = d.log[static_cast<size_t>(b) * d.maxIter + iter];
+      L.base_merit = in[I_BASE_MERIT];
+      L.base_cost = in[I_BASE_COST];
+      L.base_dyn_sse = in[I_BASE_DYN];
+      L.base_eq_sse = in[I_BASE_EQ];
+      L.merit = in[I_NEW_MERIT];
+      L.cost = in[I_NEW_COST];
+      L.dyn_sse = in[I_NEW_DYN];
+      L.eq_sse = in[I_NEW_EQ];
+      L.step_size = step;
+      L.step_type = in[I_STEPTYPE];
+      L.dx_norm = dxn;
+      L.du_norm = dun;
+      L.armijo = in[I_ARMIJO];
+      L.convergence = conv;
+      L.pad[0] = L.pad[1] = 0.0;
+    }
+    fl[F_ITER] = iter + 1;
+    fl[F_CONVCODE] = conv;
+    if (conv) fl[F_CONVERGED] = 1;
+  }
+}
+
+__global__ void __launch_bounds__(256) count_active_kernel(WbDev d) {
+  // pending = number of instances that have not converged (they enter the next line search)
+  __shared__ int cnt[256];
+  int c = 0;
+  for (int b = threadIdx.x; b < d.B; b += blockDim.x) c += !d.flags[b * F_NF + F_CONVERGED];
+  cnt[threadIdx.x] = c;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    int t = 0;
+    for (int i = 0; i < blockDim.x; ++i) t += cnt[i];
+    *d.pending = t;
+  }
+}
+
+#undef PHASE
+
+}  // namespace b200sqp

@@ -1,0 +1,125 @@
+"""Host-side mirror of ocs2::SqpSolver for a batch of whole-body MPC instances, over the C ABI (no torch types involved).
+
+Reference interface: lib/ocs2_ros2/ocs2_sqp/ocs2_sqp/include/ocs2_sqp/SqpSolver.h:60-103
+    SqpSolver(settings, optimalControlProblem, initializer)  -> B200SqpSolver(model, settings)
+    run(initTime, initState, initMode, finalTime)            -> run(instances)   (instances built by references.build_instance)
+    primalSolution(finalTime)                                -> primal_solution()
+    getIterationsLog()                                       -> iterations_log()
+    getBenchmarks()                                          -> benchmarks()
+Error behaviour follows the reference: a failed QP raises (SqpSolver.cpp:306-308 throws std::runtime_error).
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+
+from . import abi
+from . import lib as _l
+
+LOG_FIELDS = ["base_merit", "base_cost", "base_dyn_sse", "base_eq_sse", "merit", "cost", "dyn_sse", "eq_sse", "step_size", "step_type",
+              "dx_norm", "du_norm", "armijo", "convergence"]
+
+
+def _f(a):
+    return np.ascontiguousarray(a, dtype=np.float64)
+
+
+def _p(a):
+    return a.ctypes.data_as(_l.dp)
+
+
+def stack_instances(instances: list[dict]) -> dict:
+    """list of per-instance dicts (references.build_instance) -> batched arrays; all instances must share the node count."""
+    n = {len(i["t_nodes"]) for i in instances}
+    if len(n) != 1:
+        raise ValueError(f"instances of one batch must have the same number of shooting nodes, got {sorted(n)}")
+    keys = ["x0", "x_init", "u_init", "t_nodes", "node_event", "contact_flags", "swing_ref", "impact_factor", "arm_phase", "x_ref"]
+    return {k: np.stack([np.asarray(i[k]) for i in instances]) for k in keys}
+
+
+class B200SqpSolver:
+    def __init__(self, model: dict, settings: abi.Settings | None = None, device: int = 0, capture_raw_blocks: bool = False):
+        self.model = model
+        self.nx, self.nu = model["nx"], model["nu"]
+        self.settings = settings if settings is not None else abi.default_settings(model)
+        self._desc = abi.model_desc(model)
+        self._h = C.c_void_p()
+        L = _l.lib()
+        _l.check(L.b200sqp_create(C.byref(self._desc), C.byref(self.settings), C.c_int(device), C.byref(self._h)))
+        self._raw_per = 0
+        if capture_raw_blocks:
+            per = C.c_int64()
+            _l.check(L.b200sqp_stage_doubles(self._h, C.c_int(0), C.byref(per)))
+            self._raw_per = per.value
+        self.batch = self.n_nodes = 0
+
+    def close(self):
+        if self._h:
+            _l.lib().b200sqp_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # -- SolverBase::run ------------------------------------------------------------------------------------------------
+    def upload(self, batch: dict):
+        B, n = batch["t_nodes"].shape
+        if (B, n) != (self.batch, self.n_nodes):
+            _l.check(_l.lib().b200sqp_set_batch(self._h, C.c_int(B), C.c_int(n)))
+            self.batch, self.n_nodes = B, n
+        u8 = lambda a: np.ascontiguousarray(a, dtype=np.uint8)
+        self._keep = [_f(batch["x0"]), _f(batch["x_init"]), _f(batch["u_init"]), _f(batch["t_nodes"]), u8(batch["node_event"]),
+                      u8(batch["contact_flags"]), _f(batch["swing_ref"]), _f(batch["impact_factor"]), _f(batch["arm_phase"]), _f(batch["x_ref"])]
+        k = self._keep
+        _l.check(_l.lib().b200sqp_upload_instances(self._h, _p(k[0]), _p(k[1]), _p(k[2]), _p(k[3]), k[4].ctypes.data_as(_l.u8p),
+                                                   k[5].ctypes.data_as(_l.u8p), _p(k[6]), _p(k[7]), _p(k[8]), _p(k[9])))
+
+    def solve(self, stream=None):
+        _l.check(_l.lib().b200sqp_solve(self._h, C.c_void_p(stream or 0)))
+
+    def run(self, instances):
+        batch = stack_instances(instances) if isinstance(instances, list) else instances
+        self.upload(batch)
+        self.solve()
+        return self.primal_solution()
+
+    # -- results -------------------------------------------------------------------------------------------------------------
+    def primal_solution(self, with_gains: bool | None = None):
+        B, n, nx, nu = self.batch, self.n_nodes, self.nx, self.nu
+        x, u = np.zeros((B, n, nx)), np.zeros((B, n - 1, nu))
+        with_gains = bool(self.settings.use_feedback_policy) if with_gains is None else with_gains
+        K = np.zeros((B, n - 1, nx, nu)) if with_gains else None
+        log = (abi.IterLog * (B * self.settings.sqp_iteration))()
+        n_iter, status = np.zeros(B, dtype=np.int32), np.zeros(B, dtype=np.int32)
+        _l.check(_l.lib().b200sqp_download(self._h, _p(x), _p(u), None if K is None else _p(K), log, n_iter.ctypes.data_as(_l.ip),
+                                           status.ctypes.data_as(_l.ip)))
+        logs = np.frombuffer(log, dtype=np.float64).reshape(B, self.settings.sqp_iteration, 16).copy()
+        out = dict(x=x, u=u, n_iter=n_iter, status=status, log=logs)
+        if K is not None:
+            out["K"] = np.swapaxes(K, -1, -2).copy()
+        return out
+
+    def iterations_log(self):
+        return self.primal_solution(with_gains=False)["log"]
+
+    def raw_stage_blocks(self):
+        """(B, N, per) raw pre-projection blocks of the last LQ approximation (needs capture_raw_blocks=True)."""
+        B, N = self.batch, self.n_nodes - 1
+        out = np.zeros((B, N, self._raw_per))
+        _l.check(_l.lib().b200sqp_download_stage_blocks(self._h, C.c_int(0), _p(out), C.c_int64(out.size)))
+        return out
+
+    def benchmarks(self):
+        """device milliseconds of {LQ approximation, solve QP, line search, compute controller} of the last solve"""
+        ms = (C.c_float * 4)()
+        _l.check(_l.lib().b200sqp_get_stage_times(self._h, ms))
+        return list(ms)
+
+    def launch_count(self) -> int:
+        n = C.c_int64()
+        _l.check(_l.lib().b200sqp_get_launch_count(self._h, C.byref(n)))
+        return n.value
