@@ -1,0 +1,301 @@
+#!/usr/bin/env python
+"""Benchmark of the hot path: SQP solves/s for the Unitree G1 whole-body OCP (one solve = one SqpSolver::runImpl with sqpIteration = 1).
+
+    python bench.py --gpus N --steps K --warmup W                 # this repo's CUDA path (one process per GPU under torchrun)
+    python bench.py --impl reference --gpus N --steps K --warmup W  # the reference algorithm on the host cores (CPU oracle)
+
+One "step" = one batched solve of `--batch` independent MPC instances per GPU (default 256 = BASELINE.json configs[2]).
+Prints ONE JSON line (rank 0).  See DESIGN.md §Measurement for the definitions of every field.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+from pathlib import Path
+
+import numpy as np
+
+ROOT = Path(__file__).resolve().parent
+sys.path.insert(0, str(ROOT))
+
+from wb_humanoid_mpc_b200 import abi, model_loader, references  # noqa: E402
+
+METRIC = "SQP solves/sec (G1 whole-body, N=100, batched)"
+SEED = 1234
+
+
+def build_batch(model, batch, rank, horizon, gaits):
+    """Instance distribution of SURVEY.md §8d (seed 1234): perturbed initial states, velocity commands, cold start."""
+    rng = np.random.default_rng(SEED + 7919 * rank)
+    nj = model["nj"]
+    lo, hi = np.array(model["q_lower"]), np.array(model["q_upper"])
+    insts = []
+    for i in range(batch):
+        x0 = np.array(model["x_init"], float)
+        x0[2] = model["reference"]["defaultBaseHeight"]
+        x0[0:3] += rng.uniform(-0.02, 0.02, 3)
+        x0[3:6] += rng.uniform(-0.05, 0.05, 3)
+        x0[6:6 + nj] = np.clip(x0[6:6 + nj] + rng.uniform(-0.1, 0.1, nj), lo + 0.05, hi - 0.05)
+        x0[6 + nj:] += rng.uniform(-0.2, 0.2, 6 + nj)
+        cmd = [rng.uniform(-0.5, 1.0), rng.uniform(-0.3, 0.3), model["reference"]["defaultBaseHeight"], rng.uniform(-0.5, 0.5)]
+        insts.append(references.build_instance(model, x0, t0=0.0, horizon=horizon, gait=gaits[i % len(gaits)], cmd=cmd))
+    return insts
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region (B200_PROFILING.md recipe)."""
+
+    def __init__(self, index=0):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
+            "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={q}", "--format=csv,noheader,nounits", "-lms", "100", "-i", str(self.index)],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            pass
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            try:
+                sm.append(float(r[0]))
+                mx.append(float(r[1]))
+                for n, v in zip(names, r[3:7]):
+                    if v.lower().startswith("active"):
+                        reasons.add(n)
+            except (ValueError, IndexError):
+                pass
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def oracle_batch_solve(model, insts, settings, threads):
+    """The reference algorithm (oracle restatement) on the host cores, one instance per worker thread."""
+    import ctypes as C
+
+    sys.path.insert(0, str(ROOT / "tests"))
+    import oracle_lib as orc
+
+    from wb_humanoid_mpc_b200.solver import stack_instances
+
+    L = orc.lib()
+    b = stack_instances(insts)
+    desc = abi.model_desc(model)
+    f = lambda a: np.ascontiguousarray(a, dtype=np.float64)
+    u8 = lambda a: np.ascontiguousarray(a, dtype=np.uint8)
+    x, u = f(b["x_init"]).copy(), f(b["u_init"]).copy()
+    arrs = [f(b["t_nodes"]), u8(b["node_event"]), f(b["x0"]), x, u, u8(b["contact_flags"]), f(b["swing_ref"]), f(b["impact_factor"]), f(b["arm_phase"]),
+            f(b["x_ref"])]
+    u8p = C.POINTER(C.c_uint8)
+    t0 = time.perf_counter()
+    rc = L.orc_wb_sqp_batch(C.byref(desc), C.c_int(len(insts)), C.c_int(threads), C.c_int(b["t_nodes"].shape[1]), orc._p(arrs[0]),
+                            arrs[1].ctypes.data_as(u8p), orc._p(arrs[2]), orc._p(arrs[3]), orc._p(arrs[4]), arrs[5].ctypes.data_as(u8p),
+                            orc._p(arrs[6]), orc._p(arrs[7]), orc._p(arrs[8]), orc._p(arrs[9]), C.byref(settings))
+    dt = time.perf_counter() - t0
+    assert rc == 0, rc
+    return dt, x, u
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--batch", type=int, default=256, help="MPC instances per GPU")
+    ap.add_argument("--horizon", type=float, default=3.5, help="seconds; 3.5 s at dt = 0.035 s gives N = 100 intervals (+ event nodes)")
+    ap.add_argument("--gait", default="walk")
+    ap.add_argument("--cpu-sample", type=int, default=0, help="instances in the CPU-baseline sample (0 = 2 x cores)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    model = model_loader.load_packaged_model()
+    settings = abi.default_settings(model, sqp_iteration=1)
+    cores = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    n_int = int(round(args.horizon / model["sqp"]["dt"]))
+    workload = f"G1 whole-body MPC (nx=58, nu=35), dt=0.035 s x {n_int} intervals, gait={args.gait}, batch={args.batch}/GPU, sqpIteration=1, cold start"
+
+    if args.impl == "reference":
+        # the reference's own CPU implementation of the path cannot be built here (no Eigen/Pinocchio/HPIPM): the arm
+        # times the CPU oracle (restatement of the same algorithm) on all host cores, rank 0 only.
+        if rank != 0:
+            return
+        sample = args.cpu_sample or cores
+        insts = build_batch(model, sample, 0, args.horizon, [args.gait])
+        for _ in range(max(0, min(args.warmup, 1))):
+            oracle_batch_solve(model, insts[: max(1, cores // 4)], settings, cores)
+        times = []
+        for _ in range(args.steps):
+            dt, _, _ = oracle_batch_solve(model, insts, settings, cores)
+            times.append(dt)
+        total = sum(times)
+        val = sample * args.steps / total
+        line = {"impl": "reference", "metric": METRIC, "value": val, "unit": "solves/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+                "ms_per_step": 1e3 * total / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+                "data": "synthetic", "config": {"workload": workload, "n_nodes": len(insts[0]["t_nodes"]), "sample_instances_per_step": sample},
+                "cpu_baseline": {"value": val, "unit": "solves/s", "cores": cores, "kind": "port",
+                                 "sample": f"{sample} instances per step, one instance per thread, {cores} threads"},
+                "e2e": {"value": val, "unit": "solves/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+        print(json.dumps(line))
+        return
+
+    import torch
+
+    from wb_humanoid_mpc_b200.solver import B200SqpSolver, stack_instances
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the b200 arm has no CPU fallback (use --impl reference for the CPU oracle)")
+    torch.cuda.set_device(local_rank)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    insts = build_batch(model, args.batch, rank, args.horizon, [args.gait])
+    batch = stack_instances(insts)
+    n_nodes = batch["t_nodes"].shape[1]
+    solver = B200SqpSolver(model, settings, device=local_rank)
+
+    # pinned host staging buffers for the end-to-end path
+    def pin(a):
+        t = torch.from_numpy(np.ascontiguousarray(a)).pin_memory()
+        return t.numpy()
+
+    pinned = {k: pin(v if v.dtype == np.uint8 else v.astype(np.float64)) for k, v in batch.items()}
+    h2d = sum(v.nbytes for v in pinned.values())
+    B, nx, nu = args.batch, model["nx"], model["nu"]
+    d2h = B * n_nodes * nx * 8 + B * (n_nodes - 1) * nu * 8 + B * settings.sqp_iteration * 128 + B * 8
+
+    def barrier():
+        torch.cuda.synchronize()
+        if dist is not None:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    def max_over_ranks(seconds):
+        if dist is None:
+            return seconds
+        t = torch.tensor([seconds], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    # ---- device-resident throughput (value) --------------------------------------------------------------------------------
+    solver.upload(pinned)
+    for _ in range(args.warmup):
+        solver.reset()
+        solver.solve()
+    stage_acc = np.zeros(4)
+    launches = 0
+    sampler = ClockSampler(local_rank)
+    barrier()
+    if rank == 0:
+        sampler.start()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record()
+    for _ in range(args.steps):
+        solver.reset()
+        solver.solve()   # synchronises internally at the end of the line search (host reads the pending-instance counter)
+        stage_acc += np.array(solver.benchmarks())
+        launches += solver.launch_count()
+    ev1.record()
+    torch.cuda.synchronize()
+    dev_s = max_over_ranks(ev0.elapsed_time(ev1) * 1e-3)
+    barrier()
+    clocks = sampler.stop() if rank == 0 else None
+    sol = solver.primal_solution()
+    assert not sol["status"].any()
+    alphas = sol["log"][:, 0, 8]
+
+    # ---- end-to-end through the C ABI with host buffers (e2e) --------------------------------------------------------------------
+    for _ in range(min(args.warmup, 2)):
+        solver.upload(pinned)
+        solver.solve()
+        solver.primal_solution()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        solver.upload(pinned)     # H2D of every per-instance input from pinned host memory
+        solver.solve()
+        solver.primal_solution()  # D2H of the primal solution + iteration log
+    torch.cuda.synchronize()
+    e2e_s = max_over_ranks(time.perf_counter() - t0)
+    barrier()
+
+    total_solves = args.batch * world * args.steps
+    value = total_solves / dev_s
+    e2e = total_solves / e2e_s
+
+    # ---- roofline of the dominant kernel -------------------------------------------------------------------------------------------
+    stage_ms = stage_acc / args.steps
+    names = ["lq_kernel (K1)", "riccati_kernel (K2)", "rollout_kernel (K3)"]
+    dom = int(np.argmax(stage_ms[:3]))
+    N = n_nodes - 1
+    nut = 23
+    # algorithmic bytes per launch: projected stage record out of K1 / into K2, plus the per-node inputs and solution
+    rec = 8 * (58 * 58 + 58 * nut + 58 + 58 * 58 + nut * 58 + nut * nut + 58 + nut)            # A B b Q S R q r
+    proj = 8 * (35 * nut + 35 * 58 + 35)                                                    # Pu Px u0
+    node_in = 8 * (58 + 35 + 58 + 58 + 6 + 2 + 1 + 1) + 3
+    alg = {0: B * N * (rec + proj + node_in), 1: B * N * (rec + 8 * (nut * 58 + nut + 58 + nut)), 2: B * N * (8 * (3 * 58 + 35 + 58 + 35) + 32)}
+    peaks = {}
+    try:
+        peaks = json.loads((ROOT / "MEASURED_PEAKS.json").read_text())
+    except Exception:
+        pass
+    peak = peaks.get("hbm_gbs", 6650.0)
+    achieved = alg[dom] / (stage_ms[dom] * 1e-3) / 1e9
+    roofline = {"kernel": names[dom], "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                "traffic": None, "peak_source": "MEASURED_PEAKS.json (measured)" if peaks else "fallback 6.65 TB/s",
+                "algorithmic_bytes_per_launch": alg[dom], "stage_ms": {"lq": stage_ms[0], "qp": stage_ms[1], "linesearch": stage_ms[2]},
+                "note": "fp64-pipe bound, not HBM bound: see DESIGN.md; the per-stage device times are CUDA events on the launching stream"}
+
+    line = {"metric": METRIC, "value": value, "unit": "solves/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": 1e3 * dev_s / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+            "data": "synthetic",
+            "config": {"workload": workload, "n_nodes": int(n_nodes), "batch_per_gpu": args.batch, "l2": "stage blocks (%.1f GB/GPU) exceed the 126 MB L2; no flush needed" % (B * N * (rec + proj) / 1e9),
+                       "accepted_step_sizes": {str(a): int((alphas == a).sum()) for a in np.unique(alphas)}},
+            "e2e": {"value": e2e, "unit": "solves/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h)},
+            "gpu_launches": int(launches), "roofline": roofline, "clocks": clocks}
+
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        sample = args.cpu_sample or cores
+        cpu_insts = insts[:sample] if sample <= len(insts) else build_batch(model, sample, 0, args.horizon, [args.gait])
+        dt, xo, uo = oracle_batch_solve(model, cpu_insts, settings, cores)
+        line["cpu_baseline"] = {"value": sample / dt, "unit": "solves/s", "cores": cores, "kind": "port",
+                                "sample": f"{sample} of the {args.batch} instances, one per thread on {cores} threads, {dt:.1f} s"}
+        # the same instances agree between the two implementations (parity spot check on the benchmark inputs)
+        k = min(sample, len(insts))
+        err = float(np.max(np.abs(sol["x"][:k] - xo[:k])))
+        line["cpu_baseline"]["max_abs_diff_x_vs_gpu"] = err
+    if rank == 0:
+        print(json.dumps(line))
+    if dist is not None:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

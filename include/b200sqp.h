@@ -135,6 +135,10 @@ int b200sqp_upload_instances(b200sqp_handle h, const double* x0, const double* x
                              const uint8_t* node_event, const uint8_t* contact_flags, const double* swing_ref,
                              const double* impact_factor, const double* arm_phase, const double* x_ref);
 
+/* SqpSolver::reset() (SqpSolver.h:62): drop the current iterate; the next solve starts again from the uploaded initial guess
+ * (device-to-device restore, no host traffic). */
+int b200sqp_reset(b200sqp_handle h);
+
 /* SqpSolver::runImpl for every instance; asynchronous on `stream`. */
 int b200sqp_solve(b200sqp_handle h, void* stream);
 

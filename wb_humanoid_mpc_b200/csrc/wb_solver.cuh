@@ -26,6 +26,7 @@ struct WbDev {
   const WbDeviceModel* model;
   // instance inputs
   double *x0, *x, *u, *t, *swing, *impact, *arm, *xref;
+  double *xInit, *uInit;  // uploaded initial guess (restored by b200sqp_reset)
   uint8_t *event, *contact;
   // QP (nx = 58, nu_max = 23)
   QpDeviceView qp;

@@ -113,6 +113,7 @@ EXPORTED_SYMBOLS = [
     "b200sqp_destroy",
     "b200sqp_set_batch",
     "b200sqp_upload_instances",
+    "b200sqp_reset",
     "b200sqp_solve",
     "b200sqp_download",
     "b200sqp_download_stage_blocks",

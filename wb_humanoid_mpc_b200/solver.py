@@ -78,6 +78,10 @@ class B200SqpSolver:
         _l.check(_l.lib().b200sqp_upload_instances(self._h, _p(k[0]), _p(k[1]), _p(k[2]), _p(k[3]), k[4].ctypes.data_as(_l.u8p),
                                                    k[5].ctypes.data_as(_l.u8p), _p(k[6]), _p(k[7]), _p(k[8]), _p(k[9])))
 
+    def reset(self):
+        """SqpSolver::reset(): restore the uploaded initial guess on the device"""
+        _l.check(_l.lib().b200sqp_reset(self._h))
+
     def solve(self, stream=None):
         _l.check(_l.lib().b200sqp_solve(self._h, C.c_void_p(stream or 0)))
 
