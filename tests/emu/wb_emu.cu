@@ -30,7 +30,8 @@ int emu_dyn(const b200sqp_model_desc* d, const double* x, const double* u, doubl
   static DynWs w;
   const int NT = 128;
   if (deriv) {
-    RUN_PHASE(NT, dynPhaseKinematics<true>(P, m, x, u, w));
+    RUN_PHASE(NT, dynPhaseJoints<true>(P, m, x, w));
+    RUN_PHASE(NT, dynPhaseChains(P, m, x, u, w));
     RUN_PHASE(NT, dynPhaseInertia(P, m, w));
     RUN_PHASE(NT, dynPhaseBmat(P, w));
     RUN_PHASE(NT, dynPhaseComposite<true>(P, m, w));
@@ -38,7 +39,8 @@ int emu_dyn(const b200sqp_model_desc* d, const double* x, const double* u, doubl
     RUN_PHASE(NT, dynWriteFlow(P, x, u, w, xdot));
     RUN_PHASE(NT, dynPhaseJacobian(P, m, w, G));
   } else {
-    RUN_PHASE(NT, dynPhaseKinematics<false>(P, m, x, u, w));
+    RUN_PHASE(NT, dynPhaseJoints<false>(P, m, x, w));
+    RUN_PHASE(NT, dynPhaseChains(P, m, x, u, w));
     RUN_PHASE(NT, dynPhaseInertia(P, m, w));
     RUN_PHASE(NT, dynPhaseComposite<false>(P, m, w));
     RUN_PHASE(NT, dynPhaseFinal(P, m, u, w));

@@ -4,7 +4,9 @@
 
 namespace b200sqp {
 
-struct Par;  // {tid, nt} (wb_dynamics.cuh)
+struct Par {  // the calling thread's slice of a phase
+  int tid, nt;
+};
 
 // C(MxN, ldc) = (ACC ? C : 0) + alpha * op(A) * B ; op(A) = A (MxK, lda) or A^T (A stored KxM, lda) ; B is KxN (ldb)
 template <int TM, int TN, bool TRANS_A, bool ACC, class PAR>
@@ -48,6 +50,67 @@ HD void par_gemv(PAR P, int M, int K, double alpha, const double* __restrict__ A
     for (int k = 0; k < K; ++k) s = fma(TRANS_A ? A[k + i * lda] : A[i + k * lda], x[k], s);
     y[i] = ACC ? fma(alpha, s, y[i]) : alpha * s;
   }
+}
+
+}  // namespace b200sqp
+
+namespace b200sqp {
+
+// Tensor-core variant of par_gemm: fp64 DMMA (mma.sync.aligned.m8n8k4.f64) on column-major operands in shared or global memory.
+// One work item = one 8-row strip x NG column tiles, so the A fragment is loaded once per k-step and reused NG times.
+// Edges are handled by predicated (zero-filled) fragment loads and predicated stores; no padding requirements on the operands.
+// On the host (development harness) the same contraction runs as scalar loops.
+template <bool TRANS_A, bool ACC, int NG, class PAR>
+HD void par_mma_gemm(PAR P, int M, int N, int K, double alpha, const double* __restrict__ A, int lda, const double* __restrict__ B, int ldb,
+                     double* __restrict__ C, int ldc) {
+#ifdef __CUDA_ARCH__
+  const int warp = P.tid >> 5, nwarps = P.nt >> 5, lane = P.tid & 31;
+  const int tilesM = (M + 7) >> 3, tilesN = (N + 7) >> 3, groupsN = (tilesN + NG - 1) / NG;
+  const int fr = lane >> 2, fk = lane & 3;
+  for (int t = warp; t < tilesM * groupsN; t += nwarps) {
+    const int m0 = (t % tilesM) << 3, nt0 = (t / tilesM) * NG;
+    double c0[NG], c1[NG];
+#pragma unroll
+    for (int g = 0; g < NG; ++g) c0[g] = c1[g] = 0.0;
+    const int ar = m0 + fr;
+    const bool arok = ar < M;
+    for (int k0 = 0; k0 < K; k0 += 4) {
+      const int kk = k0 + fk;
+      const bool kok = kk < K;
+      const double a = (arok && kok) ? (TRANS_A ? A[kk + ar * lda] : A[ar + kk * lda]) : 0.0;
+#pragma unroll
+      for (int g = 0; g < NG; ++g) {
+        const int bn = ((nt0 + g) << 3) + fr;
+        const double b = (kok && bn < N) ? B[kk + bn * ldb] : 0.0;
+        asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+                     : "+d"(c0[g]), "+d"(c1[g])
+                     : "d"(a), "d"(b));
+      }
+    }
+    if (arok) {
+#pragma unroll
+      for (int g = 0; g < NG; ++g) {
+        const int cn = ((nt0 + g) << 3) + 2 * fk;
+        if (cn < N) {
+          double* c = &C[ar + cn * ldc];
+          *c = ACC ? fma(alpha, c0[g], *c) : alpha * c0[g];
+        }
+        if (cn + 1 < N) {
+          double* c = &C[ar + (cn + 1) * ldc];
+          *c = ACC ? fma(alpha, c1[g], *c) : alpha * c1[g];
+        }
+      }
+    }
+  }
+#else
+  for (int t = P.tid; t < M * N; t += P.nt) {
+    const int i = t % M, j = t / M;
+    double s = 0.0;
+    for (int k = 0; k < K; ++k) s = fma(TRANS_A ? A[k + i * lda] : A[i + k * lda], B[k + j * ldb], s);
+    double* c = &C[i + j * ldc];
+    *c = ACC ? fma(alpha, s, *c) : alpha * s;
+  }
+#endif
 }
 
 }  // namespace b200sqp

@@ -4,11 +4,15 @@
 // (lib/ocs2_ros2/ocs2_sqp/hpipm_catkin/src/HpipmInterface.cpp:166-455), i.e. HPIPM's unconstrained-QP path
 // (one Riccati factorisation + one substitution; reg_prim on the Hessian diagonals).
 //
-// Data layout: see include/b200sqp.h section (1).  P and p live in shared memory for the whole backward sweep;
-// each stage streams its (A|B), Q, S, R, q, r, b record from HBM exactly once in the backward sweep and (A|B), b once
-// more in the forward sweep.
+// Data layout: include/b200sqp.h section (1).  P and p live in shared memory for the whole backward sweep.  Each stage record
+// is streamed from HBM exactly once in the backward sweep; the copy of stage k-1 is issued with cp.async as soon as its
+// destination buffers are dead and overlaps the factorisation of stage k.  The 58-wide contractions run on the fp64 tensor
+// path (DMMA m8n8k4).  The forward sweep double-buffers (A|B), K, k, b the same way.
 #pragma once
+#include <cuda_pipeline.h>
+
 #include "dense.cuh"
+#include "dense_par.cuh"
 
 namespace b200sqp {
 
@@ -22,154 +26,217 @@ struct QpDeviceView {
   double reg;
 };
 
-__host__ __device__ inline size_t riccati_smem_doubles(int nx, int numax) {
-  const int nw = nx + numax;
-  // P, Pn, AB, W, Y(S~), Rs, vectors: p, qv, rv, bv, v, dxv, duv
-  return static_cast<size_t>(nx) * nx * 2 + static_cast<size_t>(nx) * nw * 2 + static_cast<size_t>(numax) * nx +
-         static_cast<size_t>(numax) * numax + 5 * static_cast<size_t>(nx) + 2 * static_cast<size_t>(numax) + 8;
+__host__ __device__ inline int even_up(int n) { return (n + 1) & ~1; }
+
+struct RicLayout {
+  int pq, ab, w, y, rs, linv, vec, total;  // sizes in doubles
+};
+__host__ __device__ inline RicLayout riccati_layout(int nx, int nm) {
+  RicLayout L;
+  const int nw = nx + nm;
+  L.pq = even_up(nx * nx);
+  L.ab = even_up(nx * nw);
+  L.w = even_up(nx * nw);
+  L.y = even_up(nm * nx);
+  L.rs = even_up(nm * nm);
+  L.linv = even_up(nm * nm);
+  L.vec = even_up(nx) * 8 + even_up(nm) * 6;
+  L.total = 2 * L.pq + 2 * L.ab + L.w + 2 * L.y + 2 * L.rs + L.linv + L.vec + 8;
+  return L;
+}
+__host__ __device__ inline size_t riccati_smem_doubles(int nx, int numax) { return static_cast<size_t>(riccati_layout(nx, numax).total); }
+
+// asynchronous global -> shared copy of n doubles by the whole block (16-byte chunks when both sides allow it)
+__device__ __forceinline__ void async_copy(double* dst, const double* src, int n) {
+  const bool wide = ((reinterpret_cast<uintptr_t>(src) | reinterpret_cast<uintptr_t>(dst)) & 15) == 0 && (n & 1) == 0;
+  if (wide) {
+    for (int i = threadIdx.x; i < (n >> 1); i += blockDim.x) __pipeline_memcpy_async(dst + 2 * i, src + 2 * i, 16);
+  } else {
+    for (int i = threadIdx.x; i < n; i += blockDim.x) __pipeline_memcpy_async(dst + i, src + i, 8);
+  }
 }
 
 __global__ void __launch_bounds__(256, 1) riccati_kernel(QpDeviceView v) {
   extern __shared__ double sm[];
   const int inst = blockIdx.x;
-  const int nx = v.nx, numax = v.numax, N = v.N;
-  const int nw = nx + numax;
-  double* P = sm;
-  double* Pn = P + nx * nx;
-  double* AB = Pn + nx * nx;     // nx x (nx+numax): [A | B]
-  double* W = AB + nx * nw;      // P * [A | B]
-  double* Y = W + nx * nw;       // numax x nx (ld numax): S~ then L^-1 S~
-  double* Rs = Y + numax * nx;   // numax x numax
-  double* pv = Rs + numax * numax;
-  double* qv = pv + nx;
-  double* bv = qv + nx;
-  double* vv = bv + nx;
-  double* xv = vv + nx;
-  double* rv = xv + nx;          // numax
-  double* uv = rv + numax;       // numax
+  const int nx = v.nx, nm = v.numax, N = v.N, nw = nx + nm;
+  const RicLayout L = riccati_layout(nx, nm);
+  double* PQ[2] = {sm, sm + L.pq};
+  double* AB[2] = {sm + 2 * L.pq, sm + 2 * L.pq + L.ab};
+  double* W = AB[1] + L.ab;
+  double* Y[2] = {W + L.w, W + L.w + L.y};
+  double* Rs[2] = {Y[1] + L.y, Y[1] + L.y + L.rs};
+  double* Linv = Rs[1] + L.rs;
+  double* vec = Linv + L.linv;
+  const int ex = even_up(nx), em = even_up(nm);
+  double* qv[2] = {vec, vec + ex};
+  double* bv[2] = {vec + 2 * ex, vec + 3 * ex};
+  double* pv = vec + 4 * ex;
+  double* vv = vec + 5 * ex;
+  double* xv = vec + 6 * ex;
+  double* tv = vec + 7 * ex;
+  double* rv[2] = {vec + 8 * ex, vec + 8 * ex + em};
+  double* yl = vec + 8 * ex + 2 * em;
+  double* uv = vec + 8 * ex + 3 * em;
+  double* kb[2] = {vec + 8 * ex + 4 * em, vec + 8 * ex + 5 * em};
   __shared__ int ok;
   if (threadIdx.x == 0) ok = 1;
+  const Par P{static_cast<int>(threadIdx.x), static_cast<int>(blockDim.x)};
 
   const size_t iN = static_cast<size_t>(inst) * N, iN1 = static_cast<size_t>(inst) * (N + 1);
+  int cur = 0;
   // terminal stage: P_N = Q_N + reg I, p_N = q_N
   {
     const double* QN = v.Q + (iN1 + N) * nx * nx;
-    for (int i = threadIdx.x; i < nx * nx; i += blockDim.x) P[i] = QN[i] + ((i % nx) == (i / nx) ? v.reg : 0.0);
+    for (int i = threadIdx.x; i < nx * nx; i += blockDim.x) PQ[cur][i] = QN[i] + ((i % nx) == (i / nx) ? v.reg : 0.0);
     block_copy(nx, v.q + (iN1 + N) * nx, pv);
     __syncthreads();
     if (v.keepP) {
-      block_copy(nx * nx, P, v.P + (iN1 + N) * nx * nx);
+      block_copy(nx * nx, PQ[cur], v.P + (iN1 + N) * nx * nx);
       block_copy(nx, pv, v.p + (iN1 + N) * nx);
     }
   }
+  auto prefetch = [&](int k, int set, double* qdst) {
+    const size_t sk = iN + k;
+    const int nu = v.nu ? v.nu[sk] : nm;
+    async_copy(AB[set], v.A + sk * nx * nx, nx * nx);
+    if (nu > 0) {
+      async_copy(AB[set] + nx * nx, v.Bm + sk * nx * nm, nx * nu);
+      async_copy(Y[set], v.S + sk * nm * nx, nm * nx);
+      async_copy(Rs[set], v.R + sk * nm * nm, nm * nm);
+      async_copy(rv[set], v.r + sk * nm, nu);
+    }
+    async_copy(qdst, v.Q + (iN1 + k) * nx * nx, nx * nx);
+    async_copy(qv[set], v.q + (iN1 + k) * nx, nx);
+    async_copy(bv[set], v.b + sk * nx, nx);
+    __pipeline_commit();
+  };
+  prefetch(N - 1, 0, PQ[1 - cur]);
 
   for (int k = N - 1; k >= 0; --k) {
-    const int nu = v.nu ? v.nu[iN + k] : numax;
+    const int set = (N - 1 - k) & 1;
+    const int nu = v.nu ? v.nu[iN + k] : nm;
     const size_t sk = iN + k;
-    // ---- load the stage record ---------------------------------------------------------------------------
-    block_copy(nx * nx, v.A + sk * nx * nx, AB);
-    if (nu > 0) block_copy(nx * nu, v.Bm + sk * nx * numax, AB + nx * nx);
-    block_copy(nx * nx, v.Q + (iN1 + k) * nx * nx, Pn);
-    if (nu > 0) {
-      block_copy(numax * nx, v.S + sk * numax * nx, Y);
-      block_copy(numax * numax, v.R + sk * numax * numax, Rs);
-      block_copy(nu, v.r + sk * numax, rv);
-    }
-    block_copy(nx, v.q + (iN1 + k) * nx, qv);
-    block_copy(nx, v.b + sk * nx, bv);
+    double* Pc = PQ[cur];
+    double* Pn = PQ[1 - cur];
+    double* ABk = AB[set];
+    double* Yk = Y[set];
+    double* Rk = Rs[set];
+    __pipeline_wait_prior(0);
     __syncthreads();
-    // ---- W = P [A|B],  v = P b + p ---------------------------------------------------------------------------
-    block_gemm<4, 4, false, false>(nx, nx + nu, nx, 1.0, P, nx, AB, nx, W, nx);
+    // ---- W = P [A|B],  v = P b + p --------------------------------------------------------------------------------
+    par_mma_gemm<false, false, 4>(P, nx, nx + nu, nx, 1.0, Pc, nx, ABk, nx, W, nx);
     for (int i = threadIdx.x; i < nx; i += blockDim.x) {
       double s = pv[i];
-      for (int j = 0; j < nx; ++j) s = fma(P[i + j * nx], bv[j], s);
+      for (int j = 0; j < nx; ++j) s = fma(Pc[i + j * nx], bv[set][j], s);
       vv[i] = s;
     }
     __syncthreads();
-    // ---- Q~ = Q + A'W_A (+reg), S~ = S + B'W_A, R~ = R + B'W_B (+reg), q~ = q + A'v, r~ = r + B'v --------------
-    block_gemm<4, 4, true, true>(nx, nx, nx, 1.0, AB, nx, W, nx, Pn, nx);
+    // P is dead: start streaming stage k-1 (its Q goes into the buffer P occupied)
+    if (k > 0) prefetch(k - 1, 1 - set, Pc);
+    // ---- Q~ = Q + A'W_A (+reg), S~ = S + B'W_A, R~ = R + B'W_B (+reg), q~ = q + A'v, r~ = r + B'v --------------------------
+    par_mma_gemm<true, true, 4>(P, nx, nx, nx, 1.0, ABk, nx, W, nx, Pn, nx);
     if (nu > 0) {
-      block_gemm<2, 4, true, true>(nu, nx, nx, 1.0, AB + nx * nx, nx, W, nx, Y, numax);
-      block_gemm<2, 2, true, true>(nu, nu, nx, 1.0, AB + nx * nx, nx, W + nx * nx, nx, Rs, numax);
-      block_gemv<true, true>(nu, nx, 1.0, AB + nx * nx, nx, vv, rv);
+      par_mma_gemm<true, true, 4>(P, nu, nx, nx, 1.0, ABk + nx * nx, nx, W, nx, Yk, nm);
+      par_mma_gemm<true, true, 3>(P, nu, nu, nx, 1.0, ABk + nx * nx, nx, W + nx * nx, nx, Rk, nm);
+      block_gemv<true, true>(nu, nx, 1.0, ABk + nx * nx, nx, vv, rv[set]);
     }
-    block_gemv<true, true>(nx, nx, 1.0, AB, nx, vv, qv);
+    block_gemv<true, true>(nx, nx, 1.0, ABk, nx, vv, qv[set]);
     __syncthreads();
     for (int i = threadIdx.x; i < nx; i += blockDim.x) Pn[i + i * nx] += v.reg;
-    for (int i = threadIdx.x; i < nu; i += blockDim.x) Rs[i + i * numax] += v.reg;
+    for (int i = threadIdx.x; i < nu; i += blockDim.x) Rk[i + i * nm] += v.reg;
     __syncthreads();
     if (nu > 0) {
-      // ---- factorise R~ = L L', Y = L^-1 S~, y = L^-1 r~ ------------------------------------------------------
-      warp_cholesky_lower(nu, Rs, numax, &ok);
+      // ---- R~ = L L' (warp 0), Linv = L^-1 (one thread per column) ------------------------------------------------------------
+      warp_cholesky_lower(nu, Rk, nm, &ok);
       __syncthreads();
-      block_trsm_lower(nu, nx, Rs, numax, Y, numax);
-      if (threadIdx.x == blockDim.x - 1) {  // y = L^-1 r~ (single column)
+      for (int c = threadIdx.x; c < nu; c += blockDim.x) {
+        // column c of L^-1 by forward substitution on e_c
         for (int i = 0; i < nu; ++i) {
-          double s = rv[i];
-          for (int j = 0; j < i; ++j) s = fma(-Rs[i + j * numax], rv[j], s);
-          rv[i] = s / Rs[i + i * numax];
+          double s = (i == c) ? 1.0 : 0.0;
+          for (int j = c; j < i; ++j) s = fma(-Rk[i + j * nm], Linv[j + c * nm], s);
+          Linv[i + c * nm] = (i < c) ? 0.0 : s / Rk[i + i * nm];
         }
       }
       __syncthreads();
-      // ---- P = Q~ - Y'Y, p = q~ - Y'y ; K = -L^-T Y, k = -L^-T y ------------------------------------------------
-      block_gemm<4, 4, true, true>(nx, nx, nu, -1.0, Y, numax, Y, numax, Pn, nx);
-      block_gemv<true, true>(nx, nu, -1.0, Y, numax, rv, qv);
-      block_trsm_lowerT_neg(nu, nx, Rs, numax, Y, numax, v.K + sk * numax * nx, numax);
-      if (threadIdx.x == blockDim.x - 1) {
-        double* kf = v.kff + sk * numax;
-        for (int i = nu - 1; i >= 0; --i) {
-          double s = rv[i];
-          for (int j = i + 1; j < nu; ++j) s = fma(-Rs[j + i * numax], -kf[j], s);
-          kf[i] = -(s / Rs[i + i * numax]);
-        }
-      }
+      // ---- Yl = L^-1 S~ (into W), yl = L^-1 r~ -------------------------------------------------------------------------------------
+      double* Yl = W;
+      par_mma_gemm<false, false, 4>(P, nu, nx, nu, 1.0, Linv, nm, Yk, nm, Yl, nm);
+      block_gemv<false, false>(nu, nu, 1.0, Linv, nm, rv[set], yl);
+      __syncthreads();
+      // ---- P = Q~ - Yl'Yl, p = q~ - Yl'yl ; K = -L^-T Yl, k = -L^-T yl -------------------------------------------------------------
+      par_mma_gemm<true, true, 4>(P, nx, nx, nu, -1.0, Yl, nm, Yl, nm, Pn, nx);
+      block_gemv<true, true>(nx, nu, -1.0, Yl, nm, yl, qv[set]);
+      par_mma_gemm<true, false, 4>(P, nu, nx, nu, -1.0, Linv, nm, Yl, nm, v.K + sk * nm * nx, nm);
+      block_gemv<true, false>(nu, nu, -1.0, Linv, nm, yl, v.kff + sk * nm);
     }
     __syncthreads();
-    // symmetrise (the lower and upper triangles were accumulated in different orders) and rotate buffers
+    // symmetrise in place (pairs), rotate buffers
     for (int t = threadIdx.x; t < nx * nx; t += blockDim.x) {
       const int i = t % nx, j = t / nx;
-      P[t] = 0.5 * (Pn[i + j * nx] + Pn[j + i * nx]);
+      if (i > j) {
+        const double m = 0.5 * (Pn[i + j * nx] + Pn[j + i * nx]);
+        Pn[i + j * nx] = m;
+        Pn[j + i * nx] = m;
+      }
     }
-    block_copy(nx, qv, pv);
+    block_copy(nx, qv[set], pv);
+    cur = 1 - cur;
     __syncthreads();
     if (v.keepP) {
-      block_copy(nx * nx, P, v.P + (iN1 + k) * nx * nx);
+      block_copy(nx * nx, PQ[cur], v.P + (iN1 + k) * nx * nx);
       block_copy(nx, pv, v.p + (iN1 + k) * nx);
     }
   }
-  // ---- forward substitution -------------------------------------------------------------------------------------
+  __syncthreads();
+  // ---- forward substitution, double-buffered ------------------------------------------------------------------------------------------
+  auto prefetchF = [&](int k, int set) {
+    const size_t sk = iN + k;
+    const int nu = v.nu ? v.nu[sk] : nm;
+    async_copy(AB[set], v.A + sk * nx * nx, nx * nx);
+    if (nu > 0) {
+      async_copy(AB[set] + nx * nx, v.Bm + sk * nx * nm, nx * nu);
+      async_copy(Y[set], v.K + sk * nm * nx, nm * nx);
+      async_copy(kb[set], v.kff + sk * nm, nu);
+    }
+    async_copy(bv[set], v.b + sk * nx, nx);
+    __pipeline_commit();
+  };
   block_copy(nx, v.dx0 + static_cast<size_t>(inst) * nx, xv);
+  prefetchF(0, 0);
   __syncthreads();
   block_copy(nx, xv, v.dx + iN1 * nx);
   for (int k = 0; k < N; ++k) {
-    const int nu = v.nu ? v.nu[iN + k] : numax;
+    const int set = k & 1;
+    const int nu = v.nu ? v.nu[iN + k] : nm;
     const size_t sk = iN + k;
-    const double* Kk = v.K + sk * numax * nx;
-    const double* Ak = v.A + sk * nx * nx;
-    const double* Bk = v.Bm + sk * nx * numax;
-    for (int i = threadIdx.x; i < numax; i += blockDim.x) {
+    __pipeline_wait_prior(0);
+    __syncthreads();
+    if (k + 1 < N) prefetchF(k + 1, 1 - set);
+    for (int i = threadIdx.x; i < nm; i += blockDim.x) {
       double s = 0.0;
       if (i < nu) {
-        s = v.kff[sk * numax + i];
-        for (int j = 0; j < nx; ++j) s = fma(Kk[i + j * numax], xv[j], s);
+        s = kb[set][i];
+        for (int j = 0; j < nx; ++j) s = fma(Y[set][i + j * nm], xv[j], s);
       }
       uv[i] = s;
-      v.du[sk * numax + i] = s;
+      v.du[sk * nm + i] = s;
     }
     __syncthreads();
     for (int i = threadIdx.x; i < nx; i += blockDim.x) {
-      double s = v.b[sk * nx + i];
+      double s = bv[set][i];
+      const double* Ak = AB[set];
       for (int j = 0; j < nx; ++j) s = fma(Ak[i + j * nx], xv[j], s);
-      for (int j = 0; j < nu; ++j) s = fma(Bk[i + j * nx], uv[j], s);
-      vv[i] = s;
+      for (int j = 0; j < nu; ++j) s = fma(Ak[nx * nx + i + j * nx], uv[j], s);
+      tv[i] = s;
     }
     __syncthreads();
     for (int i = threadIdx.x; i < nx; i += blockDim.x) {
-      xv[i] = vv[i];
-      v.dx[(iN1 + k + 1) * nx + i] = vv[i];
+      xv[i] = tv[i];
+      v.dx[(iN1 + k + 1) * nx + i] = tv[i];
     }
-    __syncthreads();
   }
+  __syncthreads();
   if (threadIdx.x == 0) {
     int bad = !ok;
     for (int i = 0; i < nx; ++i) bad |= !isfinite(xv[i]);

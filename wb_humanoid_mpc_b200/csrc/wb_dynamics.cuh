@@ -15,13 +15,10 @@
 //     so one tangent direction is O(1) work once the composites exist: one thread per column of the 6 x 93 Jacobian.
 // All functions are phase functions: every work item writes only its own outputs, phases are separated by a block barrier.
 #pragma once
+#include "dense_par.cuh"
 #include "wb_model.cuh"
 
 namespace b200sqp {
-
-struct Par {  // the calling thread's slice of a phase
-  int tid, nt;
-};
 
 // shared-memory workspace of one evaluation point (doubles)
 struct DynWs {
@@ -29,6 +26,7 @@ struct DynWs {
   double Rb[9], Sz[9], SzInv[9], v0[6], a0[6];
   double dv0[9][6], da0[9][6], dRb[3][9], dSz[3][9];  // tangents w.r.t. th(3), pdot(3), thdot(3)
   // bodies (pelvis coordinates)
+  double Rj[NB][9];  // joint placement times joint rotation (parent-relative), computed body-parallel before the chain sweep
   double R[NB][9], p[NB][3], S[NB][6], v[NB][6], a[NB][6], psd[NB][6], psdd[NB][6];
   double I[NB][36], Bm[NB][36], f[NB][6];
   double IC[NB][36], BC[NB][36], fC[NB][6];
@@ -85,11 +83,10 @@ HD void inv3(const double* A, double* Ai) {
   Ai[6] = c02 * id; Ai[7] = (A[1] * A[6] - A[0] * A[7]) * id; Ai[8] = (A[0] * A[4] - A[1] * A[3]) * id;
 }
 
-// ---- phase 1: base quantities (items 0..9) and chain kinematics (items 16..19) ------------------------------------------------
-// chains: 0 left leg, 1 right leg, 2 waist + left arm, 3 waist + right arm (waist recomputed in registers, written by chain 2 only)
+// ---- phase 1a: base quantities (items 0..9) and joint transforms (items 16..38), all independent -----------------------------------------
 template <bool DERIV>
-HD void dynPhaseKinematics(Par P, const WbDeviceModel& m, const double* x, const double* u, DynWs& w) {
-  for (int it = P.tid; it < 20; it += P.nt) {
+HD void dynPhaseJoints(Par P, const WbDeviceModel& m, const double* x, DynWs& w) {
+  for (int it = P.tid; it < 16 + NJ; it += P.nt) {
     if (it == 0) {
       D1 R[9], S[9], v0[6], a0[6];
       baseKinematics(x, -1, m.gravity, R, S, v0, a0);
@@ -119,59 +116,62 @@ HD void dynPhaseKinematics(Par P, const WbDeviceModel& m, const double* x, const
           }
       }
     } else if (it >= 16) {
-      const int ch = it - 16;
-      // values of the base needed by the recursion (recomputed locally to avoid a barrier)
-      D1 Rd[9], Sd[9], v0d[6], a0d[6];
-      baseKinematics(x, -1, m.gravity, Rd, Sd, v0d, a0d);
-      double Rl[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1};
-      V3 pl = mk(0, 0, 0);
-      V6 vl{mk(v0d[0].v, v0d[1].v, v0d[2].v), mk(v0d[3].v, v0d[4].v, v0d[5].v)};
-      V6 al{mk(a0d[0].v, a0d[1].v, a0d[2].v), mk(a0d[3].v, a0d[4].v, a0d[5].v)};
-      if (ch == 0) {  // body 0 entries
-        for (int k = 0; k < 9; ++k) w.R[0][k] = Rl[k];
-        st3(w.p[0], pl);
-        st6(w.v[0], vl);
-        st6(w.a[0], al);
-        for (int k = 0; k < 6; ++k) w.S[0][k] = w.psd[0][k] = w.psdd[0][k] = 0.0;
+      const int i = it - 16 + 1;
+      const double q = x[5 + i];
+      const double* ax = m.axis[i];
+      const double c = cos(q), s = sin(q), t = 1.0 - c;
+      const double Rq[9] = {t * ax[0] * ax[0] + c,         t * ax[0] * ax[1] - s * ax[2], t * ax[0] * ax[2] + s * ax[1],
+                            t * ax[0] * ax[1] + s * ax[2], t * ax[1] * ax[1] + c,         t * ax[1] * ax[2] - s * ax[0],
+                            t * ax[0] * ax[2] - s * ax[1], t * ax[1] * ax[2] + s * ax[0], t * ax[2] * ax[2] + c};
+      mm3(m.jR[i], Rq, w.Rj[i]);
+    }
+  }
+}
+
+// ---- phase 1b: chain sweeps (4 items): 0 left leg, 1 right leg, 2 waist + left arm, 3 waist + right arm (waist recomputed in registers,
+// written by chain 2 only).  Only the cheap parent-dependent part is sequential.
+HD void dynPhaseChains(Par P, const WbDeviceModel& m, const double* x, const double* u, DynWs& w) {
+  for (int ch = P.tid; ch < 4; ch += P.nt) {
+    double Rl[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1};
+    V3 pl = mk(0, 0, 0);
+    V6 vl = ld6(w.v0), al = ld6(w.a0);
+    if (ch == 0) {  // body 0 entries
+      for (int k = 0; k < 9; ++k) w.R[0][k] = Rl[k];
+      st3(w.p[0], pl);
+      st6(w.v[0], vl);
+      st6(w.a[0], al);
+      for (int k = 0; k < 6; ++k) w.S[0][k] = w.psd[0][k] = w.psdd[0][k] = 0.0;
+    }
+    int first, last, own;
+    if (ch == 0) { first = 1; last = 6; own = 1; }
+    else if (ch == 1) { first = 7; last = 12; own = 7; }
+    else if (ch == 2) { first = 13; last = 19; own = 13; }
+    else { first = 13; last = 23; own = 20; }
+    for (int i = first; i <= last; ++i) {
+      if (ch == 3 && i >= 16 && i < 20) continue;  // skip the left arm on the right-arm chain
+      const double qd = x[NV + 5 + i], qdd = u[12 + i - 1];
+      double Ri[9];
+      mm3(Rl, w.Rj[i], Ri);
+      const V3 pi = pl + mv(Rl, ld3(m.jp[i]));
+      const V3 om = mv(Ri, ld3(m.axis[i]));
+      const V6 Si{cross(pi, om), om};
+      const V6 psd = mcross(vl, Si);
+      const V6 vi = vl + qd * Si;
+      const V6 ai = al + qdd * Si + qd * psd;
+      const V6 psdd = mcross(al, Si) + mcross(vl, psd);
+      if (i >= own) {
+        for (int k = 0; k < 9; ++k) w.R[i][k] = Ri[k];
+        st3(w.p[i], pi);
+        st6(w.S[i], Si);
+        st6(w.v[i], vi);
+        st6(w.a[i], ai);
+        st6(w.psd[i], psd);
+        st6(w.psdd[i], psdd);
       }
-      int first, last, own;
-      if (ch == 0) { first = 1; last = 6; own = 1; }
-      else if (ch == 1) { first = 7; last = 12; own = 7; }
-      else if (ch == 2) { first = 13; last = 19; own = 13; }
-      else { first = 13; last = 23; own = 20; }
-      for (int i = first; i <= last; ++i) {
-        if (ch == 3 && i >= 16 && i < 20) continue;  // skip the left arm on the right-arm chain
-        const double q = x[5 + i], qd = x[NV + 5 + i], qdd = u[12 + i - 1];
-        // joint rotation (Rodrigues) and placement
-        const double* ax = m.axis[i];
-        const double c = cos(q), s = sin(q), t = 1.0 - c;
-        const double Rq[9] = {t * ax[0] * ax[0] + c,         t * ax[0] * ax[1] - s * ax[2], t * ax[0] * ax[2] + s * ax[1],
-                              t * ax[0] * ax[1] + s * ax[2], t * ax[1] * ax[1] + c,         t * ax[1] * ax[2] - s * ax[0],
-                              t * ax[0] * ax[2] - s * ax[1], t * ax[1] * ax[2] + s * ax[0], t * ax[2] * ax[2] + c};
-        double Rj[9], Ri[9];
-        mm3(m.jR[i], Rq, Rj);
-        mm3(Rl, Rj, Ri);
-        const V3 pi = pl + mv(Rl, ld3(m.jp[i]));
-        const V3 om = mv(Ri, ld3(ax));
-        const V6 Si{cross(pi, om), om};
-        const V6 psd = mcross(vl, Si);
-        const V6 vi = vl + qd * Si;
-        const V6 ai = al + qdd * Si + qd * psd;
-        const V6 psdd = mcross(al, Si) + mcross(vl, psd);
-        if (i >= own) {
-          for (int k = 0; k < 9; ++k) w.R[i][k] = Ri[k];
-          st3(w.p[i], pi);
-          st6(w.S[i], Si);
-          st6(w.v[i], vi);
-          st6(w.a[i], ai);
-          st6(w.psd[i], psd);
-          st6(w.psdd[i], psdd);
-        }
-        for (int k = 0; k < 9; ++k) Rl[k] = Ri[k];
-        pl = pi;
-        vl = vi;
-        al = ai;
-      }
+      for (int k = 0; k < 9; ++k) Rl[k] = Ri[k];
+      pl = pi;
+      vl = vi;
+      al = ai;
     }
   }
 }
@@ -220,28 +220,35 @@ HD void dynPhaseBmat(Par P, DynWs& w) {
   }
 }
 
-// ---- phase 4: composites = sums over subtrees (common coordinates) ------------------------------------------------------------------
+// ---- phase 4: composites = sums over subtrees (common coordinates): one item per matrix entry, children folded into parents
+// in decreasing body order (bodies are numbered parent-before-child).  The value-only path needs the root composite only.
 template <bool DERIV>
 HD void dynPhaseComposite(Par P, const WbDeviceModel& m, DynWs& w) {
-  const int per = DERIV ? 78 : 42;  // IC (36) [+ BC (36)] + fC (6)
-  for (int it = P.tid; it < NB * per; it += P.nt) {
-    const int i = it / per, e = it % per;
-    if (!DERIV && i != 0) continue;  // the value-only path needs only the root composite
-    const unsigned mask = m.subtree[i];
-    double s = 0.0;
-    if (e < 36) {
-      for (int j = i; j < NB; ++j)
-        if (mask >> j & 1u) s += w.I[j][e];
-      w.IC[i][e] = s;
-    } else if (DERIV && e < 72) {
-      for (int j = i; j < NB; ++j)
-        if (mask >> j & 1u) s += w.Bm[j][e - 36];
-      w.BC[i][e - 36] = s;
-    } else {
-      const int k = e - (DERIV ? 72 : 36);
-      for (int j = i; j < NB; ++j)
-        if (mask >> j & 1u) s += w.f[j][k];
-      w.fC[i][k] = s;
+  if (DERIV) {
+    for (int e = P.tid; e < 78; e += P.nt) {
+      if (e < 36) {
+        for (int i = 0; i < NB; ++i) w.IC[i][e] = w.I[i][e];
+        for (int i = NB - 1; i >= 1; --i) w.IC[m.parent[i]][e] += w.IC[i][e];
+      } else if (e < 72) {
+        const int k = e - 36;
+        for (int i = 0; i < NB; ++i) w.BC[i][k] = w.Bm[i][k];
+        for (int i = NB - 1; i >= 1; --i) w.BC[m.parent[i]][k] += w.BC[i][k];
+      } else {
+        const int k = e - 72;
+        for (int i = 0; i < NB; ++i) w.fC[i][k] = w.f[i][k];
+        for (int i = NB - 1; i >= 1; --i) w.fC[m.parent[i]][k] += w.fC[i][k];
+      }
+    }
+  } else {
+    for (int e = P.tid; e < 42; e += P.nt) {
+      double s = 0.0;
+      if (e < 36) {
+        for (int i = 0; i < NB; ++i) s += w.I[i][e];
+        w.IC[0][e] = s;
+      } else {
+        for (int i = 0; i < NB; ++i) s += w.f[i][e - 36];
+        w.fC[0][e - 36] = s;
+      }
     }
   }
 }

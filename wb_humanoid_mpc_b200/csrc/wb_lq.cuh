@@ -123,24 +123,38 @@ HD double xvEntry(const double* GrPrev, double c, int row, int d) {  // Xv_s(row
   return e;
 }
 HD void rkPhaseChainStage(Par P, int s, double dt, double* G, double* tmp /*6 x 93*/) {
-  // c_s for the stage point x_s = x + c_s k_{s-1}
-  const double c = (s == 1 || s == 2) ? 0.5 * dt : dt;      // s = 1,2,3 <-> RK stages 2,3,4
-  const double cp = (s == 1) ? 0.0 : (s == 2 ? 0.5 * dt : 0.5 * dt);  // c of the previous stage point (stage s-1)
+  // stage point x_s = x + c_s k_{s-1}; c = c_s, cp = c_{s-1}.  With the sparse structure of Xq, Xv each entry needs 12 products:
+  //   Gq Xq = Gq[:,d][d<29] + c ( Gq[:,d-29][29<=d<58] + cp ( Gq[:,0:6] Gr_{s-2}[:,d] + Gq[:,6+d-70][d>=70] ) )
+  //   Gv Xv = Gv[:,d-29][29<=d<58] + c ( Gv[:,0:6] Gr_{s-1}[:,d] + Gv[:,6+d-70][d>=70] )
+  const double c = (s == 3) ? dt : 0.5 * dt;
+  const double cp = (s == 1) ? 0.0 : 0.5 * dt;
   const double* Gs = G + s * 6 * NZ;
-  const double* GrP = G + (s - 1) * 6 * NZ;                    // Gr_{s-1}
-  const double* GrPP = (s >= 2) ? G + (s - 2) * 6 * NZ : nullptr;  // Gr_{s-2}
+  const double* GrP = G + (s - 1) * 6 * NZ;
+  const double* GrPP = (s >= 2) ? G + (s - 2) * 6 * NZ : nullptr;
   for (int it = P.tid; it < 6 * NZ; it += P.nt) {
     const int r = it % 6, d = it / 6;
-    double acc = (d >= NX) ? Gs[r + 6 * d] : 0.0;  // Gu_s
-    for (int k = 0; k < NV; ++k) {
-      // Xq_s(k, d) = e_q + c * Xv_{s-1}(k, d) ;  Xv_{s-1} = e_v + cp * [Gr_{s-2}; e_aj]
-      double xq = (d == k) ? 1.0 : 0.0;
-      xq += c * xvEntry(GrPP, (s >= 2) ? cp : 0.0, k, d);
-      const double xv = xvEntry(GrP, c, k, d);
-      if (xq != 0.0) acc = fma(Gs[r + 6 * k], xq, acc);
-      if (xv != 0.0) acc = fma(Gs[r + 6 * (NV + k)], xv, acc);
+    const double* Gq = Gs + r;                 // Gq[r][k] = Gq[6 * k]
+    const double* Gv = Gs + r + 6 * NV;
+    double acc = (d >= NX) ? Gs[r + 6 * d] : 0.0;
+    if (d < NV) acc += Gq[6 * d];
+    double inner_q = 0.0, inner_v = 0.0;
+    if (d >= NV && d < NX) {
+      inner_q = Gq[6 * (d - NV)];
+      acc += Gv[6 * (d - NV)];
     }
-    tmp[it] = acc;
+    if (d >= NX + 12) {
+      inner_v = Gv[6 * (6 + d - NX - 12)];
+      if (cp != 0.0) inner_q = fma(cp, Gq[6 * (6 + d - NX - 12)], inner_q);
+    }
+#pragma unroll
+    for (int k = 0; k < 6; ++k) inner_v = fma(Gv[6 * k], GrP[k + 6 * d], inner_v);
+    if (cp != 0.0) {
+      double t = 0.0;
+#pragma unroll
+      for (int k = 0; k < 6; ++k) t = fma(Gq[6 * k], GrPP[k + 6 * d], t);
+      inner_q = fma(cp, t, inner_q);
+    }
+    tmp[it] = fma(c, inner_q + inner_v, acc);
   }
 }
 
@@ -396,80 +410,115 @@ HD void costPhaseRows(Par P, const WbDeviceModel& m, const NodeIn& n, int g, con
     }
   }
 }
-// H += JR' JR ; gq += JR' coef     (items over the Hessian)
+// H += JR' JR ; gq += JR' coef
 HD void costPhaseAccumulate(Par P, int nr, const double* JR, const double* rowCoef, double* H, double* gq) {
   if (nr == 0) return;
-  for (int it = P.tid; it < NZ * NZ; it += P.nt) {
-    const int i = it % NZ, j = it / NZ;
-    double acc = 0.0;
-    for (int r = 0; r < nr; ++r) acc = fma(JR[r + JR_MAX * i], JR[r + JR_MAX * j], acc);
-    H[it] += acc;
-  }
-  for (int i = P.tid; i < NZ; i += P.nt) {
-    double acc = 0.0;
-    for (int r = 0; r < nr; ++r) acc = fma(JR[r + JR_MAX * i], rowCoef[r], acc);
-    gq[i] += acc;
-  }
+  par_mma_gemm<true, true, 4>(P, NZ, NZ, nr, 1.0, JR, JR_MAX, JR, JR_MAX, H, HLD);
+  par_gemv<true, true>(P, NZ, nr, 1.0, JR, JR_MAX, rowCoef, gq);
 }
 
 // ---- projection: Eigen::FullPivLU semantics (complete pivoting; particular solution with free variables = 0; kernel basis) ----------------
-// single work item (tid 0) does the pivot search bookkeeping; the elimination is spread over the block by the caller's phases.
-HD void luPhasePivot(Par P, int nc, int k, double* LU, int* rowOf, int* colOf, int* info) {
-  if (P.tid != 0) return;
-  int pi = k, pj = k;
-  double best = -1.0;
-  for (int j = k; j < NU; ++j)
-    for (int i = k; i < nc; ++i) {
-      const double a = fabs(LU[i + NC_MAX * j]);
-      if (a > best) {
-        best = a;
-        pi = i;
-        pj = j;
+// Whole factorisation by ONE warp: lane l owns columns l and l+32; pivot search = per-lane scan + shuffle arg-max with ties resolved
+// towards the smaller column-major index (the first maximum of Eigen's / the oracle's scan).  Host harness: sequential.
+HD void luPhaseFactor(Par P, int nc, double* LU, int* rowOf, int* colOf) {
+#ifdef __CUDA_ARCH__
+  if (P.tid >= 32) return;
+  const int lane = P.tid;
+  for (int k = 0; k < nc; ++k) {
+    double best = -1.0;
+    int bidx = 1 << 30;
+    for (int j = lane; j < NU; j += 32)
+      if (j >= k)
+        for (int i = k; i < nc; ++i) {
+          const double a = fabs(LU[i + NC_MAX * j]);
+          if (a > best) {
+            best = a;
+            bidx = j * NC_MAX + i;
+          }
+        }
+#pragma unroll
+    for (int off = 16; off; off >>= 1) {
+      const double ob = __shfl_xor_sync(0xffffffffu, best, off);
+      const int oi = __shfl_xor_sync(0xffffffffu, bidx, off);
+      if (ob > best || (ob == best && oi < bidx)) {
+        best = ob;
+        bidx = oi;
       }
     }
-  info[0] = pi;
-  info[1] = pj;
-  info[2] = (best > 0.0);
-}
-HD void luPhaseSwap(Par P, int nc, int k, double* LU, int* rowOf, int* colOf, const int* info) {
-  const int pi = info[0], pj = info[1];
-  // row swap then column swap, each element handled by one item
-  for (int j = P.tid; j < NU; j += P.nt)
+    const int pj = bidx / NC_MAX, pi = bidx % NC_MAX;
+    if (pi != k)
+      for (int j = lane; j < NU; j += 32) {
+        const double t = LU[k + NC_MAX * j];
+        LU[k + NC_MAX * j] = LU[pi + NC_MAX * j];
+        LU[pi + NC_MAX * j] = t;
+      }
+    __syncwarp();
+    if (pj != k)
+      for (int i = lane; i < nc; i += 32) {
+        const double t = LU[i + NC_MAX * k];
+        LU[i + NC_MAX * k] = LU[i + NC_MAX * pj];
+        LU[i + NC_MAX * pj] = t;
+      }
+    if (lane == 0) {
+      int t = rowOf[k];
+      rowOf[k] = rowOf[pi];
+      rowOf[pi] = t;
+      t = colOf[k];
+      colOf[k] = colOf[pj];
+      colOf[pj] = t;
+    }
+    __syncwarp();
+    const double piv = LU[k + NC_MAX * k];
+    for (int i = k + 1 + lane; i < nc; i += 32) LU[i + NC_MAX * k] /= piv;
+    __syncwarp();
+    for (int j = k + 1 + lane; j < NU; j += 32) {
+      const double ukj = LU[k + NC_MAX * j];
+      for (int i = k + 1; i < nc; ++i) LU[i + NC_MAX * j] = fma(-LU[i + NC_MAX * k], ukj, LU[i + NC_MAX * j]);
+    }
+    __syncwarp();
+  }
+#else
+  if (P.tid != 0) return;
+  for (int k = 0; k < nc; ++k) {
+    int pi = k, pj = k;
+    double best = -1.0;
+    for (int j = k; j < NU; ++j)
+      for (int i = k; i < nc; ++i) {
+        const double a = fabs(LU[i + NC_MAX * j]);
+        if (a > best) {
+          best = a;
+          pi = i;
+          pj = j;
+        }
+      }
     if (pi != k) {
-      const double t = LU[k + NC_MAX * j];
-      LU[k + NC_MAX * j] = LU[pi + NC_MAX * j];
-      LU[pi + NC_MAX * j] = t;
+      for (int j = 0; j < NU; ++j) {
+        const double t = LU[k + NC_MAX * j];
+        LU[k + NC_MAX * j] = LU[pi + NC_MAX * j];
+        LU[pi + NC_MAX * j] = t;
+      }
+      const int t = rowOf[k];
+      rowOf[k] = rowOf[pi];
+      rowOf[pi] = t;
     }
-  if (P.tid == 0 && pi != k) {
-    const int t = rowOf[k];
-    rowOf[k] = rowOf[pi];
-    rowOf[pi] = t;
-  }
-}
-HD void luPhaseSwapCols(Par P, int nc, int k, double* LU, int* colOf, const int* info) {
-  const int pj = info[1];
-  for (int i = P.tid; i < nc; i += P.nt)
     if (pj != k) {
-      const double t = LU[i + NC_MAX * k];
-      LU[i + NC_MAX * k] = LU[i + NC_MAX * pj];
-      LU[i + NC_MAX * pj] = t;
+      for (int i = 0; i < nc; ++i) {
+        const double t = LU[i + NC_MAX * k];
+        LU[i + NC_MAX * k] = LU[i + NC_MAX * pj];
+        LU[i + NC_MAX * pj] = t;
+      }
+      const int t = colOf[k];
+      colOf[k] = colOf[pj];
+      colOf[pj] = t;
     }
-  if (P.tid == 0 && pj != k) {
-    const int t = colOf[k];
-    colOf[k] = colOf[pj];
-    colOf[pj] = t;
+    const double piv = LU[k + NC_MAX * k];
+    for (int i = k + 1; i < nc; ++i) LU[i + NC_MAX * k] /= piv;
+    for (int j = k + 1; j < NU; ++j) {
+      const double ukj = LU[k + NC_MAX * j];
+      for (int i = k + 1; i < nc; ++i) LU[i + NC_MAX * j] = fma(-LU[i + NC_MAX * k], ukj, LU[i + NC_MAX * j]);
+    }
   }
-}
-HD void luPhaseScale(Par P, int nc, int k, double* LU) {
-  const double piv = LU[k + NC_MAX * k];
-  for (int i = k + 1 + P.tid; i < nc; i += P.nt) LU[i + NC_MAX * k] /= piv;
-}
-HD void luPhaseUpdate(Par P, int nc, int k, double* LU) {
-  const int rows = nc - k - 1, cols = NU - k - 1;
-  for (int it = P.tid; it < rows * cols; it += P.nt) {
-    const int i = k + 1 + it % rows, j = k + 1 + it / rows;
-    LU[i + NC_MAX * j] = fma(-LU[i + NC_MAX * k], LU[k + NC_MAX * j], LU[i + NC_MAX * j]);
-  }
+#endif
 }
 // Px = -D^+ C (35 x 58), u0 = -D^+ e, Pu = kernel (35 x nut); one item per right-hand side / kernel column
 HD void luPhaseSolve(Par P, int nc, const double* LU, const int* rowOf, const int* colOf, const double* CD, const double* ev, double* Pu,
