@@ -60,8 +60,8 @@ const char* b200sqp_last_error(void) { return g_err.c_str(); }
 const char* b200sqp_version(void) { return "b200sqp 0.1 (sm_100a, fp64)"; }
 
 int b200sqp_qp_create(int device, int batch, int N, int nx, int nu_max, b200sqp_qp* out) {
-  if (!out || batch <= 0 || N <= 0 || nx <= 0 || nu_max <= 0 || nu_max > 32)
-    return fail(B200SQP_EINVAL, "qp_create: need batch,N,nx > 0 and 0 < nu_max <= 32 (got %d,%d,%d,%d)", batch, N, nx, nu_max);
+  if (!out || batch <= 0 || N <= 0 || nx <= 0 || nx > 64 || nu_max <= 0 || nu_max > 32)
+    return fail(B200SQP_EINVAL, "qp_create: need batch,N > 0, 0 < nx <= 64 and 0 < nu_max <= 32 (got %d,%d,%d,%d)", batch, N, nx, nu_max);
   if (int rc = select_device(device)) return rc;
   const size_t smem = b200sqp::riccati_smem_doubles(nx, nu_max) * sizeof(double);
   if (smem > 227 * 1024) return fail(B200SQP_EINVAL, "qp_create: nx=%d nu_max=%d needs %zu B shared memory (> 227 KB)", nx, nu_max, smem);

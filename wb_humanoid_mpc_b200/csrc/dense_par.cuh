@@ -65,23 +65,47 @@ HD void par_mma_gemm(PAR P, int M, int N, int K, double alpha, const double* __r
                      double* __restrict__ C, int ldc) {
 #ifdef __CUDA_ARCH__
   const int warp = P.tid >> 5, nwarps = P.nt >> 5, lane = P.tid & 31;
-  const int tilesM = (M + 7) >> 3, tilesN = (N + 7) >> 3, groupsN = (tilesN + NG - 1) / NG;
+  const int tilesM = (M + 7) >> 3, tilesN = (N + 7) >> 3;
   const int fr = lane >> 2, fk = lane & 3;
-  for (int t = warp; t < tilesM * groupsN; t += nwarps) {
-    const int m0 = (t % tilesM) << 3, nt0 = (t / tilesM) * NG;
+  const int Kmain = K & ~3;
+  // work items (m-tile, group of NG n-tiles) are walked without integer division: warps stride over m-tiles inside each n-group
+  int tm = warp, ng = 0;
+  while (tm >= tilesM) {
+    tm -= tilesM;
+    ng += NG;
+  }
+  while (ng < tilesN) {
+    const int ar = (tm << 3) + fr;
+    const bool arok = ar < M;
+    const double* Ap = TRANS_A ? A + fk + (arok ? ar : 0) * lda : A + (arok ? ar : 0) + fk * lda;
+    const int astep = TRANS_A ? 4 : 4 * lda;
+    const double* Bp[NG];
+    bool bok[NG];
     double c0[NG], c1[NG];
 #pragma unroll
-    for (int g = 0; g < NG; ++g) c0[g] = c1[g] = 0.0;
-    const int ar = m0 + fr;
-    const bool arok = ar < M;
-    for (int k0 = 0; k0 < K; k0 += 4) {
-      const int kk = k0 + fk;
-      const bool kok = kk < K;
-      const double a = (arok && kok) ? (TRANS_A ? A[kk + ar * lda] : A[ar + kk * lda]) : 0.0;
+    for (int g = 0; g < NG; ++g) {
+      const int bn = ((ng + g) << 3) + fr;
+      bok[g] = bn < N;
+      Bp[g] = B + fk + (bok[g] ? bn : 0) * ldb;
+      c0[g] = c1[g] = 0.0;
+    }
+    for (int k0 = 0; k0 < Kmain; k0 += 4) {
+      const double a = arok ? *Ap : 0.0;
+      Ap += astep;
 #pragma unroll
       for (int g = 0; g < NG; ++g) {
-        const int bn = ((nt0 + g) << 3) + fr;
-        const double b = (kok && bn < N) ? B[kk + bn * ldb] : 0.0;
+        const double b = bok[g] ? Bp[g][k0] : 0.0;
+        asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+                     : "+d"(c0[g]), "+d"(c1[g])
+                     : "d"(a), "d"(b));
+      }
+    }
+    if (Kmain < K) {
+      const bool kok = Kmain + fk < K;
+      const double a = (arok && kok) ? *Ap : 0.0;
+#pragma unroll
+      for (int g = 0; g < NG; ++g) {
+        const double b = (bok[g] && kok) ? Bp[g][Kmain] : 0.0;
         asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
                      : "+d"(c0[g]), "+d"(c1[g])
                      : "d"(a), "d"(b));
@@ -90,7 +114,7 @@ HD void par_mma_gemm(PAR P, int M, int N, int K, double alpha, const double* __r
     if (arok) {
 #pragma unroll
       for (int g = 0; g < NG; ++g) {
-        const int cn = ((nt0 + g) << 3) + 2 * fk;
+        const int cn = ((ng + g) << 3) + 2 * fk;
         if (cn < N) {
           double* c = &C[ar + cn * ldc];
           *c = ACC ? fma(alpha, c0[g], *c) : alpha * c0[g];
@@ -100,6 +124,11 @@ HD void par_mma_gemm(PAR P, int M, int N, int K, double alpha, const double* __r
           *c = ACC ? fma(alpha, c1[g], *c) : alpha * c1[g];
         }
       }
+    }
+    tm += nwarps;
+    while (tm >= tilesM) {
+      tm -= tilesM;
+      ng += NG;
     }
   }
 #else

@@ -31,17 +31,18 @@ __host__ __device__ inline int even_up(int n) { return (n + 1) & ~1; }
 struct RicLayout {
   int pq, ab, w, y, rs, linv, vec, total;  // sizes in doubles
 };
+// Vectors ride along as extra matrix columns so that every matrix-vector product is folded into a tensor-core GEMM:
+//   PQ = [P | p] (nx x (nx+1)),  AB = [A | b | B] (nx x (nx+1+nm)),  Y = [S | r] (nm x (nx+1))
 __host__ __device__ inline RicLayout riccati_layout(int nx, int nm) {
   RicLayout L;
-  const int nw = nx + nm;
-  L.pq = even_up(nx * nx);
-  L.ab = even_up(nx * nw);
-  L.w = even_up(nx * nw);
-  L.y = even_up(nm * nx);
+  L.pq = even_up(nx * (nx + 1));
+  L.ab = even_up(nx * (nx + 1 + nm));
+  L.w = L.ab;
+  L.y = even_up(nm * (nx + 1));
   L.rs = even_up(nm * nm);
   L.linv = even_up(nm * nm);
-  L.vec = even_up(nx) * 8 + even_up(nm) * 6;
-  L.total = 2 * L.pq + 2 * L.ab + L.w + 2 * L.y + 2 * L.rs + L.linv + L.vec + 8;
+  L.vec = even_up(nx) * 2 + even_up(nm) * 3 + 8;
+  L.total = 2 * L.pq + 2 * L.ab + L.w + 2 * L.y + 2 * L.rs + L.linv + L.vec;
   return L;
 }
 __host__ __device__ inline size_t riccati_smem_doubles(int nx, int numax) { return static_cast<size_t>(riccati_layout(nx, numax).total); }
@@ -59,7 +60,7 @@ __device__ __forceinline__ void async_copy(double* dst, const double* src, int n
 __global__ void __launch_bounds__(256, 1) riccati_kernel(QpDeviceView v) {
   extern __shared__ double sm[];
   const int inst = blockIdx.x;
-  const int nx = v.nx, nm = v.numax, N = v.N, nw = nx + nm;
+  const int nx = v.nx, nm = v.numax, N = v.N, nx1 = nx + 1;
   const RicLayout L = riccati_layout(nx, nm);
   double* PQ[2] = {sm, sm + L.pq};
   double* AB[2] = {sm + 2 * L.pq, sm + 2 * L.pq + L.ab};
@@ -69,46 +70,40 @@ __global__ void __launch_bounds__(256, 1) riccati_kernel(QpDeviceView v) {
   double* Linv = Rs[1] + L.rs;
   double* vec = Linv + L.linv;
   const int ex = even_up(nx), em = even_up(nm);
-  double* qv[2] = {vec, vec + ex};
-  double* bv[2] = {vec + 2 * ex, vec + 3 * ex};
-  double* pv = vec + 4 * ex;
-  double* vv = vec + 5 * ex;
-  double* xv = vec + 6 * ex;
-  double* tv = vec + 7 * ex;
-  double* rv[2] = {vec + 8 * ex, vec + 8 * ex + em};
-  double* yl = vec + 8 * ex + 2 * em;
-  double* uv = vec + 8 * ex + 3 * em;
-  double* kb[2] = {vec + 8 * ex + 4 * em, vec + 8 * ex + 5 * em};
+  double* xv = vec;            // forward state [x; 1; u] is assembled in xa
+  double* tv = vec + ex;
+  double* uv = vec + 2 * ex;
+  double* kb[2] = {vec + 2 * ex + em, vec + 2 * ex + 2 * em};
   __shared__ int ok;
   if (threadIdx.x == 0) ok = 1;
   const Par P{static_cast<int>(threadIdx.x), static_cast<int>(blockDim.x)};
 
   const size_t iN = static_cast<size_t>(inst) * N, iN1 = static_cast<size_t>(inst) * (N + 1);
   int cur = 0;
-  // terminal stage: P_N = Q_N + reg I, p_N = q_N
+  // terminal stage: [P_N | p_N] = [Q_N + reg I | q_N]
   {
     const double* QN = v.Q + (iN1 + N) * nx * nx;
     for (int i = threadIdx.x; i < nx * nx; i += blockDim.x) PQ[cur][i] = QN[i] + ((i % nx) == (i / nx) ? v.reg : 0.0);
-    block_copy(nx, v.q + (iN1 + N) * nx, pv);
+    block_copy(nx, v.q + (iN1 + N) * nx, PQ[cur] + nx * nx);
     __syncthreads();
     if (v.keepP) {
       block_copy(nx * nx, PQ[cur], v.P + (iN1 + N) * nx * nx);
-      block_copy(nx, pv, v.p + (iN1 + N) * nx);
+      block_copy(nx, PQ[cur] + nx * nx, v.p + (iN1 + N) * nx);
     }
   }
   auto prefetch = [&](int k, int set, double* qdst) {
     const size_t sk = iN + k;
     const int nu = v.nu ? v.nu[sk] : nm;
     async_copy(AB[set], v.A + sk * nx * nx, nx * nx);
+    async_copy(AB[set] + nx * nx, v.b + sk * nx, nx);
     if (nu > 0) {
-      async_copy(AB[set] + nx * nx, v.Bm + sk * nx * nm, nx * nu);
+      async_copy(AB[set] + nx * nx1, v.Bm + sk * nx * nm, nx * nu);
       async_copy(Y[set], v.S + sk * nm * nx, nm * nx);
+      async_copy(Y[set] + nm * nx, v.r + sk * nm, nu);
       async_copy(Rs[set], v.R + sk * nm * nm, nm * nm);
-      async_copy(rv[set], v.r + sk * nm, nu);
     }
     async_copy(qdst, v.Q + (iN1 + k) * nx * nx, nx * nx);
-    async_copy(qv[set], v.q + (iN1 + k) * nx, nx);
-    async_copy(bv[set], v.b + sk * nx, nx);
+    async_copy(qdst + nx * nx, v.q + (iN1 + k) * nx, nx);
     __pipeline_commit();
   };
   prefetch(N - 1, 0, PQ[1 - cur]);
@@ -124,24 +119,19 @@ __global__ void __launch_bounds__(256, 1) riccati_kernel(QpDeviceView v) {
     double* Rk = Rs[set];
     __pipeline_wait_prior(0);
     __syncthreads();
-    // ---- W = P [A|B],  v = P b + p --------------------------------------------------------------------------------
-    par_mma_gemm<false, false, 4>(P, nx, nx + nu, nx, 1.0, Pc, nx, ABk, nx, W, nx);
-    for (int i = threadIdx.x; i < nx; i += blockDim.x) {
-      double s = pv[i];
-      for (int j = 0; j < nx; ++j) s = fma(Pc[i + j * nx], bv[set][j], s);
-      vv[i] = s;
-    }
+    // ---- W = P [A | b | B] ; then W_b += p  (v = P b + p) ----------------------------------------------------------
+    par_mma_gemm<false, false, 4>(P, nx, nx1 + nu, nx, 1.0, Pc, nx, ABk, nx, W, nx);
     __syncthreads();
-    // P is dead: start streaming stage k-1 (its Q goes into the buffer P occupied)
+    for (int i = threadIdx.x; i < nx; i += blockDim.x) W[nx * nx + i] += Pc[nx * nx + i];
+    __syncthreads();
+    // [P | p] is dead: start streaming stage k-1 (its [Q | q] goes into that buffer)
     if (k > 0) prefetch(k - 1, 1 - set, Pc);
-    // ---- Q~ = Q + A'W_A (+reg), S~ = S + B'W_A, R~ = R + B'W_B (+reg), q~ = q + A'v, r~ = r + B'v --------------------------
-    par_mma_gemm<true, true, 4>(P, nx, nx, nx, 1.0, ABk, nx, W, nx, Pn, nx);
+    // ---- [Q~ | q~] = [Q | q] + A'[W_A | v] (+reg), [S~ | r~] = [S | r] + B'[W_A | v], R~ = R + B'W_B (+reg) ----------------
+    par_mma_gemm<true, true, 4>(P, nx, nx1, nx, 1.0, ABk, nx, W, nx, Pn, nx);
     if (nu > 0) {
-      par_mma_gemm<true, true, 4>(P, nu, nx, nx, 1.0, ABk + nx * nx, nx, W, nx, Yk, nm);
-      par_mma_gemm<true, true, 3>(P, nu, nu, nx, 1.0, ABk + nx * nx, nx, W + nx * nx, nx, Rk, nm);
-      block_gemv<true, true>(nu, nx, 1.0, ABk + nx * nx, nx, vv, rv[set]);
+      par_mma_gemm<true, true, 4>(P, nu, nx1, nx, 1.0, ABk + nx * nx1, nx, W, nx, Yk, nm);
+      par_mma_gemm<true, true, 3>(P, nu, nu, nx, 1.0, ABk + nx * nx1, nx, W + nx * nx1, nx, Rk, nm);
     }
-    block_gemv<true, true>(nx, nx, 1.0, ABk, nx, vv, qv[set]);
     __syncthreads();
     for (int i = threadIdx.x; i < nx; i += blockDim.x) Pn[i + i * nx] += v.reg;
     for (int i = threadIdx.x; i < nu; i += blockDim.x) Rk[i + i * nm] += v.reg;
@@ -151,7 +141,6 @@ __global__ void __launch_bounds__(256, 1) riccati_kernel(QpDeviceView v) {
       warp_cholesky_lower(nu, Rk, nm, &ok);
       __syncthreads();
       for (int c = threadIdx.x; c < nu; c += blockDim.x) {
-        // column c of L^-1 by forward substitution on e_c
         for (int i = 0; i < nu; ++i) {
           double s = (i == c) ? 1.0 : 0.0;
           for (int j = c; j < i; ++j) s = fma(-Rk[i + j * nm], Linv[j + c * nm], s);
@@ -159,19 +148,19 @@ __global__ void __launch_bounds__(256, 1) riccati_kernel(QpDeviceView v) {
         }
       }
       __syncthreads();
-      // ---- Yl = L^-1 S~ (into W), yl = L^-1 r~ -------------------------------------------------------------------------------------
+      // ---- [Yl | yl] = L^-1 [S~ | r~] (into W) ---------------------------------------------------------------------------------
       double* Yl = W;
-      par_mma_gemm<false, false, 4>(P, nu, nx, nu, 1.0, Linv, nm, Yk, nm, Yl, nm);
-      block_gemv<false, false>(nu, nu, 1.0, Linv, nm, rv[set], yl);
+      double* Kout = W + even_up(nm * nx1);
+      par_mma_gemm<false, false, 4>(P, nu, nx1, nu, 1.0, Linv, nm, Yk, nm, Yl, nm);
       __syncthreads();
-      // ---- P = Q~ - Yl'Yl, p = q~ - Yl'yl ; K = -L^-T Yl, k = -L^-T yl -------------------------------------------------------------
-      par_mma_gemm<true, true, 4>(P, nx, nx, nu, -1.0, Yl, nm, Yl, nm, Pn, nx);
-      block_gemv<true, true>(nx, nu, -1.0, Yl, nm, yl, qv[set]);
-      par_mma_gemm<true, false, 4>(P, nu, nx, nu, -1.0, Linv, nm, Yl, nm, v.K + sk * nm * nx, nm);
-      block_gemv<true, false>(nu, nu, -1.0, Linv, nm, yl, v.kff + sk * nm);
+      // ---- [P | p] = [Q~ | q~] - Yl'[Yl | yl] ; [K | k] = -L^-T [Yl | yl] ---------------------------------------------------
+      par_mma_gemm<true, true, 4>(P, nx, nx1, nu, -1.0, Yl, nm, Yl, nm, Pn, nx);
+      par_mma_gemm<true, false, 4>(P, nu, nx1, nu, -1.0, Linv, nm, Yl, nm, Kout, nm);
+      __syncthreads();
+      for (int t = threadIdx.x; t < nm * nx; t += blockDim.x) v.K[sk * nm * nx + t] = (t % nm < nu) ? Kout[t] : 0.0;
+      for (int t = threadIdx.x; t < nu; t += blockDim.x) v.kff[sk * nm + t] = Kout[nm * nx + t];
     }
-    __syncthreads();
-    // symmetrise in place (pairs), rotate buffers
+    // symmetrise the P part in place (pairs), rotate buffers
     for (int t = threadIdx.x; t < nx * nx; t += blockDim.x) {
       const int i = t % nx, j = t / nx;
       if (i > j) {
@@ -180,26 +169,25 @@ __global__ void __launch_bounds__(256, 1) riccati_kernel(QpDeviceView v) {
         Pn[j + i * nx] = m;
       }
     }
-    block_copy(nx, qv[set], pv);
     cur = 1 - cur;
     __syncthreads();
     if (v.keepP) {
       block_copy(nx * nx, PQ[cur], v.P + (iN1 + k) * nx * nx);
-      block_copy(nx, pv, v.p + (iN1 + k) * nx);
+      block_copy(nx, PQ[cur] + nx * nx, v.p + (iN1 + k) * nx);
     }
   }
   __syncthreads();
-  // ---- forward substitution, double-buffered ------------------------------------------------------------------------------------------
+  // ---- forward substitution, double-buffered: x+ = [A | b | B] [x; 1; u] ----------------------------------------------------------------
   auto prefetchF = [&](int k, int set) {
     const size_t sk = iN + k;
     const int nu = v.nu ? v.nu[sk] : nm;
     async_copy(AB[set], v.A + sk * nx * nx, nx * nx);
+    async_copy(AB[set] + nx * nx, v.b + sk * nx, nx);
     if (nu > 0) {
-      async_copy(AB[set] + nx * nx, v.Bm + sk * nx * nm, nx * nu);
+      async_copy(AB[set] + nx * nx1, v.Bm + sk * nx * nm, nx * nu);
       async_copy(Y[set], v.K + sk * nm * nx, nm * nx);
       async_copy(kb[set], v.kff + sk * nm, nu);
     }
-    async_copy(bv[set], v.b + sk * nx, nx);
     __pipeline_commit();
   };
   block_copy(nx, v.dx0 + static_cast<size_t>(inst) * nx, xv);
@@ -213,22 +201,34 @@ __global__ void __launch_bounds__(256, 1) riccati_kernel(QpDeviceView v) {
     __pipeline_wait_prior(0);
     __syncthreads();
     if (k + 1 < N) prefetchF(k + 1, 1 - set);
-    for (int i = threadIdx.x; i < nm; i += blockDim.x) {
+    // du = K x + k : 8 lanes per row, shuffle-reduced
+    {
+      const int row = threadIdx.x >> 3, sub = threadIdx.x & 7;
       double s = 0.0;
-      if (i < nu) {
-        s = kb[set][i];
-        for (int j = 0; j < nx; ++j) s = fma(Y[set][i + j * nm], xv[j], s);
+      if (row < nu)
+        for (int j = sub; j < nx; j += 8) s = fma(Y[set][row + j * nm], xv[j], s);
+      s += __shfl_xor_sync(0xffffffffu, s, 4);
+      s += __shfl_xor_sync(0xffffffffu, s, 2);
+      s += __shfl_xor_sync(0xffffffffu, s, 1);
+      if (sub == 0 && row < nm) {
+        const double r = (row < nu) ? s + kb[set][row] : 0.0;
+        uv[row] = r;
+        v.du[sk * nm + row] = r;
       }
-      uv[i] = s;
-      v.du[sk * nm + i] = s;
     }
     __syncthreads();
-    for (int i = threadIdx.x; i < nx; i += blockDim.x) {
-      double s = bv[set][i];
+    // x+ = A x + b + B u : 4 lanes per row
+    {
+      const int row = threadIdx.x >> 2, sub = threadIdx.x & 3;
       const double* Ak = AB[set];
-      for (int j = 0; j < nx; ++j) s = fma(Ak[i + j * nx], xv[j], s);
-      for (int j = 0; j < nu; ++j) s = fma(Ak[nx * nx + i + j * nx], uv[j], s);
-      tv[i] = s;
+      double s = 0.0;
+      if (row < nx) {
+        for (int j = sub; j < nx; j += 4) s = fma(Ak[row + j * nx], xv[j], s);
+        for (int j = sub; j < nu; j += 4) s = fma(Ak[nx * nx1 + row + j * nx], uv[j], s);
+      }
+      s += __shfl_xor_sync(0xffffffffu, s, 2);
+      s += __shfl_xor_sync(0xffffffffu, s, 1);
+      if (sub == 0 && row < nx) tv[row] = s + Ak[nx * nx + row];
     }
     __syncthreads();
     for (int i = threadIdx.x; i < nx; i += blockDim.x) {

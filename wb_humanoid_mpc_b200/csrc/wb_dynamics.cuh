@@ -128,50 +128,75 @@ HD void dynPhaseJoints(Par P, const WbDeviceModel& m, const double* x, DynWs& w)
   }
 }
 
-// ---- phase 1b: chain sweeps (4 items): 0 left leg, 1 right leg, 2 waist + left arm, 3 waist + right arm (waist recomputed in registers,
-// written by chain 2 only).  Only the cheap parent-dependent part is sequential.
-HD void dynPhaseChains(Par P, const WbDeviceModel& m, const double* x, const double* u, DynWs& w) {
-  for (int ch = P.tid; ch < 4; ch += P.nt) {
-    double Rl[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1};
-    V3 pl = mk(0, 0, 0);
-    V6 vl = ld6(w.v0), al = ld6(w.a0);
-    if (ch == 0) {  // body 0 entries
-      for (int k = 0; k < 9; ++k) w.R[0][k] = Rl[k];
-      st3(w.p[0], pl);
-      st6(w.v[0], vl);
-      st6(w.a[0], al);
-      for (int k = 0; k < 6; ++k) w.S[0][k] = w.psd[0][k] = w.psdd[0][k] = 0.0;
+// ---- phases 1b-1e: body-parallel kinematics.  In a common (pelvis) coordinate frame the recursions collapse to sums / products over the
+// ancestor path of each body (<= 7 joints), so no thread walks a chain with the full 6D state in registers:
+//   R_i = prod Rj[k],  p_i = sum R_parent(k) jp_k,  v_i = v0 + sum S_k qd_k,  a_i = a0 + sum (S_k qdd_k + psid_k qd_k)
+// with psid_k = v_parent(k) x S_k = (v_k - S_k qd_k) x S_k.  One item per body, one barrier between passes.
+HD void dynPhaseAbsRot(Par P, const WbDeviceModel& m, DynWs& w) {
+  for (int i = P.tid; i < NB; i += P.nt) {
+    double R[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1};
+    const int len = m.pathLen[i];
+    for (int t = 0; t < len; ++t) {
+      double T[9];
+      mm3(R, w.Rj[m.path[i][t]], T);
+#pragma unroll
+      for (int k = 0; k < 9; ++k) R[k] = T[k];
     }
-    int first, last, own;
-    if (ch == 0) { first = 1; last = 6; own = 1; }
-    else if (ch == 1) { first = 7; last = 12; own = 7; }
-    else if (ch == 2) { first = 13; last = 19; own = 13; }
-    else { first = 13; last = 23; own = 20; }
-    for (int i = first; i <= last; ++i) {
-      if (ch == 3 && i >= 16 && i < 20) continue;  // skip the left arm on the right-arm chain
-      const double qd = x[NV + 5 + i], qdd = u[12 + i - 1];
-      double Ri[9];
-      mm3(Rl, w.Rj[i], Ri);
-      const V3 pi = pl + mv(Rl, ld3(m.jp[i]));
-      const V3 om = mv(Ri, ld3(m.axis[i]));
-      const V6 Si{cross(pi, om), om};
-      const V6 psd = mcross(vl, Si);
-      const V6 vi = vl + qd * Si;
-      const V6 ai = al + qdd * Si + qd * psd;
-      const V6 psdd = mcross(al, Si) + mcross(vl, psd);
-      if (i >= own) {
-        for (int k = 0; k < 9; ++k) w.R[i][k] = Ri[k];
-        st3(w.p[i], pi);
-        st6(w.S[i], Si);
-        st6(w.v[i], vi);
-        st6(w.a[i], ai);
-        st6(w.psd[i], psd);
-        st6(w.psdd[i], psdd);
-      }
-      for (int k = 0; k < 9; ++k) Rl[k] = Ri[k];
-      pl = pi;
-      vl = vi;
-      al = ai;
+#pragma unroll
+    for (int k = 0; k < 9; ++k) w.R[i][k] = R[k];
+  }
+}
+HD void dynPhaseAxes(Par P, const WbDeviceModel& m, DynWs& w) {
+  for (int i = P.tid; i < NB; i += P.nt) {
+    V3 p = mk(0, 0, 0);
+    const int len = m.pathLen[i];
+    for (int t = 0; t < len; ++t) {
+      const int k = m.path[i][t];
+      p = p + mv(w.R[m.parent[k]], ld3(m.jp[k]));
+    }
+    st3(w.p[i], p);
+    if (i == 0) {
+      for (int k = 0; k < 6; ++k) w.S[0][k] = 0.0;
+    } else {
+      const V3 om = mv(w.R[i], ld3(m.axis[i]));
+      st6(w.S[i], V6{cross(p, om), om});
+    }
+  }
+}
+HD void dynPhaseVel(Par P, const WbDeviceModel& m, const double* x, DynWs& w) {
+  for (int i = P.tid; i < NB; i += P.nt) {
+    V6 v = ld6(w.v0);
+    const int len = m.pathLen[i];
+    for (int t = 0; t < len; ++t) {
+      const int k = m.path[i][t];
+      v = v + x[NV + 5 + k] * ld6(w.S[k]);
+    }
+    st6(w.v[i], v);
+    if (i == 0) {
+      for (int k = 0; k < 6; ++k) w.psd[0][k] = 0.0;
+    } else {
+      const V6 S = ld6(w.S[i]);
+      st6(w.psd[i], mcross(v - x[NV + 5 + i] * S, S));
+    }
+  }
+}
+HD void dynPhaseAcc(Par P, const WbDeviceModel& m, const double* x, const double* u, DynWs& w) {
+  for (int i = P.tid; i < NB; i += P.nt) {
+    V6 a = ld6(w.a0);
+    const int len = m.pathLen[i];
+    for (int t = 0; t < len; ++t) {
+      const int k = m.path[i][t];
+      a = a + u[12 + k - 1] * ld6(w.S[k]) + x[NV + 5 + k] * ld6(w.psd[k]);
+    }
+    st6(w.a[i], a);
+    if (i == 0) {
+      for (int k = 0; k < 6; ++k) w.psdd[0][k] = 0.0;
+    } else {
+      const V6 S = ld6(w.S[i]), psd = ld6(w.psd[i]);
+      const double qd = x[NV + 5 + i];
+      const V6 al = a - u[12 + i - 1] * S - qd * psd;
+      const V6 vl = ld6(w.v[i]) - qd * S;
+      st6(w.psdd[i], mcross(al, S) + mcross(vl, psd));
     }
   }
 }

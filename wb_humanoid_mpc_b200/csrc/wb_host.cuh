@@ -35,6 +35,11 @@ inline const char* makeDeviceModel(const b200sqp_model_desc& d, WbDeviceModel& m
       if (a == i) mask |= 1u << j;
     }
     m.subtree[i] = mask;
+    int tmp[NB], len = 0;
+    for (int a = i; a > 0; a = m.parent[a]) tmp[len++] = a;
+    if (len > 8) return "kinematic chains deeper than 8 joints are not supported";
+    m.pathLen[i] = len;
+    for (int t = 0; t < len; ++t) m.path[i][t] = tmp[len - 1 - t];
   }
   // kinematic layout assumed by the chain kernels: legs 1-6 / 7-12, waist 13-15, arms 16-19 / 20-23
   const int expect[NB] = {-1, 0, 1, 2, 3, 4, 5, 0, 7, 8, 9, 10, 11, 0, 13, 14, 15, 16, 17, 18, 15, 20, 21, 22};

@@ -520,35 +520,73 @@ HD void luPhaseFactor(Par P, int nc, double* LU, int* rowOf, int* colOf) {
   }
 #endif
 }
-// Px = -D^+ C (35 x 58), u0 = -D^+ e, Pu = kernel (35 x nut); one item per right-hand side / kernel column
-HD void luPhaseSolve(Par P, int nc, const double* LU, const int* rowOf, const int* colOf, const double* CD, const double* ev, double* Pu,
-                     double* Px, double* u0) {
+// Px = -D^+ C (35 x 58), u0 = -D^+ e, Pu = kernel (35 x nut), from the LU factors, as small triangular inverses + GEMMs:
+//   phase A: columns of U_rr^-1 and L_rr^-1 (2*nc items) ; PC = row-permuted [C | e] (nc x 59)
+//   phase B: T = L^-1 PC
+//   phase C: Xt = -U^-1 T (nc x 59) ; Kt = -U^-1 U_rk (nc x nut)
+//   phase D: scatter through the column permutation
+struct LuSolveWs {
+  double *Uinv, *Linv, *PC, *T, *Xt, *Kt;  // each <= 14 x 59, leading dimension NC_MAX
+};
+HD void luPhaseSolveA(Par P, int nc, const double* LU, const int* rowOf, const double* CD, const double* ev, LuSolveWs ws) {
+  for (int it = P.tid; it < 2 * nc; it += P.nt) {
+    const int c = it % nc;
+    if (it < nc) {  // column c of U^-1 (upper triangular)
+      double z[NC_MAX];
+#pragma unroll
+      for (int i = 0; i < NC_MAX; ++i) z[i] = 0.0;
+#pragma unroll
+      for (int i = NC_MAX - 1; i >= 0; --i) {
+        if (i <= c && i < nc) {
+          double s = (i == c) ? 1.0 : 0.0;
+#pragma unroll
+          for (int j = i + 1; j < NC_MAX; ++j)
+            if (j <= c) s = fma(-LU[i + NC_MAX * j], z[j], s);
+          z[i] = s / LU[i + NC_MAX * i];
+        }
+      }
+#pragma unroll
+      for (int i = 0; i < NC_MAX; ++i)
+        if (i < nc) ws.Uinv[i + NC_MAX * c] = z[i];
+    } else {  // column c of L^-1 (unit lower triangular)
+      double z[NC_MAX];
+#pragma unroll
+      for (int i = 0; i < NC_MAX; ++i) z[i] = 0.0;
+#pragma unroll
+      for (int i = 0; i < NC_MAX; ++i) {
+        if (i >= c && i < nc) {
+          double s = (i == c) ? 1.0 : 0.0;
+#pragma unroll
+          for (int j = 0; j < i; ++j)
+            if (j >= c) s = fma(-LU[i + NC_MAX * j], z[j], s);
+          z[i] = s;
+        }
+      }
+#pragma unroll
+      for (int i = 0; i < NC_MAX; ++i)
+        if (i < nc) ws.Linv[i + NC_MAX * c] = z[i];
+    }
+  }
+  for (int it = P.tid; it < nc * (NX + 1); it += P.nt) {
+    const int i = it % nc, j = it / nc;
+    ws.PC[i + NC_MAX * j] = (j < NX) ? CD[rowOf[i] + NC_MAX * j] : ev[rowOf[i]];
+  }
+}
+HD void luPhaseSolveD(Par P, int nc, const int* colOf, LuSolveWs ws, double* Pu, double* Px, double* u0) {
   const int nut = NU - nc;
-  for (int it = P.tid; it < NX + 1 + nut; it += P.nt) {
-    double y[NC_MAX];
-    if (it <= NX) {
-      // right-hand side column (permuted rows), forward then backward substitution on the leading nc x nc blocks
-      for (int i = 0; i < nc; ++i) y[i] = (it < NX) ? CD[rowOf[i] + NC_MAX * it] : ev[rowOf[i]];
-      for (int k = 0; k < nc; ++k)
-        for (int i = k + 1; i < nc; ++i) y[i] = fma(-LU[i + NC_MAX * k], y[k], y[i]);
-      for (int k = nc - 1; k >= 0; --k) {
-        y[k] /= LU[k + NC_MAX * k];
-        for (int i = 0; i < k; ++i) y[i] = fma(-LU[i + NC_MAX * k], y[k], y[i]);
-      }
-      double* out = (it < NX) ? Px + static_cast<size_t>(NU) * it : u0;
-      for (int i = 0; i < NU; ++i) out[i] = 0.0;
-      for (int i = 0; i < nc; ++i) out[colOf[i]] = -y[i];
+  for (int it = P.tid; it < NU * (NX + 1 + nut); it += P.nt) {
+    const int i = it % NU, j = it / NU;
+    // which position does original column/variable i hold in the permuted order?
+    int pos = 0;
+    for (int t = 0; t < NU; ++t)
+      if (colOf[t] == i) pos = t;
+    if (j < NX) {
+      Px[i + NU * j] = (pos < nc) ? ws.Xt[pos + NC_MAX * j] : 0.0;
+    } else if (j == NX) {
+      u0[i] = (pos < nc) ? ws.Xt[pos + NC_MAX * NX] : 0.0;
     } else {
-      const int kk = it - NX - 1;
-      for (int i = 0; i < nc; ++i) y[i] = -LU[i + NC_MAX * (nc + kk)];
-      for (int k = nc - 1; k >= 0; --k) {
-        y[k] /= LU[k + NC_MAX * k];
-        for (int i = 0; i < k; ++i) y[i] = fma(-LU[i + NC_MAX * k], y[k], y[i]);
-      }
-      double* out = Pu + static_cast<size_t>(NU) * kk;
-      for (int i = 0; i < NU; ++i) out[i] = 0.0;
-      for (int i = 0; i < nc; ++i) out[colOf[i]] = y[i];
-      out[colOf[nc + kk]] = 1.0;
+      const int kk = j - NX - 1;
+      Pu[i + NU * kk] = (pos < nc) ? ws.Kt[pos + NC_MAX * kk] : (pos == nc + kk ? 1.0 : 0.0);
     }
   }
 }

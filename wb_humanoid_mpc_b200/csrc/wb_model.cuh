@@ -24,6 +24,7 @@ constexpr int LEG_LEN = 6;
 struct WbDeviceModel {
   int parent[NB];
   unsigned subtree[NB];  // bit j set <=> body j is in the subtree of body i (including i)
+  int pathLen[NB], path[NB][8];  // joints from the base to body i (inclusive), root side first
   double jR[NB][9], jp[NB][3], axis[NB][3];
   double mass[NB], com[NB][3], Icom[NB][9];
   double mtot, gravity;

@@ -76,7 +76,11 @@ __global__ void __launch_bounds__(LQ_THREADS, 1) lq_kernel(WbDev d) {
   extern __shared__ double smem[];
   const int k = blockIdx.x, b = blockIdx.y;
   if (d.flags[b * F_NF + F_CONVERGED]) return;
-  const WbDeviceModel& m = *d.model;
+  __shared__ WbDeviceModel msh;  // model constants staged once per CTA: the chain sweeps read them in dependent sequences
+  for (int i = threadIdx.x; i < static_cast<int>(sizeof(WbDeviceModel) / 8); i += blockDim.x)
+    reinterpret_cast<double*>(&msh)[i] = reinterpret_cast<const double*>(d.model)[i];
+  __syncthreads();
+  const WbDeviceModel& m = msh;
   const int N = d.N;
   const size_t node = static_cast<size_t>(b) * (N + 1) + k, stage = static_cast<size_t>(b) * N + k;
   NodeIn n;
@@ -294,7 +298,11 @@ __global__ void __launch_bounds__(RO_THREADS) rollout_kernel(WbDev d) {
   extern __shared__ double smem[];
   const int k = blockIdx.x, b = blockIdx.y;
   if (d.flags[b * F_NF + F_CONVERGED] || d.flags[b * F_NF + F_LSDONE]) return;
-  const WbDeviceModel& m = *d.model;
+  __shared__ WbDeviceModel msh;
+  for (int i = threadIdx.x; i < static_cast<int>(sizeof(WbDeviceModel) / 8); i += blockDim.x)
+    reinterpret_cast<double*>(&msh)[i] = reinterpret_cast<const double*>(d.model)[i];
+  __syncthreads();
+  const WbDeviceModel& m = msh;
   const int N = d.N;
   const size_t node = static_cast<size_t>(b) * (N + 1) + k, stage = static_cast<size_t>(b) * N + k;
   const double alpha = d.inst[b * I_ND + I_ALPHA];
