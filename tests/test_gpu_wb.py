@@ -147,3 +147,26 @@ def test_upload_validation(model):
     with pytest.raises(B200SqpError) as e2:
         B200SqpSolver(model).solve()
     assert e2.value.code == -5
+
+
+def test_receding_horizon_warm_start(model):
+    """second MPC cycle: the previous GPU solution is shifted by the reference's warm-start rule (Initialization.cpp:35-79) and the
+    warm-started solve again matches the oracle; the warm start lowers the initial constraint violation of the cold start."""
+    from wb_humanoid_mpc_b200.solver import B200SqpSolver
+
+    rng = np.random.default_rng(5)
+    st = abi.default_settings(model, sqp_iteration=1)
+    insts = make_instances(model, rng, [("stance", 1.1, [0.2, 0.0, 0.7925, 0.0])])
+    solver = B200SqpSolver(model, st)
+    first = solver.run(insts)
+    inst0 = insts[0]
+    prev = references.to_primal_solution(inst0["t_nodes"], inst0["node_event"], first["x"][0], first["u"][0])
+    t1 = 1.0 / 60.0
+    x1 = references.linear_interpolate(t1, prev["t"], prev["x"])
+    warm = references.build_instance(model, x1, t0=t1, horizon=1.1, gait="stance", cmd=[0.2, 0.0, 0.7925, 0.0], previous=prev)
+    second = B200SqpSolver(model, st).run([warm])
+    ref = oracle_solve(model, warm, st)
+    assert rel(second["x"][0], ref["x"]) < 1e-7 and rel(second["u"][0], ref["u"]) < 1e-7
+    g_cold = np.sqrt(first["log"][0, 0, 2] + first["log"][0, 0, 3])
+    g_warm = np.sqrt(second["log"][0, 0, 2] + second["log"][0, 0, 3])
+    assert g_warm < 0.2 * g_cold

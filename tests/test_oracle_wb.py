@@ -280,3 +280,42 @@ def test_walk_instance_schedule(model):
     assert np.all(sw[cf == 1][:, 0] == 0.0)
     assert inst["impact_factor"].min() < 0.1 and inst["impact_factor"].max() <= 1.0 + 1e-12
     assert len(inst["t_nodes"]) > 100
+
+
+def test_warm_start_initialization(model):
+    """initializeStateInputTrajectories: cold start = (x0, weight compensation); warm start interpolates the previous solution inside
+    the overlap and falls back to the initializer for the tail (Initialization.cpp:35-79)."""
+    x0 = np.array(model["x_init"], float)
+    cold = references.build_instance(model, x0, t0=0.0, horizon=1.1, gait="walk")
+    n = len(cold["t_nodes"])
+    assert np.allclose(cold["x_init"], np.tile(x0, (n, 1)))
+    for i in range(n - 1):
+        if cold["node_event"][i] == 1:
+            assert not cold["u_init"][i].any()
+        else:
+            assert np.allclose(cold["u_init"][i], references.weight_compensating_input(model, cold["contact_flags"][i]))
+    # a synthetic previous solution: linear-in-time states/inputs so that interpolation can be checked exactly
+    rng = np.random.default_rng(0)
+    a, b = rng.uniform(-1, 1, model["nx"]), rng.uniform(-1, 1, model["nu"])
+    prev_x = np.array([x0 + t * a for t in cold["t_nodes"]])
+    prev_u = np.array([t * b for t in cold["t_nodes"][:-1]])
+    prev = references.to_primal_solution(cold["t_nodes"], cold["node_event"], prev_x, prev_u)
+    assert len(prev["t"]) == len(prev["x"]) == len(prev["u"])
+    shift = 0.02
+    warm = references.build_instance(model, x0 + shift * a, t0=shift, horizon=1.1, gait="walk", previous=prev)
+    t_state_till, t_input_till = prev["t"][-1], prev["t"][-2]
+    assert np.allclose(warm["x_init"][0], x0 + shift * a)
+    checked_tail = checked_overlap = 0
+    for i in range(len(warm["t_nodes"]) - 1):
+        if warm["node_event"][i] == 1:
+            continue
+        t = references.interval_start(warm["t_nodes"][i], warm["node_event"][i])
+        t_next = warm["t_nodes"][i + 1]
+        if t > t_input_till or t_next > t_state_till:
+            assert np.allclose(warm["u_init"][i], references.weight_compensating_input(model, warm["contact_flags"][i]))
+            assert np.allclose(warm["x_init"][i + 1], warm["x_init"][i])
+            checked_tail += 1
+        elif warm["node_event"][i + 1] == 0 and warm["node_event"][i] == 0:
+            assert np.allclose(warm["x_init"][i + 1], x0 + t_next * a, atol=1e-6)
+            checked_overlap += 1
+    assert checked_tail >= 1 and checked_overlap > 20

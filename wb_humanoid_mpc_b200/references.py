@@ -284,8 +284,69 @@ def weight_compensating_input(model: dict, contacts):
     return u
 
 
-def build_instance(model: dict, x0, t0=0.0, horizon=None, dt=None, gait="stance", gait_start=None, cmd=None):
-    """One MPC instance (cold start) -> dict of per-node arrays in the layout of b200sqp_upload_instances."""
+def linear_interpolate(t, times, data):
+    """LinearInterpolation::interpolate (ocs2_core/include/ocs2_core/misc/implementation/LinearInterpolation.h:67-129): zero-order
+    extrapolation, for duplicated times the lower range ( ] is selected, tiny intervals snap to the closest sample."""
+    times = list(times)
+    if len(times) <= 1:
+        return np.array(data[0], float).copy()
+    index = bisect.bisect_left(times, t) - 1          # lookup::findIntervalInTimeArray
+    last = len(times) - 1
+    if index < 0:
+        idx, alpha = 0, 1.0
+    elif index < last:
+        length, till_next = times[index + 1] - times[index], times[index + 1] - t
+        if length > 2.0 * WEAK_EPS:
+            idx, alpha = index, till_next / length
+        else:
+            idx, alpha = index, (0.0 if till_next < 0.5 * length else 1.0)
+    else:
+        idx, alpha = max(last - 1, 0), 0.0
+    return alpha * np.asarray(data[idx], float) + (1.0 - alpha) * np.asarray(data[idx + 1], float)
+
+
+def to_primal_solution(t_nodes, events, x, u):
+    """multiple_shooting::toPrimalSolution (ocs2_oc/src/multiple_shooting/Helpers.cpp:60-82): inputs at PreEvent nodes repeat the previous
+    input and the last input is repeated so that time, state and input trajectories have equal length."""
+    u = [np.array(r, float) for r in u]
+    for i in range(len(u)):
+        if events[i] == EV_PRE and i > 0:
+            u[i] = u[i - 1].copy()
+    u.append(u[-1].copy())
+    return dict(t=np.array(t_nodes, float), x=np.array(x, float), u=np.array(u))
+
+
+def initialize_state_input_trajectories(model, x0, t_nodes, events, contact, previous=None):
+    """multiple_shooting::initializeStateInputTrajectories (ocs2_oc/src/multiple_shooting/Initialization.cpp:35-79): interpolate the previous
+    primal solution where it overlaps the new horizon, WeightCompInitializer for the tail (and for everything on a cold start)."""
+    n = len(t_nodes)
+    x0 = np.asarray(x0, float)
+    t_state_till = t_input_till = t_nodes[0]
+    if previous is not None and len(previous["t"]) >= 2:
+        t_state_till, t_input_till = previous["t"][-1], previous["t"][-2]
+    xs = []
+    t_init = interval_start(t_nodes[0], events[0])
+    xs.append(linear_interpolate(t_init, previous["t"], previous["x"]) if t_init < t_state_till else x0.copy())
+    us = []
+    for i in range(n - 1):
+        if events[i] == EV_PRE:
+            us.append(np.zeros(model["nu"]))
+            xs.append(xs[-1].copy())
+            continue
+        t = interval_start(t_nodes[i], events[i])
+        t_next = t_nodes[i + 1] - (WEAK_EPS if events[i + 1] == EV_PRE else 0.0)
+        if t > t_input_till or t_next > t_state_till:
+            us.append(weight_compensating_input(model, contact[i]))
+            xs.append(xs[-1].copy())
+        else:
+            us.append(linear_interpolate(t, previous["t"], previous["u"]))
+            xs.append(linear_interpolate(t_next, previous["t"], previous["x"]))
+    return np.array(xs), np.array(us)
+
+
+def build_instance(model: dict, x0, t0=0.0, horizon=None, dt=None, gait="stance", gait_start=None, cmd=None, previous=None):
+    """One MPC instance -> dict of per-node arrays in the layout of b200sqp_upload_instances.
+    `previous` = to_primal_solution(...) of the last solve enables the reference's warm start; None is a cold start."""
     sq = model["sqp"]
     horizon = sq["timeHorizon"] if horizon is None else horizon
     dt = sq["dt"] if dt is None else dt
@@ -309,7 +370,6 @@ def build_instance(model: dict, x0, t0=0.0, horizon=None, dt=None, gait="stance"
     impact = np.ones((n, 2))
     arm = np.zeros(n)
     xref = np.zeros((n, nx))
-    u_init = np.zeros((n - 1, nu))
     for i in range(n):
         t = interval_start(t_nodes[i], events[i])
         m = ms.mode_at(t)
@@ -319,8 +379,6 @@ def build_instance(model: dict, x0, t0=0.0, horizon=None, dt=None, gait="stance"
             impact[i, c] = planner.impact_factor(c, t)
         arm[i] = math.sin(2 * math.pi * (phase_variable(ms, t) - 0.15))
         xref[i] = interp_targets(tt, ts, t)
-        if i < n - 1 and events[i] != EV_PRE:
-            u_init[i] = weight_compensating_input(model, contact[i])
-    x_init = np.tile(x0, (n, 1))
+    x_init, u_init = initialize_state_input_trajectories(model, x0, t_nodes, events, contact, previous)
     return dict(x0=x0, x_init=x_init, u_init=u_init, t_nodes=t_nodes, node_event=events, contact_flags=contact, swing_ref=swing,
                 impact_factor=impact, arm_phase=arm, x_ref=xref, mode_schedule=ms)
