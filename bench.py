@@ -268,8 +268,19 @@ def main():
         pass
     peak = peaks.get("hbm_gbs", 6650.0)
     achieved = alg[dom] / (stage_ms[dom] * 1e-3) / 1e9
+    # measured DRAM traffic of the same kernel from the latest committed `ncu --set full` capture (taken at batch 64), scaled per stage
+    traffic = None
+    try:
+        short = ["lq", "ric", "ro"][dom]
+        raws = sorted((ROOT / "profiles").glob(f"ncu_{short}_*_raw.json"))
+        if raws:
+            raw = json.loads(raws[-1].read_text())
+            per_stage = (float(raw["dram__bytes_read.sum"]) + float(raw["dram__bytes_write.sum"])) * 1e6 / (64 * N)
+            traffic = per_stage * B * N
+    except Exception:
+        traffic = None
     roofline = {"kernel": names[dom], "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "traffic": None, "peak_source": "MEASURED_PEAKS.json (measured)" if peaks else "fallback 6.65 TB/s",
+                "traffic": traffic, "peak_source": "MEASURED_PEAKS.json (measured)" if peaks else "fallback 6.65 TB/s",
                 "algorithmic_bytes_per_launch": alg[dom], "stage_ms": {"lq": stage_ms[0], "qp": stage_ms[1], "linesearch": stage_ms[2]},
                 "note": "fp64-pipe bound, not HBM bound: see DESIGN.md; the per-stage device times are CUDA events on the launching stream"}
 
