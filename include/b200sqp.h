@@ -113,6 +113,7 @@ typedef struct b200sqp_settings {
   double reg_prim;             /* HPIPM reg_prim */
   int32_t use_feedback_policy; /* useFeedbackPolicy: compute remapped K (toPrimalSolution, SqpSolver.cpp:331-344) */
   int32_t global_step;         /* 0: per-instance line search (reference semantics); 1: one step size for the whole (multi-GPU) batch */
+  int32_t create_value_function; /* createValueFunction: keep the Riccati cost-to-go (extractValueFunction, SqpSolver.cpp:321-329) */
 } b200sqp_settings;
 void b200sqp_default_settings(b200sqp_settings* s);
 
@@ -155,13 +156,18 @@ typedef struct b200sqp_iter_log {
  *   log [B][sqp_iteration], n_iter [B], status [B]. Synchronises. */
 int b200sqp_download(b200sqp_handle h, double* x, double* u, double* K, b200sqp_iter_log* log, int32_t* n_iter, int32_t* status);
 
+/* SqpSolver::getValueFunction data (needs settings.create_value_function): quadratic cost-to-go of the last iteration's QP,
+ * re-centred on the linearisation trajectory as in extractValueFunction (dfdx -= dfdxx * x):  P [B][n_nodes][nx*nx], p [B][n_nodes][nx]. */
+int b200sqp_download_value_function(b200sqp_handle h, double* P, double* p);
+
 /* Stage blocks of the last LQ approximation, for block-level parity tests:
  *   which = 0 raw (before projection): A [nx*nx] B [nx*nu] b [nx] Q S(nu x nx) R q r C(nc_max x nx) D(nc_max x nu) e nc
  *   see b200sqp_stage_layout for offsets. */
 int b200sqp_download_stage_blocks(b200sqp_handle h, int which, double* out, int64_t out_doubles);
 int b200sqp_stage_doubles(b200sqp_handle h, int which, int64_t* per_node);
 
-/* SqpSolver::getBenchmarks(): device ms of {LQ approximation, solve QP, line search, compute controller} of the last solve */
+/* SqpSolver::getBenchmarks(): device ms of {LQ approximation, solve QP, line search} of the last solve; ms[3] = the share of ms[0] spent in
+ * the projection kernel (the reference's fourth timer, computeController, has no separate counterpart: the remap runs inside the QP stage) */
 int b200sqp_get_stage_times(b200sqp_handle h, float ms[4]);
 /* number of kernel launches issued by the last b200sqp_solve */
 int b200sqp_get_launch_count(b200sqp_handle h, int64_t* launches);

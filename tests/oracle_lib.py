@@ -262,6 +262,13 @@ class WbOracle:
         self.L.orc_wb_last_qp(self.h, _p(dx), _p(du), _p(K), _pi(nut))
         return dict(x=xs, u=us, log=log[: nit.value], dx=dx, du=du, K=np.swapaxes(K, 1, 2).copy(), nut=nut)
 
+    def last_value_function(self, x_lin):
+        n = len(x_lin)
+        P, p = np.zeros((n, self.nx, self.nx)), np.zeros((n, self.nx))
+        rc = self.L.orc_wb_last_value_function(self.h, _p(F(x_lin)), _p(P), _p(p))
+        assert rc == 0
+        return np.swapaxes(P, 1, 2).copy(), p
+
     def raw_per_node(self):
         nx, nu = self.nx, self.nu
         return 2 * nx * nx + 2 * nx * nu + nu * nu + 2 * nx + nu + 1 + 14 * (nx + nu + 1) + 1

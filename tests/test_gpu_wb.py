@@ -170,3 +170,21 @@ def test_receding_horizon_warm_start(model):
     g_cold = np.sqrt(first["log"][0, 0, 2] + first["log"][0, 0, 3])
     g_warm = np.sqrt(second["log"][0, 0, 2] + second["log"][0, 0, 3])
     assert g_warm < 0.2 * g_cold
+
+
+def test_value_function_matches_oracle(model):
+    """createValueFunction: Riccati cost-to-go re-centred as in SqpSolver::extractValueFunction (SqpSolver.cpp:321-329)"""
+    from wb_humanoid_mpc_b200.solver import B200SqpSolver
+
+    rng = np.random.default_rng(6)
+    insts = make_instances(model, rng, [("stance", 0.8, None)])
+    st = abi.default_settings(model, sqp_iteration=1, create_value_function=1)
+    solver = B200SqpSolver(model, st)
+    solver.run(insts)
+    P, p = solver.value_function()
+    wb = orc.WbOracle(model)
+    inst = insts[0]
+    wb.set_nodes(inst["contact_flags"], inst["swing_ref"], inst["impact_factor"], inst["arm_phase"], inst["x_ref"])
+    wb.sqp(inst["t_nodes"], inst["node_event"], inst["x0"], inst["x_init"], inst["u_init"], st)
+    Po, po = wb.last_value_function(inst["x_init"])
+    assert rel(P[0], Po) < 1e-7 and rel(p[0], po) < 1e-6

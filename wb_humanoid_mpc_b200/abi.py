@@ -69,6 +69,7 @@ class Settings(C.Structure):
         ("reg_prim", C.c_double),
         ("use_feedback_policy", C.c_int32),
         ("global_step", C.c_int32),
+        ("create_value_function", C.c_int32),
     ]
 
 
@@ -80,7 +81,7 @@ class IterLog(C.Structure):
 def default_settings(model: dict | None = None, **over) -> Settings:
     """sqp::Settings defaults (SqpSettings.h:42-86) overridden by the G1 task.info values, then by keyword arguments."""
     s = Settings(sqp_iteration=1, delta_tol=1e-4, cost_tol=1e-4, alpha_decay=0.5, alpha_min=1e-4, gamma_c=1e-6, g_max=1e-2, g_min=1e-6,
-                 armijo_factor=1e-4, reg_prim=1e-12, use_feedback_policy=0, global_step=0)
+                 armijo_factor=1e-4, reg_prim=1e-12, use_feedback_policy=0, global_step=0, create_value_function=0)
     if model is not None:
         sq = model["sqp"]
         s.sqp_iteration, s.delta_tol, s.g_max, s.g_min = sq["sqpIteration"], sq["deltaTol"], sq["g_max"], sq["g_min"]

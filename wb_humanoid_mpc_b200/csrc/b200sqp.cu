@@ -236,6 +236,7 @@ void b200sqp_default_settings(b200sqp_settings* s) {
   s->reg_prim = 1e-12;
   s->use_feedback_policy = 0;
   s->global_step = 0;
+  s->create_value_function = 0;
 }
 
 }  // extern "C"

@@ -28,8 +28,7 @@ struct DynWs {
   // bodies (pelvis coordinates)
   double Rj[NB][9];  // joint placement times joint rotation (parent-relative), computed body-parallel before the chain sweep
   double R[NB][9], p[NB][3], S[NB][6], v[NB][6], a[NB][6], psd[NB][6], psdd[NB][6];
-  double I[NB][36], Bm[NB][36], f[NB][6];
-  double IC[NB][36], BC[NB][36], fC[NB][6];
+  double I[NB][36], Bm[NB][36], f[NB][6];  // per body; folded IN PLACE into subtree composites by dynPhaseComposite
   // finals
   double pc[2][3], lf[2][3], lm[2][3];  // contact points, local contact force / moment
   double N[6], IcInv[9], y[3], qddb[6];
@@ -245,23 +244,21 @@ HD void dynPhaseBmat(Par P, DynWs& w) {
   }
 }
 
-// ---- phase 4: composites = sums over subtrees (common coordinates): one item per matrix entry, children folded into parents
-// in decreasing body order (bodies are numbered parent-before-child).  The value-only path needs the root composite only.
+// ---- phase 4: composites = sums over subtrees (common coordinates), folded in place: one item per matrix entry, children added to
+// parents in decreasing body order (bodies are numbered parent-before-child).  After this phase I, Bm, f hold IC, BC, fC.
+// The value-only path needs the root composite only.
 template <bool DERIV>
 HD void dynPhaseComposite(Par P, const WbDeviceModel& m, DynWs& w) {
   if (DERIV) {
     for (int e = P.tid; e < 78; e += P.nt) {
       if (e < 36) {
-        for (int i = 0; i < NB; ++i) w.IC[i][e] = w.I[i][e];
-        for (int i = NB - 1; i >= 1; --i) w.IC[m.parent[i]][e] += w.IC[i][e];
+        for (int i = NB - 1; i >= 1; --i) w.I[m.parent[i]][e] += w.I[i][e];
       } else if (e < 72) {
         const int k = e - 36;
-        for (int i = 0; i < NB; ++i) w.BC[i][k] = w.Bm[i][k];
-        for (int i = NB - 1; i >= 1; --i) w.BC[m.parent[i]][k] += w.BC[i][k];
+        for (int i = NB - 1; i >= 1; --i) w.Bm[m.parent[i]][k] += w.Bm[i][k];
       } else {
         const int k = e - 72;
-        for (int i = 0; i < NB; ++i) w.fC[i][k] = w.f[i][k];
-        for (int i = NB - 1; i >= 1; --i) w.fC[m.parent[i]][k] += w.fC[i][k];
+        for (int i = NB - 1; i >= 1; --i) w.f[m.parent[i]][k] += w.f[i][k];
       }
     }
   } else {
@@ -269,10 +266,10 @@ HD void dynPhaseComposite(Par P, const WbDeviceModel& m, DynWs& w) {
       double s = 0.0;
       if (e < 36) {
         for (int i = 0; i < NB; ++i) s += w.I[i][e];
-        w.IC[0][e] = s;
+        w.I[0][e] = s;
       } else {
         for (int i = 0; i < NB; ++i) s += w.f[i][e - 36];
-        w.fC[0][e - 36] = s;
+        w.f[0][e - 36] = s;
       }
     }
   }
@@ -292,11 +289,11 @@ HD void dynPhaseFinal(Par P, const WbDeviceModel& m, const double* u, DynWs& w) 
     E.l = E.l + lf;
     E.a = E.a + cross(pc, lf) + lm;
   }
-  const V6 N = E - ld6(w.fC[0]);
+  const V6 N = E - ld6(w.f[0]);
   st6(w.N, N);
   double Ic[9];
   for (int r = 0; r < 3; ++r)
-    for (int k = 0; k < 3; ++k) Ic[3 * r + k] = w.IC[0][6 * (3 + r) + 3 + k];
+    for (int k = 0; k < 3; ++k) Ic[3 * r + k] = w.I[0][6 * (3 + r) + 3 + k];
   inv3(Ic, w.IcInv);
   const V3 y = mv(w.IcInv, N.a);
   st3(w.y, y);
@@ -335,7 +332,7 @@ HD void dynPhaseJacobian(Par P, const WbDeviceModel& m, const DynWs& w, double* 
       const int dir = d < 6 ? d - 3 : 3 + (d - NV);
       const V6 dv0 = ld6(w.dv0[dir]), da0 = ld6(w.da0[dir]);
       const V6 v0 = ld6(w.v0);
-      const V6 dF = 2.0 * m6v(w.BC[0], dv0) + m6v(w.IC[0], mcross(v0, dv0) + da0);
+      const V6 dF = 2.0 * m6v(w.Bm[0], dv0) + m6v(w.I[0], mcross(v0, dv0) + da0);
       dN = V6{-dF.l, -dF.a};
       if (d < 6) {
         const double* dR = w.dRb[dir];
@@ -353,7 +350,7 @@ HD void dynPhaseJacobian(Par P, const WbDeviceModel& m, const DynWs& w, double* 
     } else if (d < NV) {  // joint position q_k
       const int k = d - 6 + 1;
       const V6 S = ld6(w.S[k]);
-      const V6 dF = fcross(S, ld6(w.fC[k])) + m6v(w.IC[k], ld6(w.psdd[k])) + 2.0 * m6v(w.BC[k], ld6(w.psd[k]));
+      const V6 dF = fcross(S, ld6(w.f[k])) + m6v(w.I[k], ld6(w.psdd[k])) + 2.0 * m6v(w.Bm[k], ld6(w.psd[k]));
       dN = V6{-dF.l, -dF.a};
       for (int c = 0; c < 2; ++c) {
         const int b = m.frameBody[3 * c];
@@ -363,7 +360,7 @@ HD void dynPhaseJacobian(Par P, const WbDeviceModel& m, const DynWs& w, double* 
         }
       }
       // d Ic = rot block of (S x* IC - IC S x)
-      const double* X = w.IC[k];
+      const double* X = w.I[k];
       double dIc[9];
       const double sx[9] = {0, -S.l.z, S.l.y, S.l.z, 0, -S.l.x, -S.l.y, S.l.x, 0};
       const double wx[9] = {0, -S.a.z, S.a.y, S.a.z, 0, -S.a.x, -S.a.y, S.a.x, 0};
@@ -381,7 +378,7 @@ HD void dynPhaseJacobian(Par P, const WbDeviceModel& m, const DynWs& w, double* 
       baseAccTangent(m, w, dN, dIc, nullptr, nullptr, col);
     } else if (d < NX) {  // joint velocity qd_k
       const int k = d - NV - 6 + 1;
-      const V6 dF = 2.0 * (m6v(w.IC[k], ld6(w.psd[k])) + m6v(w.BC[k], ld6(w.S[k])));
+      const V6 dF = 2.0 * (m6v(w.I[k], ld6(w.psd[k])) + m6v(w.Bm[k], ld6(w.S[k])));
       dN = V6{-dF.l, -dF.a};
       baseAccTangent(m, w, dN, nullptr, nullptr, nullptr, col);
     } else if (d < NX + 12) {  // contact wrench components
@@ -397,7 +394,7 @@ HD void dynPhaseJacobian(Par P, const WbDeviceModel& m, const DynWs& w, double* 
       baseAccTangent(m, w, dN, nullptr, nullptr, nullptr, col);
     } else {  // joint acceleration qdd_k
       const int k = d - NX - 12 + 1;
-      const V6 dF = m6v(w.IC[k], ld6(w.S[k]));
+      const V6 dF = m6v(w.I[k], ld6(w.S[k]));
       dN = V6{-dF.l, -dF.a};
       baseAccTangent(m, w, dN, nullptr, nullptr, nullptr, col);
     }

@@ -17,8 +17,8 @@
 
 namespace b200sqp {
 
-constexpr int HLD = NZ;        // Hessian [Q S'; S R] stored as one 93 x 93 column-major block
-constexpr int JR_MAX = 18;     // weighted Gauss-Newton / penalty rows processed per group (lives in the G[1..3] slots)
+constexpr int JR_MAX = 52;     // Gauss-Newton / penalty rows of one node: 2 x 18 (both feet swinging) + 16 collision rows
+constexpr int JR_CHUNK = 18;   // rows staged per Hessian accumulation step in K1b
 
 struct NodeIn {  // per-node inputs (see b200sqp_upload_instances)
   const double *x, *u, *xnext, *xref;
@@ -29,7 +29,23 @@ struct NodeIn {  // per-node inputs (see b200sqp_upload_instances)
   int terminal;
 };
 
-// shared-memory map of the LQ kernel (offsets in doubles)
+// Intermediate record written by K1a (node physics) and consumed by K1b (dense algebra), one per intermediate node, in HBM/L2.
+// Offsets in doubles.
+struct Mid {
+  static constexpr int AB12 = 0;                         // 12 x 93 (ld 12): rows 0-5 base-position rows of [A|B], rows 6-11 base-velocity rows
+  static constexpr int B_ = AB12 + 12 * NZ;              // defect b (58)
+  static constexpr int CD = B_ + NX;                     // 14 x 93 (ld 14)
+  static constexpr int E = CD + NC_MAX * NZ;             // 14
+  static constexpr int HDG = E + NC_MAX;                 // Hessian diagonal (93), not yet multiplied by dt
+  static constexpr int GQ = HDG + NZ;                    // cost gradient (93)
+  static constexpr int FRIC = GQ + NZ;                   // 2 x (3 x 3) friction-cone Hessian blocks
+  static constexpr int JR = FRIC + 18;                   // weighted rows (ld JR_MAX) x 93
+  static constexpr int COEF = JR + JR_MAX * NZ;          // gradient coefficient per row (already folded into GQ; kept for inspection)
+  static constexpr int META = COEF + JR_MAX;             // nc, nrows, dt*cost, dt
+  static constexpr int JF = META + 4;                    // scratch: dense foot Jacobians 2 x (18 x 93)
+  static constexpr int SIZE = JF + 2 * FQ * NZ;
+};
+
 struct NodeOut {  // global-memory destinations of one node
   double *A, *Bt, *b, *Q, *St, *Rt, *q, *rt;  // projected stage record in the QP layout (nx = 58, nu_max = 23)
   double *Pu, *Px, *u0;                       // projection u = Pu ut + Px dx + u0
@@ -38,52 +54,77 @@ struct NodeOut {  // global-memory destinations of one node
   double* raw;                                // optional raw (pre-projection) block dump, oracle layout; may be null
 };
 
+// shared-memory map of K1a (node physics)
 struct LqWs {
-  DynWs* dyn;      // R1 (later: LU, Pu, Px, u0)
-  double* G;       // R2: 4 x (6 x 93)  (later: JR rows)
-  double* JF;      // R3: 2 x (18 x 93) (later: T1 = S + R Px)
-  double* H;       // R4: 93 x 93       (first used as scratch for JFl, FP, DFP)
-  double* AB;      // R5: 58 x 93  [A | B]
-  double* CD;      // R6: 14 x 93 (ld 14) then e (14)
-  double* fs;      // 4 x 58 stage flows, then b (58)
+  DynWs* dyn;
+  double* G;       // 4 x (6 x 93)
+  double *JFl, *FP, *DFP, *tmpG;
+  double* fs;      // 4 x 58 stage flows, b (58), stage point (58)
   double* FV;      // 2 x 18 foot values
-  double* vec;     // q-gradient (93), misc scalars
-  // aliases
-  double *JFl, *FP, *DFP, *JR, *LU, *Pu, *Px, *u0, *T1, *ev, *gq, *sc;
-  int* iw;         // small integer scratch (pivots), lives in vec tail
+  double *gq, *hd, *pv, *sc, *rowCoef, *rowVal;
 };
-
 HD size_t lqWsDoubles() {
   const size_t dynD = (sizeof(DynWs) + 7) / 8;
-  return dynD + 4 * 6 * NZ + 2 * FQ * NZ + static_cast<size_t>(NZ) * NZ + static_cast<size_t>(NX) * NZ + (NC_MAX * NZ + NC_MAX) + 6 * NX +
-         2 * FQ + (NZ + 256);
+  return dynD + 4 * 6 * NZ + 2 * FLOC * FQ + 3 * NFRAMES + NFRAMES * 15 * 3 + 6 * NX + 2 * FQ + 2 * NZ + 96 + 16 + 2 * JR_MAX + 8;
 }
 HD void lqWsMap(double* base, LqWs& s) {
   const size_t dynD = (sizeof(DynWs) + 7) / 8;
   s.dyn = reinterpret_cast<DynWs*>(base);
   s.G = base + dynD;
-  s.JF = s.G + 4 * 6 * NZ;
-  s.H = s.JF + 2 * FQ * NZ;
-  s.AB = s.H + static_cast<size_t>(NZ) * NZ;
-  s.CD = s.AB + static_cast<size_t>(NX) * NZ;
-  s.fs = s.CD + NC_MAX * NZ + NC_MAX;
+  s.JFl = s.G + 4 * 6 * NZ;
+  s.FP = s.JFl + 2 * FLOC * FQ;
+  s.DFP = s.FP + 3 * NFRAMES;
+  s.tmpG = s.JFl;  // the local foot tangents are dead once the stage-0 Jacobians are assembled (6 x 93 <= 2 x 36 x 18)
+  s.fs = s.DFP + NFRAMES * 15 * 3;
   s.FV = s.fs + 6 * NX;
-  s.vec = s.FV + 2 * FQ;
-  s.ev = s.CD + NC_MAX * NZ;
-  s.gq = s.vec;            // 93
-  s.sc = s.vec + NZ;       // scalars: [0] cost, [1] nc, [2] nut, [3..] penalties
-  s.iw = reinterpret_cast<int*>(s.vec + NZ + 64);  // 96 doubles = 192 ints
-  // scratch inside AB before [A|B] is assembled
-  s.JFl = s.AB;                         // 2*36*18 = 1296
-  s.FP = s.AB + 2 * FLOC * FQ;          // 30
-  s.DFP = s.FP + 3 * NFRAMES;           // 10*15*3 = 450
-  // aliases of dead regions
-  s.JR = s.G + 6 * NZ;                  // JR_MAX x 93 (ld JR_MAX) = 1674 = the G[1..3] slots, free until the later RK stages
-  s.LU = base;                          // 14 x 35
-  s.Pu = base + NC_MAX * NU;            // 35 x 23
-  s.Px = s.Pu + NU * NUT_MAX;           // 35 x 58
-  s.u0 = s.Px + NU * NX;                // 35
-  s.T1 = s.JF;                          // 35 x 58 (2030 <= 3348)
+  s.gq = s.FV + 2 * FQ;
+  s.hd = s.gq + NZ;
+  s.pv = s.hd + NZ;
+  s.sc = s.pv + 96;
+  s.rowCoef = s.sc + 16;
+  s.rowVal = s.rowCoef + JR_MAX;
+}
+
+// shared-memory map of K1b (projection + change of variables): <= 104 KB so that two CTAs share an SM
+struct PjWs {
+  double *Px, *Pu, *u0;          // 35 x 58, 35 x 23, 35
+  double *Q, *S, *R;             // 58 x 58, 35 x 58 (ld 35), 35 x 35
+  double *gq, *rr, *bvec, *sc;   // 93, 35, 58, 16
+  double* scratch;               // 3072 doubles: {CD, e, LU, AB12} -> {JR chunk} -> {T1, RPu}
+  int* iw;
+  // views into scratch
+  double *CD, *ev, *LU, *AB12, *JRc, *T1, *RPu, *Uinv, *Linv, *PC, *T, *Xt, *Kt;
+};
+HD size_t pjWsDoubles() { return NU * NX + NU * NUT_MAX + 36 + NX * NX + NU * NX + NU * NU + 1 + NZ + 1 + 36 + NX + 16 + 4400 + 64; }
+HD void pjWsMap(double* base, PjWs& s) {
+  s.Px = base;
+  s.Pu = s.Px + NU * NX;
+  s.u0 = s.Pu + NU * NUT_MAX;
+  s.Q = s.u0 + 36;
+  s.S = s.Q + NX * NX;
+  s.R = s.S + NU * NX;
+  s.gq = s.R + NU * NU + 1;
+  s.rr = s.gq + NZ + 1;
+  s.bvec = s.rr + 36;
+  s.sc = s.bvec + NX;
+  s.scratch = s.sc + 16;
+  s.iw = reinterpret_cast<int*>(s.scratch + 4400);
+  // phase 1 (projection): CD | e | LU | triangular-solve workspace
+  s.CD = s.scratch;                          // 14 x 93 = 1302
+  s.ev = s.CD + NC_MAX * NZ;                 // 14
+  s.LU = s.ev + NC_MAX;                      // 14 x 35 = 490
+  s.Uinv = s.LU + NC_MAX * NU;               // 196
+  s.Linv = s.Uinv + NC_MAX * NC_MAX;         // 196
+  s.PC = s.Linv + NC_MAX * NC_MAX;           // 14 x 59 = 826
+  s.T = s.PC + NC_MAX * (NX + 1);            // 826   (ends at 3850)
+  s.Xt = s.CD;                               // CD is dead once PC holds the permuted copy: 826
+  s.Kt = s.PC;                               // PC is dead once T = L^-1 PC exists: 14 x 23 = 322
+  // phase 2 (dynamics change of variables)
+  s.AB12 = s.scratch;                        // 12 x 93 = 1116
+  // phase 3 (Hessian) / phase 4 (cost change of variables)
+  s.JRc = s.scratch;                         // 18 x 93 = 1674
+  s.T1 = s.scratch;                          // 35 x 58 = 2030
+  s.RPu = s.scratch + NU * NX;               // 35 x 23 = 805  (ends at 2835)
 }
 
 HD void penRelaxed(double mu, double delta, double h, double& v, double& d1, double& d2) {
@@ -158,28 +199,38 @@ HD void rkPhaseChainStage(Par P, int s, double dt, double* G, double* tmp /*6 x 
   }
 }
 
-// A = I + sum_s w_s dk_s/dx, B = sum_s w_s dk_s/du ; b = x + sum w_s k_s - xnext  (AB is 58 x 93 column-major, ld 58)
-HD void rkPhaseAssemble(Par P, double dt, const double* x, const double* xnext, const double* G, const double* fs, double* AB, double* b) {
+// The 12 dense rows of [A | B] (A = I + sum_s w_s dk_s/dx, B = sum_s w_s dk_s/du): base position rows 0-5 and base velocity rows 29-34;
+// every other row is a fixed pattern (q_j+ = q_j + dt v_j + dt^2/2 a_j, v_j+ = v_j + dt a_j).  b = x + sum w_s k_s - xnext.
+HD void rkPhaseAssemble12(Par P, double dt, const double* x, const double* xnext, const double* G, const double* fs, double* AB12, double* b) {
   const double w[4] = {dt / 6.0, dt / 3.0, dt / 3.0, dt / 6.0};
   const double cs[4] = {0.0, 0.5 * dt, 0.5 * dt, dt};
-  for (int it = P.tid; it < NX * NZ; it += P.nt) {
-    const int r = it % NX, d = it / NX;
+  for (int it = P.tid; it < 12 * NZ; it += P.nt) {
+    const int rr = it % 12, d = it / 12;
+    const int r = rr < 6 ? rr : NV + (rr - 6);
     double acc = (r == d) ? 1.0 : 0.0;
-    if (r < NV) {
-      // position rows: sum_s w_s Xv_s(r, d)
+    if (rr < 6) {
       for (int s = 0; s < 4; ++s) acc = fma(w[s], xvEntry(s > 0 ? G + (s - 1) * 6 * NZ : nullptr, cs[s], r, d), acc);
-    } else if (r < NV + 6) {
-      for (int s = 0; s < 4; ++s) acc = fma(w[s], G[s * 6 * NZ + (r - NV) + 6 * d], acc);
     } else {
-      if (d == NX + 12 + (r - NV - 6)) acc += dt;
+      for (int s = 0; s < 4; ++s) acc = fma(w[s], G[s * 6 * NZ + (rr - 6) + 6 * d], acc);
     }
-    AB[it] = acc;
+    AB12[it] = acc;
   }
   for (int r = P.tid; r < NX; r += P.nt) {
     double acc = x[r];
     for (int s = 0; s < 4; ++s) acc = fma(w[s], fs[s * NX + r], acc);
     b[r] = acc - xnext[r];
   }
+}
+// dense entry (r, d) of [A | B] from the 12 stored rows and the fixed pattern
+HD double abEntry(const double* AB12, double dt, int r, int d) {
+  if (r < 6) return AB12[r + 12 * d];
+  if (r >= NV && r < NV + 6) return AB12[6 + (r - NV) + 12 * d];
+  if (r < NV) {  // joint position row
+    const int j = r - 6;
+    return (d == r ? 1.0 : 0.0) + (d == NV + r ? dt : 0.0) + (d == NX + 12 + j ? 0.5 * dt * dt : 0.0);
+  }
+  const int j = r - NV - 6;  // joint velocity row
+  return (d == r ? 1.0 : 0.0) + (d == NX + 12 + j ? dt : 0.0);
 }
 
 // ---- equality constraints C dx + D du + e (collection order of WBMpcInterface.cpp:172-181) ----------------------------------------------
@@ -221,13 +272,12 @@ HD void conPhaseAssemble(Par P, const WbDeviceModel& m, const NodeIn& n, const d
 
 // ---- costs ------------------------------------------------------------------------------------------------------------------------------------
 // phase A: zero H, diagonal terms, gradient of the quadratic tracking cost, joint limits, friction cone (items over 93 + a few)
-HD void costPhaseInit(Par P, const WbDeviceModel& m, const NodeIn& n, double* H, double* gq, double* sc) {
-  for (int it = P.tid; it < NZ * NZ; it += P.nt) H[it] = 0.0;
+HD void costPhaseInit(Par P, double* gq, double* sc) {
   for (int i = P.tid; i < NZ; i += P.nt) gq[i] = 0.0;
   if (P.tid == 0) sc[0] = 0.0;
 }
 template <bool DERIV = true>
-HD void costPhaseDiagonal(Par P, const WbDeviceModel& m, const NodeIn& n, double* H, double* gq, double* pv /*partial values, 96*/) {
+HD void costPhaseDiagonal(Par P, const WbDeviceModel& m, const NodeIn& n, double* hdiag, double* gq, double* pv /*partial values, 96*/) {
   // friction-cone penalty derivative (needed for the Hessian shift on every diagonal entry)
   double fricD1[2] = {0.0, 0.0};
   for (int c = 0; c < 2; ++c)
@@ -274,7 +324,7 @@ HD void costPhaseDiagonal(Par P, const WbDeviceModel& m, const NodeIn& n, double
       hd += m.Rd[j];
     }
     if (DERIV) {
-      H[i + HLD * i] += hd;
+      hdiag[i] = hd;
       gq[i] += g;
     }
     pv[i] = val;
@@ -282,9 +332,11 @@ HD void costPhaseDiagonal(Par P, const WbDeviceModel& m, const NodeIn& n, double
 }
 // friction cone blocks (items = contacts): value, gradient, 3x3 Hessian block  (FrictionForceConeConstraint.cpp:145-224)
 template <bool DERIV = true>
-HD void costPhaseFriction(Par P, const WbDeviceModel& m, const NodeIn& n, double* H, double* gq, double* pv) {
+HD void costPhaseFriction(Par P, const WbDeviceModel& m, const NodeIn& n, double* fric /*2 x 9*/, double* gq, double* pv) {
   for (int c = P.tid; c < 2; c += P.nt) {
     pv[NZ + c] = 0.0;
+    if (DERIV)
+      for (int k = 0; k < 9; ++k) fric[9 * c + k] = 0.0;
     if (!n.contact[c]) continue;
     const double* F = n.u + 6 * c;
     const double Ft2 = F[0] * F[0] + F[1] * F[1] + m.fricReg, Ft = sqrt(Ft2), Ft32 = Ft * Ft2;
@@ -298,7 +350,7 @@ HD void costPhaseFriction(Par P, const WbDeviceModel& m, const NodeIn& n, double
     const int o = NX + 6 * c;
     for (int i = 0; i < 3; ++i) {
       gq[o + i] += d1 * dh[i];
-      for (int j = 0; j < 3; ++j) H[(o + i) + HLD * (o + j)] += d2 * dh[i] * dh[j] + d1 * ddh[3 * i + j];
+      for (int j = 0; j < 3; ++j) fric[9 * c + 3 * i + j] = d2 * dh[i] * dh[j] + d1 * ddh[3 * i + j];
     }
   }
 }
@@ -318,7 +370,7 @@ HD void collisionPair(int r, int& a, int& b, bool& knee) {
   knee = (r == 9);
 }
 HD void costPhaseRows(Par P, const WbDeviceModel& m, const NodeIn& n, int g, const double* JF, const double* FV, const DynWs& w, const double* FP,
-                      const double* DFP, double* JR, double* rowCoef, double* rowVal, bool valuesOnly = false) {
+                      const double* DFP, double* JR, int ldJR, double* rowCoef, double* rowVal, bool valuesOnly = false) {
   const int nr = groupRows(n, g);
   // one item per (row, entry); entry == NZ carries the row scalars
   for (int it = P.tid; it < nr * (valuesOnly ? 1 : NZ + 1); it += P.nt) {
@@ -403,18 +455,20 @@ HD void costPhaseRows(Par P, const WbDeviceModel& m, const NodeIn& n, int g, con
         }
       }
     }
-    if (d < NZ) JR[r + JR_MAX * d] = entry;
+    if (d < NZ) JR[r + ldJR * d] = entry;
     else {
       rowCoef[r] = coef;
       rowVal[r] = value;
     }
   }
 }
-// H += JR' JR ; gq += JR' coef
-HD void costPhaseAccumulate(Par P, int nr, const double* JR, const double* rowCoef, double* H, double* gq) {
-  if (nr == 0) return;
-  par_mma_gemm<true, true, 4>(P, NZ, NZ, nr, 1.0, JR, JR_MAX, JR, JR_MAX, H, HLD);
-  par_gemv<true, true>(P, NZ, nr, 1.0, JR, JR_MAX, rowCoef, gq);
+// gq += JR' coef for one row group (K1a; the Hessian part JR'JR is formed in K1b)
+HD void costPhaseGradient(Par P, int nr, const double* JR, int ldJR, const double* rowCoef, double* gq) {
+  for (int i = P.tid; i < NZ; i += P.nt) {
+    double acc = 0.0;
+    for (int r = 0; r < nr; ++r) acc = fma(JR[r + ldJR * i], rowCoef[r], acc);
+    gq[i] += acc;
+  }
 }
 
 // ---- projection: Eigen::FullPivLU semantics (complete pivoting; particular solution with free variables = 0; kernel basis) ----------------

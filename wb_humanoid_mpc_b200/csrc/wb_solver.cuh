@@ -1,5 +1,6 @@
 // Device kernels of the whole-body SQP iteration and the per-handle device state.
-//   K1 lq_kernel        one CTA per (instance, shooting node): LQ approximation + projection   (SqpSolver::setupQuadraticSubproblem)
+//   K1a lq_dyn_kernel   one CTA per (instance, shooting node): dynamics/cost/constraint linearisation  (SqpSolver::setupQuadraticSubproblem)
+//   K1b lq_proj_kernel  one CTA per (instance, stage): constraint projection + change of input variables (projectTranscription)
 //   K2 riccati_kernel   riccati.cuh                                                            (HpipmInterface::solve)
 //   K4a remap_kernel    du = Pu dut + Px dx + u0, K = Pu Kt + Px, Armijo / norm partial sums    (remapProjectedInput/Gain, armijoDescentMetric)
 //   K3 rollout_kernel   one CTA per (instance, node): value-only RK4 defect, cost, constraints at x + alpha dx   (computePerformance)
@@ -13,7 +14,8 @@
 
 namespace b200sqp {
 
-constexpr int LQ_THREADS = 256;
+constexpr int LQA_THREADS = 128;
+constexpr int LQB_THREADS = 256;
 constexpr int RO_THREADS = 128;
 constexpr double kWeakEps = 1e-9;  // numeric_traits::weakEpsilon (ocs2_core/include/ocs2_core/NumericTraits.h:51)
 
@@ -38,6 +40,7 @@ struct WbDev {
   double* inst;      // [B][I_ND]
   int* flags;        // [B][F_NF]
   int* pending;      // number of instances whose line search is still running
+  double* mid;       // K1a -> K1b records [B][N][Mid::SIZE]
   double* raw;       // optional [B][N][rawPer]
   long long rawPer;
   b200sqp_iter_log* log;  // [B][maxIter]
@@ -72,15 +75,30 @@ __device__ __forceinline__ void loadNode(const WbDev& d, int b, int k, NodeIn& n
   }                                                  \
   __syncthreads();
 
-__global__ void __launch_bounds__(LQ_THREADS, 1) lq_kernel(WbDev d) {
+__device__ __forceinline__ NodeOut nodeOut(const WbDev& d, size_t node, size_t stage) {
+  NodeOut out;
+  out.A = const_cast<double*>(d.qp.A) + stage * NX * NX;
+  out.Bt = const_cast<double*>(d.qp.Bm) + stage * NX * NUT_MAX;
+  out.b = const_cast<double*>(d.qp.b) + stage * NX;
+  out.Q = const_cast<double*>(d.qp.Q) + node * NX * NX;
+  out.St = const_cast<double*>(d.qp.S) + stage * NUT_MAX * NX;
+  out.Rt = const_cast<double*>(d.qp.R) + stage * NUT_MAX * NUT_MAX;
+  out.q = const_cast<double*>(d.qp.q) + node * NX;
+  out.rt = const_cast<double*>(d.qp.r) + stage * NUT_MAX;
+  out.Pu = d.Pu + stage * NU * NUT_MAX;
+  out.Px = d.Px + stage * NU * NX;
+  out.u0 = d.u0p + stage * NU;
+  out.nut = const_cast<int*>(d.qp.nu) + stage;
+  out.perf = d.perfNode + node * 4;
+  out.raw = d.raw ? d.raw + stage * d.rawPer : nullptr;
+  return out;
+}
+
+// K1a: node physics.  Intermediate nodes write their Mid record; terminal and event nodes are finished here.
+__global__ void __launch_bounds__(LQA_THREADS, 3) lq_dyn_kernel(WbDev d) {
   extern __shared__ double smem[];
   const int k = blockIdx.x, b = blockIdx.y;
   if (d.flags[b * F_NF + F_CONVERGED]) return;
-  __shared__ WbDeviceModel msh;  // model constants staged once per CTA: the chain sweeps read them in dependent sequences
-  for (int i = threadIdx.x; i < static_cast<int>(sizeof(WbDeviceModel) / 8); i += blockDim.x)
-    reinterpret_cast<double*>(&msh)[i] = reinterpret_cast<const double*>(d.model)[i];
-  __syncthreads();
-  const WbDeviceModel& m = msh;
   const int N = d.N;
   const size_t node = static_cast<size_t>(b) * (N + 1) + k, stage = static_cast<size_t>(b) * N + k;
   NodeIn n;
@@ -89,6 +107,7 @@ __global__ void __launch_bounds__(LQ_THREADS, 1) lq_kernel(WbDev d) {
   double* perf = d.perfNode + node * 4;
   if (k == N) {
     // setupTerminalNode: final cost 1/2 (x - xref)' Qf (x - xref)   (Transcription.cpp:125-154, HumanoidCostConstraintFactory.cpp:218-228)
+    const WbDeviceModel& m = *d.model;
     double* Q = const_cast<double*>(d.qp.Q) + node * NX * NX;
     double* q = const_cast<double*>(d.qp.q) + node * NX;
     for (int i = threadIdx.x; i < NX * NX; i += blockDim.x) Q[i] = (i % NX == i / NX) ? m.Qfd[i % NX] : 0.0;
@@ -110,23 +129,9 @@ __global__ void __launch_bounds__(LQ_THREADS, 1) lq_kernel(WbDev d) {
   }
   n.u = d.u + stage * NU;
   n.xnext = d.x + (node + 1) * NX;
-  NodeOut out;
-  out.A = d.qp.A ? const_cast<double*>(d.qp.A) + stage * NX * NX : nullptr;
-  out.Bt = const_cast<double*>(d.qp.Bm) + stage * NX * NUT_MAX;
-  out.b = const_cast<double*>(d.qp.b) + stage * NX;
-  out.Q = const_cast<double*>(d.qp.Q) + node * NX * NX;
-  out.St = const_cast<double*>(d.qp.S) + stage * NUT_MAX * NX;
-  out.Rt = const_cast<double*>(d.qp.R) + stage * NUT_MAX * NUT_MAX;
-  out.q = const_cast<double*>(d.qp.q) + node * NX;
-  out.rt = const_cast<double*>(d.qp.r) + stage * NUT_MAX;
-  out.Pu = d.Pu + stage * NU * NUT_MAX;
-  out.Px = d.Px + stage * NU * NX;
-  out.u0 = d.u0p + stage * NU;
-  out.nut = const_cast<int*>(d.qp.nu) + stage;
-  out.perf = perf;
-  out.raw = d.raw ? d.raw + stage * d.rawPer : nullptr;
   if (n.event == 1) {
     // setupEventNode: identity jump map, no cost, no input (Transcription.cpp:156-192)
+    NodeOut out = nodeOut(d, node, stage);
     double part = 0.0;
     for (int i = threadIdx.x; i < NX * NX; i += blockDim.x) {
       out.A[i] = (i % NX == i / NX) ? 1.0 : 0.0;
@@ -158,9 +163,30 @@ __global__ void __launch_bounds__(LQ_THREADS, 1) lq_kernel(WbDev d) {
     }
     return;
   }
+  __shared__ WbDeviceModel msh;  // model constants staged once per CTA: the kinematic phases read them in dependent sequences
+  for (int i = threadIdx.x; i < static_cast<int>(sizeof(WbDeviceModel) / 8); i += blockDim.x)
+    reinterpret_cast<double*>(&msh)[i] = reinterpret_cast<const double*>(d.model)[i];
+  __syncthreads();
+  const WbDeviceModel& m = msh;
   LqWs s;
   lqWsMap(smem, s);
-#include "wb_node_body.inc"
+  double* const mid = d.mid + stage * Mid::SIZE;
+#include "wb_node_a.inc"
+}
+
+// K1b: projection + change of input variables of the intermediate nodes, from the Mid records.
+__global__ void __launch_bounds__(LQB_THREADS, 2) lq_proj_kernel(WbDev d) {
+  extern __shared__ double smem[];
+  const int k = blockIdx.x, b = blockIdx.y;
+  if (d.flags[b * F_NF + F_CONVERGED]) return;
+  const size_t node = static_cast<size_t>(b) * (d.N + 1) + k, stage = static_cast<size_t>(b) * d.N + k;
+  if (d.event[node] == 1) return;
+  const double* __restrict__ const mid = d.mid + stage * Mid::SIZE;
+  const double dt = mid[Mid::META + 3];
+  PjWs s;
+  pjWsMap(smem, s);
+  NodeOut out = nodeOut(d, node, stage);
+#include "wb_node_b.inc"
 }
 
 // ---- K4a: remap the projected QP solution, Armijo metric and norms (one CTA per (instance, stage)) --------------------------------------------
@@ -466,6 +492,20 @@ __global__ void __launch_bounds__(256) accept_kernel(WbDev d) {
     fl[F_ITER] = iter + 1;
     fl[F_CONVCODE] = conv;
     if (conv) fl[F_CONVERGED] = 1;
+  }
+}
+
+// extractValueFunction (SqpSolver.cpp:321-329): p_i -= P_i x_i with x the linearisation trajectory (before the step); one CTA per node
+__global__ void __launch_bounds__(64) value_function_kernel(WbDev d) {
+  const int k = blockIdx.x, b = blockIdx.y;
+  if (d.flags[b * F_NF + F_CONVERGED]) return;
+  const size_t node = static_cast<size_t>(b) * (d.N + 1) + k;
+  const double* Pm = d.qp.P + node * NX * NX;
+  const double* x = d.x + node * NX;
+  for (int i = threadIdx.x; i < NX; i += blockDim.x) {
+    double s = 0.0;
+    for (int j = 0; j < NX; ++j) s = fma(Pm[i + NX * j], x[j], s);
+    d.qp.p[node * NX + i] -= s;
   }
 }
 

@@ -107,6 +107,13 @@ class B200SqpSolver:
             out["K"] = np.swapaxes(K, -1, -2).copy()
         return out
 
+    def value_function(self):
+        """getValueFunction data: (P [B, n, nx, nx], p [B, n, nx]) of the last iteration (needs settings.create_value_function)"""
+        B, n, nx = self.batch, self.n_nodes, self.nx
+        P, p = np.zeros((B, n, nx, nx)), np.zeros((B, n, nx))
+        _l.check(_l.lib().b200sqp_download_value_function(self._h, _p(P), _p(p)))
+        return np.swapaxes(P, -1, -2).copy(), p
+
     def iterations_log(self):
         return self.primal_solution(with_gains=False)["log"]
 
