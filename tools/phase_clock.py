@@ -1,0 +1,73 @@
+"""Per-phase cycle table of the phase-scheduled kernels (development aid).
+
+  python tools/phase_clock.py --build            # here: cross-compile the instrumented library (tools/_clk/, git-ignored)
+  gpurun -- python tools/phase_clock.py --node 20 --batch 256   # on the GPU box: one SQP iteration, print the tables
+
+The instrumented build (-DB200SQP_PHASE_CLOCK) records clock64() of thread 0 of ONE CTA after every phase barrier; the CTA runs inside the
+full grid, so the cycles include the contention of its co-resident CTAs.  Not a product path and never a bench number.
+"""
+import argparse
+import ctypes as C
+import os
+import sys
+from pathlib import Path
+
+ROOT = Path(__file__).resolve().parents[1]
+sys.path.insert(0, str(ROOT))
+os.environ["B200SQP_LIB"] = str(ROOT / "tools" / "_clk" / "libb200sqp_clk.so")
+os.environ["B200SQP_NVCC_EXTRA"] = "-DB200SQP_PHASE_CLOCK"
+
+ap = argparse.ArgumentParser()
+ap.add_argument("--build", action="store_true")
+ap.add_argument("--node", type=int, default=20)
+ap.add_argument("--batch", type=int, default=256)
+ap.add_argument("--top", type=int, default=200)
+args = ap.parse_args()
+
+from wb_humanoid_mpc_b200 import lib  # noqa: E402
+
+if args.build:
+    lib.build(force=True)
+    print("built", lib.SO)
+    sys.exit(0)
+
+import numpy as np  # noqa: E402
+
+import bench  # noqa: E402
+from wb_humanoid_mpc_b200 import abi, model_loader  # noqa: E402
+from wb_humanoid_mpc_b200.solver import B200SqpSolver, stack_instances  # noqa: E402
+
+model = model_loader.load_packaged_model()
+settings = abi.default_settings(model, sqp_iteration=1)
+insts = bench.build_batch(model, args.batch, 0, 3.5, ["walk"])
+batch = stack_instances(insts)
+solver = B200SqpSolver(model, settings, device=0)
+L = lib.lib()
+L.b200sqp_debug_phase_clocks.restype = C.c_int
+L.b200sqp_debug_phase_clocks.argtypes = [C.c_int, C.POINTER(C.c_longlong), C.c_int, C.c_int]
+solver.upload(batch)
+node = args.node
+print("node", node, "contact", batch["contact_flags"][0, node], "event", batch["node_event"][0, node])
+L.b200sqp_debug_phase_clocks(0, None, 0, node)
+for _ in range(2):
+    solver.reset()
+    solver.solve()
+files = {0: "wb_node_a.inc", 1: "wb_node_b.inc", 2: "wb_rollout_body.inc"}
+for kid, name in [(0, "K1a lq_dyn_kernel"), (1, "K1b lq_proj_kernel"), (2, "K3 rollout_kernel")]:
+    buf = (C.c_longlong * (2 * 512))()
+    n = L.b200sqp_debug_phase_clocks(kid, buf, 512, -1)
+    a = np.array(buf[:2 * n], dtype=np.int64).reshape(n, 2)
+    src = (ROOT / "wb_humanoid_mpc_b200" / "csrc" / files[kid]).read_text().split("\n")
+    tot = a[-1, 1] - a[0, 1]
+    print(f"\n== {name}: {n - 1} phases, {tot} cycles")
+    rows = []
+    for i in range(1, n):
+        rows.append((int(a[i, 1] - a[i - 1, 1]), int(a[i, 0]), i))
+    # aggregate by source line (RK stages repeat the same lines)
+    agg = {}
+    for cyc, line, i in rows:
+        c, k = agg.get(line, (0, 0))
+        agg[line] = (c + cyc, k + 1)
+    for line, (cyc, k) in sorted(agg.items(), key=lambda kv: -kv[1][0])[:args.top]:
+        text = src[line - 1].strip()[:110] if 0 < line <= len(src) else "?"
+        print(f"  {cyc:8d} {100.0 * cyc / tot:5.1f}%  x{k:<2d} L{line:<4d} {text}")

@@ -7,6 +7,12 @@ namespace b200sqp {
 struct Par {  // the calling thread's slice of a phase
   int tid, nt;
 };
+// the same phase slice with the item assignment rotated by k threads: lets several item loops of one phase start on different threads
+HD Par rot(Par P, int k) {
+  int t = P.tid - (k % P.nt);
+  if (t < 0) t += P.nt;
+  return Par{t, P.nt};
+}
 
 // C(MxN, ldc) = (ACC ? C : 0) + alpha * op(A) * B ; op(A) = A (MxK, lda) or A^T (A stored KxM, lda) ; B is KxN (ldb)
 template <int TM, int TN, bool TRANS_A, bool ACC, class PAR>

@@ -34,11 +34,22 @@ struct DynWs {
   double N[6], IcInv[9], y[3], qddb[6];
 };
 
-HD void zyx(const D1* th, D1* R, D1* S) {
+// Base kinematics with one tangent direction (dir in 0..8 = th, pdot, thdot; dir < 0: values only).  Straight-line code: the value lane and
+// the nine tangent lanes of a warp run the same instruction stream.
+HD void baseKinematics(const double* x, int dir, double g, D1* R, D1* S, D1* v0, D1* a0) {
+  D1 th[3], pd[3], td[3], sn[3], cs[3];
+#pragma unroll
+  for (int k = 0; k < 3; ++k) {
+    th[k] = D1{x[3 + k], dir == k ? 1.0 : 0.0};
+    pd[k] = D1{x[NV + k], dir == 3 + k ? 1.0 : 0.0};
+    td[k] = D1{x[NV + 3 + k], dir == 6 + k ? 1.0 : 0.0};
+    double sv, cv;
+    sincos(th[k].v, &sv, &cv);
+    sn[k] = D1{sv, cv * th[k].d};
+    cs[k] = D1{cv, -sv * th[k].d};
+  }
   // Rz(th0) Ry(th1) Rx(th2) and the body-frame angular-velocity map of Pinocchio's JointModelSphericalZYX
-  const D1 c0{cos(th[0].v), -sin(th[0].v) * th[0].d}, s0{sin(th[0].v), cos(th[0].v) * th[0].d};
-  const D1 c1{cos(th[1].v), -sin(th[1].v) * th[1].d}, s1{sin(th[1].v), cos(th[1].v) * th[1].d};
-  const D1 c2{cos(th[2].v), -sin(th[2].v) * th[2].d}, s2{sin(th[2].v), cos(th[2].v) * th[2].d};
+  const D1 c0 = cs[0], s0 = sn[0], c1 = cs[1], s1 = sn[1], c2 = cs[2], s2 = sn[2];
   const D1 zero{0.0, 0.0}, one{1.0, 0.0};
   R[0] = c0 * c1; R[1] = c0 * s1 * s2 - s0 * c2; R[2] = c0 * s1 * c2 + s0 * s2;
   R[3] = s0 * c1; R[4] = s0 * s1 * s2 + c0 * c2; R[5] = s0 * s1 * c2 - c0 * s2;
@@ -46,18 +57,6 @@ HD void zyx(const D1* th, D1* R, D1* S) {
   S[0] = -s1;     S[1] = zero; S[2] = one;
   S[3] = c1 * s2; S[4] = c2;   S[5] = zero;
   S[6] = c1 * c2; S[7] = -s2;  S[8] = zero;
-}
-
-// Base kinematics with one tangent direction (dir in 0..8 = th, pdot, thdot; dir < 0: values only).
-HD void baseKinematics(const double* x, int dir, double g, D1* R, D1* S, D1* v0, D1* a0) {
-  D1 th[3], pd[3], td[3];
-#pragma unroll
-  for (int k = 0; k < 3; ++k) {
-    th[k] = D1{x[3 + k], dir == k ? 1.0 : 0.0};
-    pd[k] = D1{x[NV + k], dir == 3 + k ? 1.0 : 0.0};
-    td[k] = D1{x[NV + 3 + k], dir == 6 + k ? 1.0 : 0.0};
-  }
-  zyx(th, R, S);
   // vl = R' pdot, wb = S thdot
   const DV3 vl{R[0] * pd[0] + R[3] * pd[1] + R[6] * pd[2], R[1] * pd[0] + R[4] * pd[1] + R[7] * pd[2], R[2] * pd[0] + R[5] * pd[1] + R[8] * pd[2]};
   const DV3 wb{S[0] * td[0] + S[1] * td[1] + S[2] * td[2], S[3] * td[0] + S[4] * td[1] + S[5] * td[2], S[6] * td[0] + S[7] * td[1] + S[8] * td[2]};
@@ -67,8 +66,6 @@ HD void baseKinematics(const double* x, int dir, double g, D1* R, D1* S, D1* v0,
   a0[0] = c.x + g * R[6];
   a0[1] = c.y + g * R[7];
   a0[2] = c.z + g * R[8];
-  const D1 c1{cos(th[1].v), -sin(th[1].v) * th[1].d}, s1{sin(th[1].v), cos(th[1].v) * th[1].d};
-  const D1 c2{cos(th[2].v), -sin(th[2].v) * th[2].d}, s2{sin(th[2].v), cos(th[2].v) * th[2].d};
   a0[3] = -(c1 * td[1] * td[0]);
   a0[4] = (c1 * c2 * td[2] - s1 * s2 * td[1]) * td[0] - s2 * td[2] * td[1];
   a0[5] = -((s1 * c2 * td[1] + c1 * s2 * td[2]) * td[0]) - c2 * td[2] * td[1];
@@ -82,43 +79,48 @@ HD void inv3(const double* A, double* Ai) {
   Ai[6] = c02 * id; Ai[7] = (A[1] * A[6] - A[0] * A[7]) * id; Ai[8] = (A[0] * A[4] - A[1] * A[3]) * id;
 }
 
-// ---- phase 1a: base quantities (items 0..9) and joint transforms (items 16..38), all independent -----------------------------------------
+// ---- phase 1a: base quantities (warp 0: lane 0 values, lanes 1..9 tangents) and joint transforms (warp 1), all independent ---------
 template <bool DERIV>
 HD void dynPhaseJoints(Par P, const WbDeviceModel& m, const double* x, DynWs& w) {
-  for (int it = P.tid; it < 16 + NJ; it += P.nt) {
-    if (it == 0) {
+  for (int it = P.tid; it < 32 + NJ; it += P.nt) {
+    if (it < (DERIV ? 10 : 1)) {
+      const int dir = it - 1;
       D1 R[9], S[9], v0[6], a0[6];
-      baseKinematics(x, -1, m.gravity, R, S, v0, a0);
-      double Sv[9];
-      for (int k = 0; k < 9; ++k) {
-        w.Rb[k] = R[k].v;
-        w.Sz[k] = Sv[k] = S[k].v;
-      }
-      inv3(Sv, w.SzInv);
-      for (int k = 0; k < 6; ++k) {
-        w.v0[k] = v0[k].v;
-        w.a0[k] = a0[k].v;
-      }
-    } else if (it >= 1 && it <= 9) {
-      if (DERIV) {
-        const int dir = it - 1;
-        D1 R[9], S[9], v0[6], a0[6];
-        baseKinematics(x, dir, m.gravity, R, S, v0, a0);
+      baseKinematics(x, dir, m.gravity, R, S, v0, a0);
+      if (dir < 0) {
+        double Sv[9];
+#pragma unroll
+        for (int k = 0; k < 9; ++k) {
+          w.Rb[k] = R[k].v;
+          w.Sz[k] = Sv[k] = S[k].v;
+        }
+        inv3(Sv, w.SzInv);
+#pragma unroll
+        for (int k = 0; k < 6; ++k) {
+          w.v0[k] = v0[k].v;
+          w.a0[k] = a0[k].v;
+        }
+      } else {
+#pragma unroll
         for (int k = 0; k < 6; ++k) {
           w.dv0[dir][k] = v0[k].d;
           w.da0[dir][k] = a0[k].d;
         }
-        if (dir < 3)
+        if (dir < 3) {
+#pragma unroll
           for (int k = 0; k < 9; ++k) {
             w.dRb[dir][k] = R[k].d;
             w.dSz[dir][k] = S[k].d;
           }
+        }
       }
-    } else if (it >= 16) {
-      const int i = it - 16 + 1;
+    } else if (it >= 32) {
+      const int i = it - 32 + 1;
       const double q = x[5 + i];
       const double* ax = m.axis[i];
-      const double c = cos(q), s = sin(q), t = 1.0 - c;
+      double s, c;
+      sincos(q, &s, &c);
+      const double t = 1.0 - c;
       const double Rq[9] = {t * ax[0] * ax[0] + c,         t * ax[0] * ax[1] - s * ax[2], t * ax[0] * ax[2] + s * ax[1],
                             t * ax[0] * ax[1] + s * ax[2], t * ax[1] * ax[1] + c,         t * ax[1] * ax[2] - s * ax[0],
                             t * ax[0] * ax[2] - s * ax[1], t * ax[1] * ax[2] + s * ax[0], t * ax[2] * ax[2] + c};

@@ -42,8 +42,7 @@ struct Mid {
   static constexpr int JR = FRIC + 18;                   // weighted rows (ld JR_MAX) x 93
   static constexpr int COEF = JR + JR_MAX * NZ;          // gradient coefficient per row (already folded into GQ; kept for inspection)
   static constexpr int META = COEF + JR_MAX;             // nc, nrows, dt*cost, dt
-  static constexpr int JF = META + 4;                    // scratch: dense foot Jacobians 2 x (18 x 93)
-  static constexpr int SIZE = JF + 2 * FQ * NZ;
+  static constexpr int SIZE = META + 4;
 };
 
 struct NodeOut {  // global-memory destinations of one node
@@ -61,11 +60,11 @@ struct LqWs {
   double *JFl, *FP, *DFP, *tmpG;
   double* fs;      // 4 x 58 stage flows, b (58), stage point (58)
   double* FV;      // 2 x 18 foot values
-  double *gq, *hd, *pv, *sc, *rowCoef, *rowVal;
+  double *gq, *gfoot, *ev, *pv, *sc, *rowCoef, *rowVal;   // gfoot: 2 x 93 swing-foot cost gradients ; sc[4..9]: friction gradient
 };
 HD size_t lqWsDoubles() {
   const size_t dynD = (sizeof(DynWs) + 7) / 8;
-  return dynD + 4 * 6 * NZ + 2 * FLOC * FQ + 3 * NFRAMES + NFRAMES * 15 * 3 + 6 * NX + 2 * FQ + 2 * NZ + 96 + 16 + 2 * JR_MAX + 8;
+  return dynD + 4 * 6 * NZ + 2 * FLOC * FQ + 3 * NFRAMES + NFRAMES * 15 * 3 + 6 * NX + 2 * FQ + 3 * NZ + NC_MAX + 96 + 16 + 2 * JR_MAX + 9;
 }
 HD void lqWsMap(double* base, LqWs& s) {
   const size_t dynD = (sizeof(DynWs) + 7) / 8;
@@ -78,37 +77,49 @@ HD void lqWsMap(double* base, LqWs& s) {
   s.fs = s.DFP + NFRAMES * 15 * 3;
   s.FV = s.fs + 6 * NX;
   s.gq = s.FV + 2 * FQ;
-  s.hd = s.gq + NZ;
-  s.pv = s.hd + NZ;
+  s.gfoot = s.gq + NZ;
+  s.ev = s.gfoot + 2 * NZ;
+  s.pv = s.ev + NC_MAX;
   s.sc = s.pv + 96;
   s.rowCoef = s.sc + 16;
   s.rowVal = s.rowCoef + JR_MAX;
 }
 
-// shared-memory map of K1b (projection + change of variables): <= 104 KB so that two CTAs share an SM
+// shared-memory map of K1b (projection + change of variables): <= 113 KB so that two CTAs share an SM.
+// The change of variables works in the pivoted variable order of the LU (u = [pivot vars (nc) ; free vars (nut)]), where
+//   Px = [X ; 0],  u0 = [x0 ; 0],  Pu = [K ; I]      (X | x0 = Xt, K = Kt)
+// so every contraction over the 35 inputs shrinks to one over the nc <= 14 pivot variables.
 struct PjWs {
-  double *Px, *Pu, *u0;          // 35 x 58, 35 x 23, 35
   double *Q, *S, *R;             // 58 x 58, 35 x 58 (ld 35), 35 x 35
-  double *gq, *rr, *bvec, *sc;   // 93, 35, 58, 16
-  double* scratch;               // 3072 doubles: {CD, e, LU, AB12} -> {JR chunk} -> {T1, RPu}
-  int* iw;
-  // views into scratch
-  double *CD, *ev, *LU, *AB12, *JRc, *T1, *RPu, *Uinv, *Linv, *PC, *T, *Xt, *Kt;
+  double *gq, *bvec;             // 93, 58
+  double *Xt, *Kt;               // nc x 59 (ld 14): [X | x0] ; nc x nut (ld 14)
+  double* AB12;                  // 12 x 93 (ld 12)
+  double* scratch;
+  int* iw;                       // rowOf[16] colOf[36] posOf[36]
+  // phase-1 views (projection)
+  double *CD, *ev, *LU, *Uinv, *Linv, *PC, *T;
+  // dynamics views
+  double *B1, *D12;              // 12 x nc (ld 12) ; 12 x (59 + nut) (ld 12)
+  // Hessian view
+  double* JRc;                   // JR_CHUNK x 93 (ld JR_CHUNK)
+  // cost change-of-variables views
+  double *T11, *T12, *R11, *R21, *W, *V, *rr;   // nc x 58 (ld 14), nut x 58 (ld 23), nc x nc (ld 14), nut x nc (ld 23), nc x nut (ld 14), nut x nut (ld 23), 35 + 35
 };
-HD size_t pjWsDoubles() { return NU * NX + NU * NUT_MAX + 36 + NX * NX + NU * NX + NU * NU + 1 + NZ + 1 + 36 + NX + 16 + 4400 + 64; }
+constexpr int PJ_SCRATCH = 3856;
+HD size_t pjWsDoubles() {
+  return NX * NX + NU * NX + NU * NU + 1 + NZ + 1 + NX + NC_MAX * (NX + 1) + NC_MAX * NUT_MAX + 12 * NZ + PJ_SCRATCH + 48;
+}
 HD void pjWsMap(double* base, PjWs& s) {
-  s.Px = base;
-  s.Pu = s.Px + NU * NX;
-  s.u0 = s.Pu + NU * NUT_MAX;
-  s.Q = s.u0 + 36;
+  s.Q = base;
   s.S = s.Q + NX * NX;
   s.R = s.S + NU * NX;
   s.gq = s.R + NU * NU + 1;
-  s.rr = s.gq + NZ + 1;
-  s.bvec = s.rr + 36;
-  s.sc = s.bvec + NX;
-  s.scratch = s.sc + 16;
-  s.iw = reinterpret_cast<int*>(s.scratch + 4400);
+  s.bvec = s.gq + NZ + 1;
+  s.Xt = s.bvec + NX;
+  s.Kt = s.Xt + NC_MAX * (NX + 1);
+  s.AB12 = s.Kt + NC_MAX * NUT_MAX;
+  s.scratch = s.AB12 + 12 * NZ;
+  s.iw = reinterpret_cast<int*>(s.scratch + PJ_SCRATCH);
   // phase 1 (projection): CD | e | LU | triangular-solve workspace
   s.CD = s.scratch;                          // 14 x 93 = 1302
   s.ev = s.CD + NC_MAX * NZ;                 // 14
@@ -117,14 +128,19 @@ HD void pjWsMap(double* base, PjWs& s) {
   s.Linv = s.Uinv + NC_MAX * NC_MAX;         // 196
   s.PC = s.Linv + NC_MAX * NC_MAX;           // 14 x 59 = 826
   s.T = s.PC + NC_MAX * (NX + 1);            // 826   (ends at 3850)
-  s.Xt = s.CD;                               // CD is dead once PC holds the permuted copy: 826
-  s.Kt = s.PC;                               // PC is dead once T = L^-1 PC exists: 14 x 23 = 322
-  // phase 2 (dynamics change of variables)
-  s.AB12 = s.scratch;                        // 12 x 93 = 1116
-  // phase 3 (Hessian) / phase 4 (cost change of variables)
+  // dynamics change of variables
+  s.B1 = s.scratch;                          // 12 x 14 = 168
+  s.D12 = s.B1 + 12 * NC_MAX;                // 12 x 82 = 984
+  // Hessian
   s.JRc = s.scratch;                         // 18 x 93 = 1674
-  s.T1 = s.scratch;                          // 35 x 58 = 2030
-  s.RPu = s.scratch + NU * NX;               // 35 x 23 = 805  (ends at 2835)
+  // cost change of variables
+  s.T11 = s.scratch;                         // 14 x 58 = 812
+  s.T12 = s.T11 + NC_MAX * NX;               // 23 x 58 = 1334
+  s.R11 = s.T12 + NUT_MAX * NX;              // 196
+  s.R21 = s.R11 + NC_MAX * NC_MAX;           // 23 x 14 = 322
+  s.W = s.R21 + NUT_MAX * NC_MAX;            // 14 x 23 = 322
+  s.V = s.W + NC_MAX * NUT_MAX;              // 23 x 23 = 529
+  s.rr = s.V + NUT_MAX * NUT_MAX;            // 70   (ends at 3585)
 }
 
 HD void penRelaxed(double mu, double delta, double h, double& v, double& d1, double& d2) {
@@ -272,10 +288,6 @@ HD void conPhaseAssemble(Par P, const WbDeviceModel& m, const NodeIn& n, const d
 
 // ---- costs ------------------------------------------------------------------------------------------------------------------------------------
 // phase A: zero H, diagonal terms, gradient of the quadratic tracking cost, joint limits, friction cone (items over 93 + a few)
-HD void costPhaseInit(Par P, double* gq, double* sc) {
-  for (int i = P.tid; i < NZ; i += P.nt) gq[i] = 0.0;
-  if (P.tid == 0) sc[0] = 0.0;
-}
 template <bool DERIV = true>
 HD void costPhaseDiagonal(Par P, const WbDeviceModel& m, const NodeIn& n, double* hdiag, double* gq, double* pv /*partial values, 96*/) {
   // friction-cone penalty derivative (needed for the Hessian shift on every diagonal entry)
@@ -325,18 +337,20 @@ HD void costPhaseDiagonal(Par P, const WbDeviceModel& m, const NodeIn& n, double
     }
     if (DERIV) {
       hdiag[i] = hd;
-      gq[i] += g;
+      gq[i] = g;
     }
     pv[i] = val;
   }
 }
 // friction cone blocks (items = contacts): value, gradient, 3x3 Hessian block  (FrictionForceConeConstraint.cpp:145-224)
 template <bool DERIV = true>
-HD void costPhaseFriction(Par P, const WbDeviceModel& m, const NodeIn& n, double* fric /*2 x 9*/, double* gq, double* pv) {
+HD void costPhaseFriction(Par P, const WbDeviceModel& m, const NodeIn& n, double* fric /*2 x 9*/, double* fricG /*2 x 3*/, double* pv) {
   for (int c = P.tid; c < 2; c += P.nt) {
     pv[NZ + c] = 0.0;
-    if (DERIV)
+    if (DERIV) {
       for (int k = 0; k < 9; ++k) fric[9 * c + k] = 0.0;
+      for (int k = 0; k < 3; ++k) fricG[3 * c + k] = 0.0;
+    }
     if (!n.contact[c]) continue;
     const double* F = n.u + 6 * c;
     const double Ft2 = F[0] * F[0] + F[1] * F[1] + m.fricReg, Ft = sqrt(Ft2), Ft32 = Ft * Ft2;
@@ -347,9 +361,8 @@ HD void costPhaseFriction(Par P, const WbDeviceModel& m, const NodeIn& n, double
     const double ddh[9] = {-(F[1] * F[1] + m.fricReg) / Ft32, F[0] * F[1] / Ft32, 0, F[0] * F[1] / Ft32, -(F[0] * F[0] + m.fricReg) / Ft32, 0, 0, 0, 0};
     pv[NZ + c] = v;
     if (!DERIV) continue;
-    const int o = NX + 6 * c;
     for (int i = 0; i < 3; ++i) {
-      gq[o + i] += d1 * dh[i];
+      fricG[3 * c + i] = d1 * dh[i];
       for (int j = 0; j < 3; ++j) fric[9 * c + 3 * i + j] = d2 * dh[i] * dh[j] + d1 * ddh[3 * i + j];
     }
   }
@@ -462,11 +475,87 @@ HD void costPhaseRows(Par P, const WbDeviceModel& m, const NodeIn& n, int g, con
     }
   }
 }
-// gq += JR' coef for one row group (K1a; the Hessian part JR'JR is formed in K1b)
-HD void costPhaseGradient(Par P, int nr, const double* JR, int ldJR, const double* rowCoef, double* gq) {
+// Fused foot phase, one item per (foot c, tangent direction d): column d of the foot's 18 quantities (scatter of the local tangents + the
+// chain through the base acceleration, J_fb G) is formed in registers and consumed at once: the foot's equality-constraint rows go to CD,
+// a swinging foot's 18 weighted residual rows to JR, and its share of the cost gradient to gfoot[c][d].  Nothing dense is staged.
+HD int footZToLocal(const WbDeviceModel& m, int c, int d) {
+  int body, base;
+  if (d < 6) return d;                              // pb, th
+  if (d < NV) {
+    body = d - 6 + 1;                               // q_leg
+    base = 6;
+  } else if (d < NV + 6) {
+    return 12 + (d - NV);                           // pd, thd
+  } else if (d < NX) {
+    body = d - NV - 6 + 1;                          // qd_leg
+    base = 18;
+  } else if (d < NX + 12) {
+    return -1;                                      // contact wrenches act only through qdd_b
+  } else {
+    body = d - NX - 12 + 1;                         // qdd_leg
+    base = 24;
+  }
+#pragma unroll
+  for (int t = 0; t < LEG_LEN; ++t)
+    if (m.legBody[c][t] == body) return base + t;
+  return -1;
+}
+HD void footPhaseColumns(Par P, const WbDeviceModel& m, const NodeIn& n, const double* JFl, const double* G, const double* FV, double* CD,
+                         double* JR, double* gfoot) {
+  const int n0 = n.contact[0] ? 6 : 7;
+  for (int it = P.tid; it < 2 * NZ; it += P.nt) {
+    const int c = it / NZ, d = it - c * NZ;
+    double col[FQ];
+    const int l = footZToLocal(m, c, d);
+    const double* src = JFl + (c * FLOC + (l >= 0 ? l : 0)) * FQ;
+#pragma unroll
+    for (int k = 0; k < FQ; ++k) col[k] = (l >= 0) ? src[k] : 0.0;
+#pragma unroll
+    for (int j = 0; j < 6; ++j) {
+      const double g = G[j + 6 * d];
+      const double* jb = JFl + (c * FLOC + 30 + j) * FQ;
+#pragma unroll
+      for (int k = 12; k < FQ; ++k) col[k] = fma(jb[k], g, col[k]);
+    }
+    double* cd = CD + (c ? n0 : 0) + NC_MAX * d;
+    double gsum = 0.0;
+    if (n.contact[c]) {
+      // ZeroAccelerationConstraintCppAd rows (see conPhaseAssemble)
+#pragma unroll
+      for (int lr = 0; lr < 6; ++lr) {
+        const double Av = lr < 2 ? m.gLinVelXY : (lr == 2 ? m.gLinVelZ : m.gAngVel);
+        const double Aa = lr < 2 ? m.gLinAccXY : (lr == 2 ? m.gLinAccZ : m.gAngAcc);
+        const double Ax = lr == 2 ? m.gPosZ : (lr >= 3 ? m.gOri : 0.0);
+        cd[lr] = Ax * col[lr] + Av * col[6 + lr] + Aa * col[12 + lr];
+      }
+    } else {
+#pragma unroll
+      for (int lr = 0; lr < 6; ++lr) cd[lr] = (d == NX + 6 * c + lr) ? 1.0 : 0.0;            // ZeroWrenchConstraint
+      cd[6] = m.gPosZ * col[2] + m.gLinVelZ * col[8] + m.gLinAccZ * col[14];                 // SwingLegVerticalConstraintCppAd
+      double* jr = JR + (c ? groupRows(n, 0) : 0) + JR_MAX * d;                              // EndEffectorDynamicsFootCost rows
+#pragma unroll
+      for (int r = 0; r < FQ; ++r) {
+        const double sw = (r < 3) ? 0.0 : m.footSqrtW[r] * n.impact[c];
+        const double e = sw * col[r];
+        jr[r] = e;
+        gsum = fma(e, sw * FV[FQ * c + r], gsum);
+      }
+    }
+    gfoot[it] = gsum;
+  }
+}
+// gq += swing-foot gradients + friction gradient + JR' coef over the rows [r0, r1) that were written row-wise (moment / collision rows)
+HD void costPhaseGradient(Par P, const NodeIn& n, const double* JR, const double* rowCoef, const double* gfoot, const double* fricG, double* gq) {
+  const int g0 = groupRows(n, 0), g1 = groupRows(n, 1), g2 = groupRows(n, 2);
   for (int i = P.tid; i < NZ; i += P.nt) {
-    double acc = 0.0;
-    for (int r = 0; r < nr; ++r) acc = fma(JR[r + ldJR * i], rowCoef[r], acc);
+    double acc = gfoot[i] + gfoot[NZ + i];
+    if (i >= NX && i < NX + 12 && (i - NX) % 6 < 3) acc += fricG[3 * ((i - NX) / 6) + (i - NX) % 6];
+    const double* col = JR + JR_MAX * i;
+    if (n.contact[0])
+      for (int r = 0; r < g0; ++r) acc = fma(col[r], rowCoef[r], acc);
+    if (n.contact[1])
+      for (int r = g0; r < g0 + g1; ++r) acc = fma(col[r], rowCoef[r], acc);
+    for (int r = g0 + g1; r < g0 + g1 + g2; ++r) acc = fma(col[r], rowCoef[r], acc);
     gq[i] += acc;
   }
 }
@@ -626,21 +715,23 @@ HD void luPhaseSolveA(Par P, int nc, const double* LU, const int* rowOf, const d
     ws.PC[i + NC_MAX * j] = (j < NX) ? CD[rowOf[i] + NC_MAX * j] : ev[rowOf[i]];
   }
 }
-HD void luPhaseSolveD(Par P, int nc, const int* colOf, LuSolveWs ws, double* Pu, double* Px, double* u0) {
+// scatter the solution through the column permutation to the layout the remap kernel reads (global memory):
+//   Px (35 x 58), u0 (35), Pu (35 x nut)
+HD void luPhaseInversePerm(Par P, const int* colOf, int* posOf) {
+  for (int t = P.tid; t < NU; t += P.nt) posOf[colOf[t]] = t;
+}
+HD void luPhaseScatter(Par P, int nc, const int* posOf, const double* Xt, const double* Kt, double* Pu, double* Px, double* u0) {
   const int nut = NU - nc;
-  for (int it = P.tid; it < NU * (NX + 1 + nut); it += P.nt) {
+  for (int it = P.tid; it < NU * (NX + 1 + NUT_MAX); it += P.nt) {
     const int i = it % NU, j = it / NU;
-    // which position does original column/variable i hold in the permuted order?
-    int pos = 0;
-    for (int t = 0; t < NU; ++t)
-      if (colOf[t] == i) pos = t;
+    const int pos = posOf[i];
     if (j < NX) {
-      Px[i + NU * j] = (pos < nc) ? ws.Xt[pos + NC_MAX * j] : 0.0;
+      Px[i + NU * j] = (pos < nc) ? Xt[pos + NC_MAX * j] : 0.0;
     } else if (j == NX) {
-      u0[i] = (pos < nc) ? ws.Xt[pos + NC_MAX * NX] : 0.0;
+      u0[i] = (pos < nc) ? Xt[pos + NC_MAX * NX] : 0.0;
     } else {
       const int kk = j - NX - 1;
-      Pu[i + NU * kk] = (pos < nc) ? ws.Kt[pos + NC_MAX * kk] : (pos == nc + kk ? 1.0 : 0.0);
+      Pu[i + NU * kk] = (kk < nut) ? ((pos < nc) ? Kt[pos + NC_MAX * kk] : (pos == nc + kk ? 1.0 : 0.0)) : 0.0;
     }
   }
 }

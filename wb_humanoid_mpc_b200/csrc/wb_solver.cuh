@@ -68,12 +68,39 @@ __device__ __forceinline__ void loadNode(const WbDev& d, int b, int k, NodeIn& n
   }
 }
 
+// Development aid (never in the shipped build): with -DB200SQP_PHASE_CLOCK thread 0 of one CTA records (source line, clock64) after every
+// phase barrier; tools/phase_clock.py turns that into a per-phase cycle table.
+#ifdef B200SQP_PHASE_CLOCK
+__device__ long long g_phaseClk[4][512][2];
+__device__ int g_phaseCnt[4];
+__device__ int g_phaseNode = 20;
+#define PHASE_CLOCK_BEGIN(id)                                                                  \
+  const int clkId_ = (id);                                                                     \
+  int clkN_ = 0;                                                                               \
+  const bool clkOn_ = (threadIdx.x == 0 && blockIdx.y == 0 && static_cast<int>(blockIdx.x) == g_phaseNode); \
+  if (clkOn_) {                                                                                \
+    g_phaseClk[clkId_][0][0] = 0;                                                              \
+    g_phaseClk[clkId_][0][1] = clock64();                                                      \
+    clkN_ = 1;                                                                                 \
+  }
+#define PHASE_TICK()                                   \
+  if (clkOn_ && clkN_ < 512) {                         \
+    g_phaseClk[clkId_][clkN_][0] = __LINE__;           \
+    g_phaseClk[clkId_][clkN_][1] = clock64();          \
+    g_phaseCnt[clkId_] = ++clkN_;                      \
+  }
+#else
+#define PHASE_CLOCK_BEGIN(id)
+#define PHASE_TICK()
+#endif
+
 #define PHASE(...)                                   \
   {                                                  \
     const Par P{static_cast<int>(threadIdx.x), static_cast<int>(blockDim.x)}; \
     __VA_ARGS__                                      \
   }                                                  \
-  __syncthreads();
+  __syncthreads();                                   \
+  PHASE_TICK()
 
 __device__ __forceinline__ NodeOut nodeOut(const WbDev& d, size_t node, size_t stage) {
   NodeOut out;
@@ -171,6 +198,7 @@ __global__ void __launch_bounds__(LQA_THREADS, 3) lq_dyn_kernel(WbDev d) {
   LqWs s;
   lqWsMap(smem, s);
   double* const mid = d.mid + stage * Mid::SIZE;
+  PHASE_CLOCK_BEGIN(0)
 #include "wb_node_a.inc"
 }
 
@@ -186,6 +214,7 @@ __global__ void __launch_bounds__(LQB_THREADS, 2) lq_proj_kernel(WbDev d) {
   PjWs s;
   pjWsMap(smem, s);
   NodeOut out = nodeOut(d, node, stage);
+  PHASE_CLOCK_BEGIN(1)
 #include "wb_node_b.inc"
 }
 
@@ -372,6 +401,7 @@ __global__ void __launch_bounds__(RO_THREADS) rollout_kernel(WbDev d) {
     }
     return;
   }
+  PHASE_CLOCK_BEGIN(2)
 #include "wb_rollout_body.inc"
 }
 
@@ -524,5 +554,7 @@ __global__ void __launch_bounds__(256) count_active_kernel(WbDev d) {
 }
 
 #undef PHASE
+#undef PHASE_TICK
+#undef PHASE_CLOCK_BEGIN
 
 }  // namespace b200sqp

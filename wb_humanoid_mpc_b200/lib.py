@@ -13,7 +13,7 @@ from pathlib import Path
 
 PKG = Path(__file__).resolve().parent
 CSRC = PKG / "csrc"
-SO = PKG / "libb200sqp.so"
+SO = Path(os.environ["B200SQP_LIB"]) if os.environ.get("B200SQP_LIB") else PKG / "libb200sqp.so"  # override: development builds only
 INCLUDE = PKG.parent / "include"
 
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "-shared", "-Xcompiler", "-fPIC",
@@ -46,7 +46,7 @@ def build(force: bool = False, verbose: bool = False) -> Path:
     if not force and not needs_build():
         return SO
     nvcc = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
-    flags = list(NVCC_FLAGS)
+    flags = list(NVCC_FLAGS) + os.environ.get("B200SQP_NVCC_EXTRA", "").split()  # extra flags: development builds only
     if not (CSRC / "wb_solver.cuh").exists():
         flags.remove("-DB200SQP_WITH_WB")
     cmd = [nvcc, *flags, "-o", str(SO), str(CSRC / "b200sqp.cu")]
