@@ -61,6 +61,8 @@ inline const char* makeDeviceModel(const b200sqp_model_desc& d, WbDeviceModel& m
       b = m.parent[b];
     }
     if (b != 0) return "contact frames must hang off a 6-joint leg attached to the base";
+    for (int l = 0; l < LEG_LEN; ++l)
+      if (m.legBody[c][l] != 1 + LEG_LEN * c + l) return "the leg joints must be bodies 1..12 (left leg first): the structured penalty rows assume it";
   }
   for (int k = 0; k < 4; ++k) m.rect[k] = d.contact_rect[k];
   for (int i = 0; i < NX; ++i) {

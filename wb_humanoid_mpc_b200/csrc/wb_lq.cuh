@@ -17,8 +17,12 @@
 
 namespace b200sqp {
 
-constexpr int JR_MAX = 52;     // Gauss-Newton / penalty rows of one node: 2 x 18 (both feet swinging) + 16 collision rows
-constexpr int JR_CHUNK = 18;   // rows staged per Hessian accumulation step in K1b
+// Gauss-Newton / penalty rows of one node, by structure:
+constexpr int JS_MAX = 30;     // dense rows: 15 weighted residual rows (quantities 3..17) per swinging foot
+constexpr int JU_MAX = 24;     // structured rows: 4 contact-moment rows per stance foot + 16 foot-collision rows (when a foot swings)
+constexpr int NUC = 27;        // column support of the structured rows: th (3), the 12 leg joint positions, the 12 contact wrench entries
+HD int ucolToZ(int i) { return i < 15 ? 3 + i : NX + (i - 15); }
+HD int zToUcol(int d) { return (d >= 3 && d < 18) ? d - 3 : ((d >= NX && d < NX + 12) ? 15 + d - NX : -1); }
 
 struct NodeIn {  // per-node inputs (see b200sqp_upload_instances)
   const double *x, *u, *xnext, *xref;
@@ -39,10 +43,10 @@ struct Mid {
   static constexpr int HDG = E + NC_MAX;                 // Hessian diagonal (93), not yet multiplied by dt
   static constexpr int GQ = HDG + NZ;                    // cost gradient (93)
   static constexpr int FRIC = GQ + NZ;                   // 2 x (3 x 3) friction-cone Hessian blocks
-  static constexpr int JR = FRIC + 18;                   // weighted rows (ld JR_MAX) x 93
-  static constexpr int COEF = JR + JR_MAX * NZ;          // gradient coefficient per row (already folded into GQ; kept for inspection)
-  static constexpr int META = COEF + JR_MAX;             // nc, nrows, dt*cost, dt
-  static constexpr int SIZE = META + 4;
+  static constexpr int JS = FRIC + 18;                   // dense weighted rows (ld JS_MAX) x 93
+  static constexpr int JU = JS + JS_MAX * NZ;            // structured weighted rows (ld JU_MAX) x NUC compact columns
+  static constexpr int META = JU + JU_MAX * NUC;         // nc, swing rows, structured rows, dt, dt*cost
+  static constexpr int SIZE = META + 6;
 };
 
 struct NodeOut {  // global-memory destinations of one node
@@ -53,6 +57,21 @@ struct NodeOut {  // global-memory destinations of one node
   double* raw;                                // optional raw (pre-projection) block dump, oracle layout; may be null
 };
 
+// per-row scalars of the structured rows
+struct RowWs {
+  double *wsq, *coef, *val;   // sqrt of the penalty curvature, gradient coefficient of the weighted row, penalty value  (JU_MAX each)
+  double* aux;                // collision rows: unit separation direction [JU_MAX][3]
+  double* Rf;                 // stance feet: world rotation of the foot frame [2][9]
+};
+HD constexpr size_t rowWsDoubles() { return 3 * JU_MAX + 3 * JU_MAX + 18; }
+HD void rowWsMap(double* base, RowWs& r) {
+  r.wsq = base;
+  r.coef = r.wsq + JU_MAX;
+  r.val = r.coef + JU_MAX;
+  r.aux = r.val + JU_MAX;
+  r.Rf = r.aux + 3 * JU_MAX;
+}
+
 // shared-memory map of K1a (node physics)
 struct LqWs {
   DynWs* dyn;
@@ -60,11 +79,13 @@ struct LqWs {
   double *JFl, *FP, *DFP, *tmpG;
   double* fs;      // 4 x 58 stage flows, b (58), stage point (58)
   double* FV;      // 2 x 18 foot values
-  double *gq, *gfoot, *ev, *pv, *sc, *rowCoef, *rowVal;   // gfoot: 2 x 93 swing-foot cost gradients ; sc[4..9]: friction gradient
+  double *gq, *gfoot, *ev, *pv, *sc;   // gfoot: 2 x 93 swing-foot cost gradients ; sc[4..9]: friction gradient
+  double *valS, *JU;                   // swing-row values (2 x 18) ; structured rows (aliases dyn->Bm, free between stage 0 and stage 1)
+  RowWs rw;
 };
 HD size_t lqWsDoubles() {
   const size_t dynD = (sizeof(DynWs) + 7) / 8;
-  return dynD + 4 * 6 * NZ + 2 * FLOC * FQ + 3 * NFRAMES + NFRAMES * 15 * 3 + 6 * NX + 2 * FQ + 3 * NZ + NC_MAX + 96 + 16 + 2 * JR_MAX + 9;
+  return dynD + 4 * 6 * NZ + 2 * FLOC * FQ + 3 * NFRAMES + NFRAMES * 15 * 3 + 6 * NX + 2 * FQ + 3 * NZ + NC_MAX + 96 + 16 + 2 * FQ + rowWsDoubles() + 9;
 }
 HD void lqWsMap(double* base, LqWs& s) {
   const size_t dynD = (sizeof(DynWs) + 7) / 8;
@@ -81,8 +102,10 @@ HD void lqWsMap(double* base, LqWs& s) {
   s.ev = s.gfoot + 2 * NZ;
   s.pv = s.ev + NC_MAX;
   s.sc = s.pv + 96;
-  s.rowCoef = s.sc + 16;
-  s.rowVal = s.rowCoef + JR_MAX;
+  s.valS = s.sc + 16;
+  rowWsMap(s.valS + 2 * FQ, s.rw);
+  s.JU = &s.dyn->Bm[0][0];
+  static_assert(JU_MAX * NUC <= NB * 36, "structured rows must fit the Bm alias");
 }
 
 // shared-memory map of K1b (projection + change of variables): <= 113 KB so that two CTAs share an SM.
@@ -101,7 +124,7 @@ struct PjWs {
   // dynamics views
   double *B1, *D12;              // 12 x nc (ld 12) ; 12 x (59 + nut) (ld 12)
   // Hessian view
-  double* JRc;                   // JR_CHUNK x 93 (ld JR_CHUNK)
+  double* JRc;                   // swing rows, JS_MAX x 93 (ld JS_MAX)
   // cost change-of-variables views
   double *T11, *T12, *R11, *R21, *W, *V, *rr;   // nc x 58 (ld 14), nut x 58 (ld 23), nc x nc (ld 14), nut x nc (ld 23), nc x nut (ld 14), nut x nut (ld 23), 35 + 35
 };
@@ -132,7 +155,7 @@ HD void pjWsMap(double* base, PjWs& s) {
   s.B1 = s.scratch;                          // 12 x 14 = 168
   s.D12 = s.B1 + 12 * NC_MAX;                // 12 x 82 = 984
   // Hessian
-  s.JRc = s.scratch;                         // 18 x 93 = 1674
+  s.JRc = s.scratch;                         // 30 x 93 = 2790
   // cost change of variables
   s.T11 = s.scratch;                         // 14 x 58 = 812
   s.T12 = s.T11 + NC_MAX * NX;               // 23 x 58 = 1334
@@ -368,12 +391,11 @@ HD void costPhaseFriction(Par P, const WbDeviceModel& m, const NodeIn& n, double
   }
 }
 
-// Row groups of the Gauss-Newton / penalty terms: group 0/1 = foot 0/1 (swing: 18 residual rows, stance: 4 moment rows), group 2 = collision.
-// Fills JR (ld JR_MAX, weighted rows), rowCoef (gradient coefficient per weighted row) and the value contribution; returns rows via sc.
-HD int groupRows(const NodeIn& n, int g) {
-  if (g < 2) return n.contact[g] ? 4 : FQ;
-  return (n.contact[0] && n.contact[1]) ? 0 : 16;
-}
+// ---- structured penalty rows -------------------------------------------------------------------------------------------------------------------
+HD int momRows(const NodeIn& n, int c) { return n.contact[c] ? 4 : 0; }
+HD int collRows(const NodeIn& n) { return (n.contact[0] && n.contact[1]) ? 0 : 16; }
+HD int structRows(const NodeIn& n) { return momRows(n, 0) + momRows(n, 1) + collRows(n); }
+HD int swingRows(const NodeIn& n) { return (n.contact[0] ? 0 : 15) + (n.contact[1] ? 0 : 15); }
 HD void collisionPair(int r, int& a, int& b, bool& knee) {
   // FootCollisionConstraint.cpp:112-137 ; frames: 0 fl, 1 fl_p1, 2 fl_p2, 3 fr, 4 fr_p1, 5 fr_p2, 6 ankle_l, 7 ankle_r, 8 knee_l, 9 knee_r
   const int A[16] = {1, 1, 2, 2, 0, 0, 3, 3, 0, 8, 0, 1, 2, 3, 4, 5};
@@ -382,99 +404,96 @@ HD void collisionPair(int r, int& a, int& b, bool& knee) {
   b = B[r];
   knee = (r == 9);
 }
-HD void costPhaseRows(Par P, const WbDeviceModel& m, const NodeIn& n, int g, const double* JF, const double* FV, const DynWs& w, const double* FP,
-                      const double* DFP, double* JR, int ldJR, double* rowCoef, double* rowVal, bool valuesOnly = false) {
-  const int nr = groupRows(n, g);
-  // one item per (row, entry); entry == NZ carries the row scalars
-  for (int it = P.tid; it < nr * (valuesOnly ? 1 : NZ + 1); it += P.nt) {
-    const int r = it % nr, d = valuesOnly ? NZ : it / nr;
-    double wsq = 0.0, coef = 0.0, value = 0.0, entry = 0.0;
-    if (g < 2 && !n.contact[g]) {
-      // EndEffectorDynamicsFootCost residual rows (EndEffectorDynamicsFootCost.cpp:91-124): sqrtW * impact * [0, oriErr, v, w, a, alpha]
-      const double sw = m.footSqrtW[r] * n.impact[g];
-      const double res = (r < 3) ? 0.0 : sw * FV[FQ * g + r];
-      wsq = 1.0;
-      coef = res;
-      value = 0.5 * res * res;
-      if (d < NZ) entry = (r < 3) ? 0.0 : sw * JF[static_cast<size_t>(g * NZ + d) * FQ + r];
-    } else if (g < 2) {
-      // ContactMomentXYConstraintCppAd (ContactMomentXYConstraintCppAd.cpp:86-104) under a relaxed barrier
-      const int b = m.frameBody[3 * g];
+// per-row scalars, one item per structured row (row order: moment rows of foot 0, of foot 1, collision rows)
+HD void costPhaseRowScalars(Par P, const WbDeviceModel& m, const NodeIn& n, const DynWs& w, const double* FP, RowWs rw) {
+  const int nm0 = momRows(n, 0), nm = nm0 + momRows(n, 1), nr = nm + collRows(n);
+  for (int it = P.tid; it < nr; it += P.nt) {
+    double wsq = 0.0, coef = 0.0, v = 0.0, d1, d2;
+    if (it < nm) {
+      // ContactMomentXYConstraintCppAd (ContactMomentXYConstraintCppAd.cpp:86-104) under a relaxed barrier:  h_r = sm * lm[ax] + bound * lf.z
+      const int c = (it < nm0) ? 0 : 1, r = it - (c ? nm0 : 0);
       double Rf[9];
-      mm3(w.Rb, w.R[b], Rf);
-      const V3 fw = ld3(n.u + 6 * g), mw = ld3(n.u + 6 * g + 3);
-      const V3 lf = mtv(Rf, fw), lm = mtv(Rf, mw);
-      // h_r = sm * lm[ax] + bound * lf.z
-      const int ax = r < 2 ? 0 : 1;
+      mm3(w.Rb, w.R[m.frameBody[3 * c]], Rf);
+      const V3 lf = mtv(Rf, ld3(n.u + 6 * c)), lm = mtv(Rf, ld3(n.u + 6 * c + 3));
       const double sm = (r == 0 || r == 3) ? 1.0 : -1.0;
       const double bound = (r == 0) ? -m.rect[2] : (r == 1 ? m.rect[3] : (r == 2 ? -m.rect[0] : m.rect[1]));
-      const double lmv = ax == 0 ? lm.x : lm.y;
-      const double h = sm * lmv + bound * lf.z;
-      double v, d1, d2;
+      const double h = sm * (r < 2 ? lm.x : lm.y) + bound * lf.z;
       penRelaxed(m.momMu, m.momDelta, h, v, d1, d2);
       wsq = sqrt(d2);
       coef = d1 / wsq;
-      value = v;
-      if (d < NZ) {
-        double dh = 0.0;
-        // tangent of the foot rotation: dRf = [omega]x Rf  -> d(Rf' a) = -Rf'(omega x a)
-        V3 om = mk(0, 0, 0);
-        bool rot = false;
-        if (d >= 3 && d < 6) {
-          // world angular direction of th_k: columns of Rb Sz
-          const int k = d - 3;
-          om = mv(w.Rb, mk(w.Sz[k], w.Sz[3 + k], w.Sz[6 + k]));
-          rot = true;
-        } else if (d >= 6 && d < NV) {
-          const int kb = d - 6 + 1;
-          if (m.subtree[kb] >> b & 1u) {
-            om = mv(w.Rb, ld3(w.S[kb] + 3));
-            rot = true;
-          }
-        }
-        if (rot) {
-          const V3 dlf = -mtv(Rf, cross(om, fw)), dlm = -mtv(Rf, cross(om, mw));
-          dh = sm * (ax == 0 ? dlm.x : dlm.y) + bound * dlf.z;
-        } else if (d >= NX + 6 * g && d < NX + 6 * g + 6) {
-          const int j = d - NX - 6 * g;
-          const V3 col = mk(Rf[3 * (j % 3)], Rf[3 * (j % 3) + 1], Rf[3 * (j % 3) + 2]);  // Rf' e_j = row j of Rf
-          if (j < 3) dh = bound * col.z;
-          else dh = sm * (ax == 0 ? col.x : col.y);
-        }
-        entry = wsq * dh;
-      }
+      if (r == 0)
+        for (int k = 0; k < 9; ++k) rw.Rf[9 * c + k] = Rf[k];
     } else {
       // FootCollisionConstraint under the piecewise-polynomial barrier
       int a, b;
       bool knee;
-      collisionPair(r, a, b, knee);
+      collisionPair(it - nm, a, b, knee);
       const V3 dv = ld3(FP + 3 * a) - ld3(FP + 3 * b);
       const double dist = sqrt(dot(dv, dv));
-      const double h = dist - 2.0 * (knee ? m.rKnee : m.rFoot);
-      double v, d1, d2;
-      penPwPoly(m.collMu, m.collDelta, h, v, d1, d2);
-      value = v;
+      penPwPoly(m.collMu, m.collDelta, dist - 2.0 * (knee ? m.rKnee : m.rFoot), v, d1, d2);
       if (d2 > 0.0) {
         wsq = sqrt(d2);
         coef = d1 / wsq;
-        if (d < NZ) {
-          int dl = -1;
-          if (d >= 3 && d < 6) dl = d - 3;
-          else if (d >= 6 && d < 18) dl = 3 + (d - 6);
-          if (dl >= 0) {
-            const V3 t = ld3(DFP + (a * 15 + dl) * 3) - ld3(DFP + (b * 15 + dl) * 3);
-            entry = wsq * dot(dv, t) / dist;
-          }
-        }
       }
+      st3(rw.aux + 3 * it, (1.0 / dist) * dv);
     }
-    if (d < NZ) JR[r + ldJR * d] = entry;
-    else {
-      rowCoef[r] = coef;
-      rowVal[r] = value;
-    }
+    rw.wsq[it] = wsq;
+    rw.coef[it] = coef;
+    rw.val[it] = v;
   }
 }
+// weighted row entries over the compact column support, one item per (row, compact column)
+HD void costPhaseRowEntries(Par P, const WbDeviceModel& m, const NodeIn& n, const DynWs& w, const double* DFP, RowWs rw, double* JU) {
+  const int nm0 = momRows(n, 0), nm = nm0 + momRows(n, 1), nr = nm + collRows(n);
+  for (int it = P.tid; it < nr * NUC; it += P.nt) {
+    const int r = it % nr, i = it / nr;
+    double e = 0.0;
+    if (r < nm) {
+      const int c = (r < nm0) ? 0 : 1, lr = r - (c ? nm0 : 0);
+      const int b = m.frameBody[3 * c];
+      const double* Rf = rw.Rf + 9 * c;
+      const double sm = (lr == 0 || lr == 3) ? 1.0 : -1.0;
+      const double bound = (lr == 0) ? -m.rect[2] : (lr == 1 ? m.rect[3] : (lr == 2 ? -m.rect[0] : m.rect[1]));
+      if (i < 15) {
+        // tangent of the foot rotation: dRf = [omega]x Rf  ->  d(Rf' a) = -Rf'(omega x a)
+        V3 om = mk(0, 0, 0);
+        bool rotd = false;
+        if (i < 3) {
+          om = mv(w.Rb, mk(w.Sz[i], w.Sz[3 + i], w.Sz[6 + i]));   // world angular direction of th_i
+          rotd = true;
+        } else if (m.subtree[i - 2] >> b & 1u) {
+          om = mv(w.Rb, ld3(w.S[i - 2] + 3));
+          rotd = true;
+        }
+        if (rotd) {
+          const V3 dlf = -mtv(Rf, cross(om, ld3(n.u + 6 * c))), dlm = -mtv(Rf, cross(om, ld3(n.u + 6 * c + 3)));
+          e = sm * (lr < 2 ? dlm.x : dlm.y) + bound * dlf.z;
+        }
+      } else {
+        const int j = i - 15 - 6 * c;
+        if (j >= 0 && j < 6) {
+          const V3 col = mk(Rf[3 * (j % 3)], Rf[3 * (j % 3) + 1], Rf[3 * (j % 3) + 2]);  // Rf' e_j = row j of Rf
+          e = (j < 3) ? bound * col.z : sm * (lr < 2 ? col.x : col.y);
+        }
+      }
+    } else if (i < 15) {
+      int a, b;
+      bool knee;
+      collisionPair(r - nm, a, b, knee);
+      e = dot(ld3(rw.aux + 3 * r), ld3(DFP + (a * 15 + i) * 3) - ld3(DFP + (b * 15 + i) * 3));
+    }
+    JU[r + JU_MAX * i] = rw.wsq[r] * e;
+  }
+}
+// values of the swing-foot residual rows: valS[c][r] = 1/2 (sqrtW_r impact_c FV_r)^2   (EndEffectorDynamicsFootCost.cpp:91-124)
+HD void costPhaseSwingValues(Par P, const WbDeviceModel& m, const NodeIn& n, const double* FV, double* valS) {
+  for (int it = P.tid; it < 2 * FQ; it += P.nt) {
+    const int c = it / FQ, r = it % FQ;
+    const double res = (n.contact[c] || r < 3) ? 0.0 : m.footSqrtW[r] * n.impact[c] * FV[it];
+    valS[it] = 0.5 * res * res;
+  }
+}
+
 // Fused foot phase, one item per (foot c, tangent direction d): column d of the foot's 18 quantities (scatter of the local tangents + the
 // chain through the base acceleration, J_fb G) is formed in registers and consumed at once: the foot's equality-constraint rows go to CD,
 // a swinging foot's 18 weighted residual rows to JR, and its share of the cost gradient to gfoot[c][d].  Nothing dense is staged.
@@ -501,7 +520,7 @@ HD int footZToLocal(const WbDeviceModel& m, int c, int d) {
   return -1;
 }
 HD void footPhaseColumns(Par P, const WbDeviceModel& m, const NodeIn& n, const double* JFl, const double* G, const double* FV, double* CD,
-                         double* JR, double* gfoot) {
+                         double* JS, double* gfoot) {
   const int n0 = n.contact[0] ? 6 : 7;
   for (int it = P.tid; it < 2 * NZ; it += P.nt) {
     const int c = it / NZ, d = it - c * NZ;
@@ -532,32 +551,31 @@ HD void footPhaseColumns(Par P, const WbDeviceModel& m, const NodeIn& n, const d
 #pragma unroll
       for (int lr = 0; lr < 6; ++lr) cd[lr] = (d == NX + 6 * c + lr) ? 1.0 : 0.0;            // ZeroWrenchConstraint
       cd[6] = m.gPosZ * col[2] + m.gLinVelZ * col[8] + m.gLinAccZ * col[14];                 // SwingLegVerticalConstraintCppAd
-      double* jr = JR + (c ? groupRows(n, 0) : 0) + JR_MAX * d;                              // EndEffectorDynamicsFootCost rows
+      double* js = JS + ((c && !n.contact[0]) ? 15 : 0) + JS_MAX * d;                        // EndEffectorDynamicsFootCost rows 3..17
 #pragma unroll
-      for (int r = 0; r < FQ; ++r) {
-        const double sw = (r < 3) ? 0.0 : m.footSqrtW[r] * n.impact[c];
+      for (int r = 3; r < FQ; ++r) {
+        const double sw = m.footSqrtW[r] * n.impact[c];
         const double e = sw * col[r];
-        jr[r] = e;
+        js[r - 3] = e;
         gsum = fma(e, sw * FV[FQ * c + r], gsum);
       }
     }
     gfoot[it] = gsum;
   }
 }
-// gq += swing-foot gradients + friction gradient + JR' coef over the rows [r0, r1) that were written row-wise (moment / collision rows)
-HD void costPhaseGradient(Par P, const NodeIn& n, const double* JR, const double* rowCoef, const double* gfoot, const double* fricG, double* gq) {
-  const int g0 = groupRows(n, 0), g1 = groupRows(n, 1), g2 = groupRows(n, 2);
+// gq += swing-foot gradients + friction gradient + JU' coef ; the structured rows are copied to the record on the way
+HD void costPhaseGradient(Par P, const NodeIn& n, const double* JU, const double* coef, const double* gfoot, const double* fricG, double* gq,
+                          double* midJU) {
+  const int nr = structRows(n);
   for (int i = P.tid; i < NZ; i += P.nt) {
     double acc = gfoot[i] + gfoot[NZ + i];
     if (i >= NX && i < NX + 12 && (i - NX) % 6 < 3) acc += fricG[3 * ((i - NX) / 6) + (i - NX) % 6];
-    const double* col = JR + JR_MAX * i;
-    if (n.contact[0])
-      for (int r = 0; r < g0; ++r) acc = fma(col[r], rowCoef[r], acc);
-    if (n.contact[1])
-      for (int r = g0; r < g0 + g1; ++r) acc = fma(col[r], rowCoef[r], acc);
-    for (int r = g0 + g1; r < g0 + g1 + g2; ++r) acc = fma(col[r], rowCoef[r], acc);
+    const int uc = zToUcol(i);
+    if (uc >= 0)
+      for (int r = 0; r < nr; ++r) acc = fma(JU[r + JU_MAX * uc], coef[r], acc);
     gq[i] += acc;
   }
+  for (int it = P.tid; it < JU_MAX * NUC; it += P.nt) midJU[it] = (it % JU_MAX < nr) ? JU[it] : 0.0;
 }
 
 // ---- projection: Eigen::FullPivLU semantics (complete pivoting; particular solution with free variables = 0; kernel basis) ----------------
@@ -742,9 +760,12 @@ namespace b200sqp {
 // workspace of the value-only rollout kernel (K3)
 struct RoWs {
   DynWs* dyn;
-  double *fs, *xs, *FV, *FP, *pv, *rowCoef, *rowVal, *ev, *sc, *xa, *xna, *ua;
+  double *fs, *xs, *FV, *FP, *pv, *valS, *ev, *sc, *xa, *xna, *ua;
+  RowWs rw;
 };
-HD size_t roWsDoubles() { return (sizeof(DynWs) + 7) / 8 + 4 * NX + NX + 2 * FQ + 3 * NFRAMES + 96 + 2 * JR_MAX + NC_MAX + 8 + 2 * NX + NU + 5; }
+HD size_t roWsDoubles() {
+  return (sizeof(DynWs) + 7) / 8 + 4 * NX + NX + 2 * FQ + 3 * NFRAMES + 96 + 2 * FQ + rowWsDoubles() + NC_MAX + 8 + 2 * NX + NU + 5;
+}
 HD void roWsMap(double* base, RoWs& r) {
   r.dyn = reinterpret_cast<DynWs*>(base);
   r.fs = base + (sizeof(DynWs) + 7) / 8;
@@ -752,9 +773,9 @@ HD void roWsMap(double* base, RoWs& r) {
   r.FV = r.xs + NX;
   r.FP = r.FV + 2 * FQ;
   r.pv = r.FP + 3 * NFRAMES;
-  r.rowCoef = r.pv + 96;
-  r.rowVal = r.rowCoef + JR_MAX;
-  r.ev = r.rowVal + JR_MAX;
+  r.valS = r.pv + 96;
+  rowWsMap(r.valS + 2 * FQ, r.rw);
+  r.ev = r.valS + 2 * FQ + rowWsDoubles();
   r.sc = r.ev + NC_MAX;
   r.xa = r.sc + 8;
   r.xna = r.xa + NX;
