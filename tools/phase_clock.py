@@ -71,3 +71,16 @@ for kid, name in [(0, "K1a lq_dyn_kernel"), (1, "K1b lq_proj_kernel"), (2, "K3 r
     for line, (cyc, k) in sorted(agg.items(), key=lambda kv: -kv[1][0])[:args.top]:
         text = src[line - 1].strip()[:110] if 0 < line <= len(src) else "?"
         print(f"  {cyc:8d} {100.0 * cyc / tot:5.1f}%  x{k:<2d} L{line:<4d} {text}")
+
+buf = (C.c_longlong * 64)()
+n = L.b200sqp_debug_phase_clocks(3, buf, 32, -1)
+a = np.array(buf[:64], dtype=np.int64).reshape(32, 2)
+src = (ROOT / "wb_humanoid_mpc_b200" / "csrc" / "riccati.cuh").read_text().split("\n")
+tot = a[:, 1].sum()
+print(f"\n== K2 riccati_kernel (instance 0, cycles summed over all stages): {tot} cycles")
+for slot in range(32):
+    if a[slot, 1] > 0:
+        line = int(a[slot, 0])
+        # show the statement that precedes the barrier
+        ctx = " | ".join(t.strip()[:70] for t in src[max(0, line - 4):line - 1])
+        print(f"  slot {slot:2d} {a[slot, 1]:9d} {100.0 * a[slot, 1] / tot:5.1f}%  L{line:<4d} {ctx}")

@@ -96,6 +96,46 @@ __device__ __forceinline__ void warp_cholesky_lower(int n, double* __restrict__ 
   if (lane == 0 && !good) *ok = 0;
 }
 
+// Fused Cholesky factorisation and triangular inverse of an n x n SPD matrix (n <= NMAX <= 32) by ONE warp, register resident and
+// branch free.  Lane j owns the FULL symmetric column j of the matrix (a[]) and column j of L^-1 (z[]); rows / columns >= n are padded
+// with the identity, so the loops are compile-time.  Step k: every lane forms its own L[j][k] = a[k] / sqrt(pivot) from its own register
+// (symmetry), column k of L is broadcast once (one shuffle per row) and used twice, for the symmetric trailing update
+// a[i] -= L[i][k] L[j][k] and for the right-looking inverse update z[i] -= L[i][k] z[k].  No shared-memory traffic, no division.
+// Writes Linv (lower triangular, zeros above the diagonal); *ok = 0 on a non-positive pivot.
+template <int NMAX>
+__device__ __forceinline__ void warp_chol_inverse(int n, const double* __restrict__ A, int lda, double* __restrict__ Linv, int ldl, int* ok) {
+  const int lane = threadIdx.x & 31;
+  double a[NMAX], z[NMAX];
+#pragma unroll
+  for (int i = 0; i < NMAX; ++i) {
+    const int r = i > lane ? i : lane, c = i > lane ? lane : i;   // lower-triangle source of the symmetric entry (i, lane)
+    a[i] = (i < n && lane < n) ? A[r + c * lda] : ((i == lane) ? 1.0 : 0.0);
+    z[i] = (i == lane) ? 1.0 : 0.0;
+  }
+  bool good = true;
+#pragma unroll
+  for (int k = 0; k < NMAX; ++k) {
+    double d = __shfl_sync(0xffffffffu, a[k], k);
+    if (!(d > 0.0)) {
+      good = false;
+      d = 1.0;
+    }
+    const double inv = rsqrt(d);
+    const double ljk = a[k] * inv;   // L[lane][k]
+    z[k] *= inv;
+#pragma unroll
+    for (int i = k + 1; i < NMAX; ++i) {
+      const double v = __shfl_sync(0xffffffffu, a[i], k) * inv;   // L[i][k]
+      a[i] = fma(-v, ljk, a[i]);
+      z[i] = fma(-v, z[k], z[i]);
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < NMAX; ++i)
+    if (i < n && lane < n) Linv[i + lane * ldl] = z[i];
+  if (lane == 0 && !good) *ok = 0;
+}
+
 // X = L^-1 X for an n x m right-hand side (column-major, ldx); one thread per column
 __device__ __forceinline__ void block_trsm_lower(int n, int m, const double* __restrict__ L, int ldl, double* __restrict__ X, int ldx) {
   for (int c = threadIdx.x; c < m; c += blockDim.x) {

@@ -16,6 +16,25 @@
 
 namespace b200sqp {
 
+// development aid (tools/phase_clock.py, -DB200SQP_PHASE_CLOCK): cycles of instance 0 accumulated per barrier slot over all stages
+#ifdef B200SQP_PHASE_CLOCK
+__device__ long long g_ricClk[32][2];
+#define RIC_TICK(slot)                                                   \
+  if (threadIdx.x == 0 && blockIdx.x == 0) {                             \
+    const long long now_ = clock64();                                    \
+    g_ricClk[slot][0] = __LINE__;                                        \
+    g_ricClk[slot][1] += now_ - ricT_;                                   \
+    ricT_ = now_;                                                        \
+  }
+#define RIC_CLOCK_BEGIN()                                                \
+  long long ricT_ = clock64();                                           \
+  if (threadIdx.x == 0 && blockIdx.x == 0)                               \
+    for (int i_ = 0; i_ < 32; ++i_) g_ricClk[i_][0] = g_ricClk[i_][1] = 0;
+#else
+#define RIC_TICK(slot)
+#define RIC_CLOCK_BEGIN()
+#endif
+
 struct QpDeviceView {
   int B, N, nx, numax;
   const double *A, *Bm, *b, *Q, *S, *R, *q, *r, *dx0;
@@ -107,6 +126,7 @@ __global__ void __launch_bounds__(256, 1) riccati_kernel(QpDeviceView v) {
     __pipeline_commit();
   };
   prefetch(N - 1, 0, PQ[1 - cur]);
+  RIC_CLOCK_BEGIN()
 
   for (int k = N - 1; k >= 0; --k) {
     const int set = (N - 1 - k) & 1;
@@ -119,11 +139,14 @@ __global__ void __launch_bounds__(256, 1) riccati_kernel(QpDeviceView v) {
     double* Rk = Rs[set];
     __pipeline_wait_prior(0);
     __syncthreads();
+    RIC_TICK(1)
     // ---- W = P [A | b | B] ; then W_b += p  (v = P b + p) ----------------------------------------------------------
     par_mma_gemm<false, false, 4>(P, nx, nx1 + nu, nx, 1.0, Pc, nx, ABk, nx, W, nx);
     __syncthreads();
+    RIC_TICK(2)
     for (int i = threadIdx.x; i < nx; i += blockDim.x) W[nx * nx + i] += Pc[nx * nx + i];
     __syncthreads();
+    RIC_TICK(3)
     // [P | p] is dead: start streaming stage k-1 (its [Q | q] goes into that buffer)
     if (k > 0) prefetch(k - 1, 1 - set, Pc);
     // ---- [Q~ | q~] = [Q | q] + A'[W_A | v] (+reg), [S~ | r~] = [S | r] + B'[W_A | v], R~ = R + B'W_B (+reg) ----------------
@@ -133,30 +156,32 @@ __global__ void __launch_bounds__(256, 1) riccati_kernel(QpDeviceView v) {
       par_mma_gemm<true, true, 3>(P, nu, nu, nx, 1.0, ABk + nx * nx1, nx, W + nx * nx1, nx, Rk, nm);
     }
     __syncthreads();
+    RIC_TICK(4)
     for (int i = threadIdx.x; i < nx; i += blockDim.x) Pn[i + i * nx] += v.reg;
     for (int i = threadIdx.x; i < nu; i += blockDim.x) Rk[i + i * nm] += v.reg;
     __syncthreads();
+    RIC_TICK(5)
     if (nu > 0) {
-      // ---- R~ = L L' (warp 0), Linv = L^-1 (one thread per column) ------------------------------------------------------------
-      warp_cholesky_lower(nu, Rk, nm, &ok);
-      __syncthreads();
-      for (int c = threadIdx.x; c < nu; c += blockDim.x) {
-        for (int i = 0; i < nu; ++i) {
-          double s = (i == c) ? 1.0 : 0.0;
-          for (int j = c; j < i; ++j) s = fma(-Rk[i + j * nm], Linv[j + c * nm], s);
-          Linv[i + c * nm] = (i < c) ? 0.0 : s / Rk[i + i * nm];
-        }
+      // ---- R~ = L L', Linv = L^-1: fused, register resident, warp 0 ---------------------------------------------------------------
+      if (threadIdx.x < 32) {
+        if (nm <= 8) warp_chol_inverse<8>(nu, Rk, nm, Linv, nm, &ok);
+        else if (nm <= 16) warp_chol_inverse<16>(nu, Rk, nm, Linv, nm, &ok);
+        else if (nm <= 24) warp_chol_inverse<24>(nu, Rk, nm, Linv, nm, &ok);
+        else warp_chol_inverse<32>(nu, Rk, nm, Linv, nm, &ok);
       }
       __syncthreads();
+      RIC_TICK(6)
       // ---- [Yl | yl] = L^-1 [S~ | r~] (into W) ---------------------------------------------------------------------------------
       double* Yl = W;
       double* Kout = W + even_up(nm * nx1);
       par_mma_gemm<false, false, 4>(P, nu, nx1, nu, 1.0, Linv, nm, Yk, nm, Yl, nm);
       __syncthreads();
+    RIC_TICK(8)
       // ---- [P | p] = [Q~ | q~] - Yl'[Yl | yl] ; [K | k] = -L^-T [Yl | yl] ---------------------------------------------------
       par_mma_gemm<true, true, 4>(P, nx, nx1, nu, -1.0, Yl, nm, Yl, nm, Pn, nx);
       par_mma_gemm<true, false, 4>(P, nu, nx1, nu, -1.0, Linv, nm, Yl, nm, Kout, nm);
       __syncthreads();
+    RIC_TICK(9)
       for (int t = threadIdx.x; t < nm * nx; t += blockDim.x) v.K[sk * nm * nx + t] = (t % nm < nu) ? Kout[t] : 0.0;
       for (int t = threadIdx.x; t < nu; t += blockDim.x) v.kff[sk * nm + t] = Kout[nm * nx + t];
     }
@@ -171,12 +196,14 @@ __global__ void __launch_bounds__(256, 1) riccati_kernel(QpDeviceView v) {
     }
     cur = 1 - cur;
     __syncthreads();
+    RIC_TICK(10)
     if (v.keepP) {
       block_copy(nx * nx, PQ[cur], v.P + (iN1 + k) * nx * nx);
       block_copy(nx, PQ[cur] + nx * nx, v.p + (iN1 + k) * nx);
     }
   }
   __syncthreads();
+    RIC_TICK(11)
   // ---- forward substitution, double-buffered: x+ = [A | b | B] [x; 1; u] ----------------------------------------------------------------
   auto prefetchF = [&](int k, int set) {
     const size_t sk = iN + k;
@@ -193,6 +220,7 @@ __global__ void __launch_bounds__(256, 1) riccati_kernel(QpDeviceView v) {
   block_copy(nx, v.dx0 + static_cast<size_t>(inst) * nx, xv);
   prefetchF(0, 0);
   __syncthreads();
+    RIC_TICK(12)
   block_copy(nx, xv, v.dx + iN1 * nx);
   for (int k = 0; k < N; ++k) {
     const int set = k & 1;
@@ -200,6 +228,7 @@ __global__ void __launch_bounds__(256, 1) riccati_kernel(QpDeviceView v) {
     const size_t sk = iN + k;
     __pipeline_wait_prior(0);
     __syncthreads();
+    RIC_TICK(13)
     if (k + 1 < N) prefetchF(k + 1, 1 - set);
     // du = K x + k : 8 lanes per row, shuffle-reduced
     {
@@ -217,6 +246,7 @@ __global__ void __launch_bounds__(256, 1) riccati_kernel(QpDeviceView v) {
       }
     }
     __syncthreads();
+    RIC_TICK(14)
     // x+ = A x + b + B u : 4 lanes per row
     {
       const int row = threadIdx.x >> 2, sub = threadIdx.x & 3;
@@ -231,12 +261,14 @@ __global__ void __launch_bounds__(256, 1) riccati_kernel(QpDeviceView v) {
       if (sub == 0 && row < nx) tv[row] = s + Ak[nx * nx + row];
     }
     __syncthreads();
+    RIC_TICK(15)
     for (int i = threadIdx.x; i < nx; i += blockDim.x) {
       xv[i] = tv[i];
       v.dx[(iN1 + k + 1) * nx + i] = tv[i];
     }
   }
   __syncthreads();
+    RIC_TICK(16)
   if (threadIdx.x == 0) {
     int bad = !ok;
     for (int i = 0; i < nx; ++i) bad |= !isfinite(xv[i]);
