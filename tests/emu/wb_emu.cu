@@ -31,11 +31,7 @@ int emu_dyn(const b200sqp_model_desc* d, const double* x, const double* u, doubl
   const int NT = 128;
   if (deriv) {
     RUN_PHASE(NT, dynPhaseJoints<true>(P, m, x, w));
-    RUN_PHASE(NT, dynPhaseAbsRot(P, m, w));
-    RUN_PHASE(NT, dynPhaseAxes(P, m, w));
-    RUN_PHASE(NT, dynPhaseVel(P, m, x, w));
-    RUN_PHASE(NT, dynPhaseAcc(P, m, x, u, w));
-    RUN_PHASE(NT, dynPhaseInertia(P, m, w));
+    RUN_PHASE(NT, dynPhaseBodies(P, m, x, u, w));
     RUN_PHASE(NT, dynPhaseBmat(P, w));
     RUN_PHASE(NT, dynPhaseComposite<true>(P, m, w));
     RUN_PHASE(NT, dynPhaseFinal(P, m, u, w));
@@ -43,11 +39,7 @@ int emu_dyn(const b200sqp_model_desc* d, const double* x, const double* u, doubl
     RUN_PHASE(NT, dynPhaseJacobian(P, m, w, G));
   } else {
     RUN_PHASE(NT, dynPhaseJoints<false>(P, m, x, w));
-    RUN_PHASE(NT, dynPhaseAbsRot(P, m, w));
-    RUN_PHASE(NT, dynPhaseAxes(P, m, w));
-    RUN_PHASE(NT, dynPhaseVel(P, m, x, w));
-    RUN_PHASE(NT, dynPhaseAcc(P, m, x, u, w));
-    RUN_PHASE(NT, dynPhaseInertia(P, m, w));
+    RUN_PHASE(NT, dynPhaseBodies(P, m, x, u, w));
     RUN_PHASE(NT, dynPhaseComposite<false>(P, m, w));
     RUN_PHASE(NT, dynPhaseFinal(P, m, u, w));
     RUN_PHASE(NT, dynWriteFlow(P, x, u, w, xdot));

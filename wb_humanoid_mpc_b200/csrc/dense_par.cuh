@@ -14,6 +14,19 @@ HD Par rot(Par P, int k) {
   return Par{t, P.nt};
 }
 
+// dst[0..n) = src[0..n) by the whole phase, four independent loads in flight per thread (global -> shared staging of a record)
+HD void par_copy(Par P, double* __restrict__ dst, const double* __restrict__ src, int n) {
+  int i = P.tid;
+  for (; i + 3 * P.nt < n; i += 4 * P.nt) {
+    const double a = src[i], b = src[i + P.nt], c = src[i + 2 * P.nt], d = src[i + 3 * P.nt];
+    dst[i] = a;
+    dst[i + P.nt] = b;
+    dst[i + 2 * P.nt] = c;
+    dst[i + 3 * P.nt] = d;
+  }
+  for (; i < n; i += P.nt) dst[i] = src[i];
+}
+
 // C(MxN, ldc) = (ACC ? C : 0) + alpha * op(A) * B ; op(A) = A (MxK, lda) or A^T (A stored KxM, lda) ; B is KxN (ldb)
 template <int TM, int TN, bool TRANS_A, bool ACC, class PAR>
 HD void par_gemm(PAR P, int M, int N, int K, double alpha, const double* __restrict__ A, int lda, const double* __restrict__ B, int ldb,

@@ -71,6 +71,8 @@ HD void baseKinematics(const double* x, int dir, double g, D1* R, D1* S, D1* v0,
   a0[5] = -((s1 * c2 * td[1] + c1 * s2 * td[2]) * td[0]) - c2 * td[2] * td[1];
 }
 
+// (Ir - m c^ c^) w : rotational block of the spatial inertia about the pelvis origin applied to w
+HD V3 mvIr(const double* Ir, double ms, V3 c, V3 w) { return mv(Ir, w) - ms * cross(c, cross(c, w)); }
 HD void inv3(const double* A, double* Ai) {
   const double c00 = A[4] * A[8] - A[5] * A[7], c01 = A[5] * A[6] - A[3] * A[8], c02 = A[3] * A[7] - A[4] * A[6];
   const double det = A[0] * c00 + A[1] * c01 + A[2] * c02, id = 1.0 / det;
@@ -129,104 +131,70 @@ HD void dynPhaseJoints(Par P, const WbDeviceModel& m, const double* x, DynWs& w)
   }
 }
 
-// ---- phases 1b-1e: body-parallel kinematics.  In a common (pelvis) coordinate frame the recursions collapse to sums / products over the
-// ancestor path of each body (<= 7 joints), so no thread walks a chain with the full 6D state in registers:
-//   R_i = prod Rj[k],  p_i = sum R_parent(k) jp_k,  v_i = v0 + sum S_k qd_k,  a_i = a0 + sum (S_k qdd_k + psid_k qd_k)
-// with psid_k = v_parent(k) x S_k = (v_k - S_k qd_k) x S_k.  One item per body, one barrier between passes.
-HD void dynPhaseAbsRot(Par P, const WbDeviceModel& m, DynWs& w) {
+// ---- phase 1b: body-parallel kinematics and body dynamics in ONE pass.  In a common (pelvis) coordinate frame every per-body quantity
+// is a sum / product over the ancestor path of the body (<= 7 joints):
+//   R_i = prod Rj[k],  p_i = sum R_parent(k) jp_k,  S_k = [p_k x w_k ; w_k],  v_i = v0 + sum S_k qd_k,
+//   psd_k = v_parent(k) x S_k,  a_i = a0 + sum (S_k qdd_k + psd_k qd_k),  psdd_k = a_parent(k) x S_k + v_parent(k) x psd_k
+// so one thread per body walks its own path, recomputing its ancestors' cheap quantities instead of waiting for them behind barriers
+// (this replaces five barrier-separated sweeps), and finishes with the body's spatial inertia and force in the same item.
+HD void dynPhaseBodies(Par P, const WbDeviceModel& m, const double* x, const double* u, DynWs& w) {
   for (int i = P.tid; i < NB; i += P.nt) {
     double R[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1};
-    const int len = m.pathLen[i];
-    for (int t = 0; t < len; ++t) {
-      double T[9];
-      mm3(R, w.Rj[m.path[i][t]], T);
-#pragma unroll
-      for (int k = 0; k < 9; ++k) R[k] = T[k];
-    }
-#pragma unroll
-    for (int k = 0; k < 9; ++k) w.R[i][k] = R[k];
-  }
-}
-HD void dynPhaseAxes(Par P, const WbDeviceModel& m, DynWs& w) {
-  for (int i = P.tid; i < NB; i += P.nt) {
     V3 p = mk(0, 0, 0);
+    V6 v = ld6(w.v0), a = ld6(w.a0);
+    V6 S{mk(0, 0, 0), mk(0, 0, 0)}, psd = S, psdd = S;
     const int len = m.pathLen[i];
     for (int t = 0; t < len; ++t) {
       const int k = m.path[i][t];
-      p = p + mv(w.R[m.parent[k]], ld3(m.jp[k]));
+      p = p + mv(R, ld3(m.jp[k]));
+      double T[9];
+      mm3(R, w.Rj[k], T);
+#pragma unroll
+      for (int e = 0; e < 9; ++e) R[e] = T[e];
+      const V3 om = mv(R, ld3(m.axis[k]));
+      S = V6{cross(p, om), om};
+      const double qd = x[NV + 5 + k], qdd = u[12 + k - 1];
+      psd = mcross(v, S);                      // v, a still hold the parent's values here
+      psdd = mcross(a, S) + mcross(v, psd);
+      v = v + qd * S;
+      a = a + qdd * S + qd * psd;
     }
+#pragma unroll
+    for (int e = 0; e < 9; ++e) w.R[i][e] = R[e];
     st3(w.p[i], p);
-    if (i == 0) {
-      for (int k = 0; k < 6; ++k) w.S[0][k] = 0.0;
-    } else {
-      const V3 om = mv(w.R[i], ld3(m.axis[i]));
-      st6(w.S[i], V6{cross(p, om), om});
-    }
-  }
-}
-HD void dynPhaseVel(Par P, const WbDeviceModel& m, const double* x, DynWs& w) {
-  for (int i = P.tid; i < NB; i += P.nt) {
-    V6 v = ld6(w.v0);
-    const int len = m.pathLen[i];
-    for (int t = 0; t < len; ++t) {
-      const int k = m.path[i][t];
-      v = v + x[NV + 5 + k] * ld6(w.S[k]);
-    }
+    st6(w.S[i], S);
     st6(w.v[i], v);
-    if (i == 0) {
-      for (int k = 0; k < 6; ++k) w.psd[0][k] = 0.0;
-    } else {
-      const V6 S = ld6(w.S[i]);
-      st6(w.psd[i], mcross(v - x[NV + 5 + i] * S, S));
-    }
-  }
-}
-HD void dynPhaseAcc(Par P, const WbDeviceModel& m, const double* x, const double* u, DynWs& w) {
-  for (int i = P.tid; i < NB; i += P.nt) {
-    V6 a = ld6(w.a0);
-    const int len = m.pathLen[i];
-    for (int t = 0; t < len; ++t) {
-      const int k = m.path[i][t];
-      a = a + u[12 + k - 1] * ld6(w.S[k]) + x[NV + 5 + k] * ld6(w.psd[k]);
-    }
     st6(w.a[i], a);
-    if (i == 0) {
-      for (int k = 0; k < 6; ++k) w.psdd[0][k] = 0.0;
-    } else {
-      const V6 S = ld6(w.S[i]), psd = ld6(w.psd[i]);
-      const double qd = x[NV + 5 + i];
-      const V6 al = a - u[12 + i - 1] * S - qd * psd;
-      const V6 vl = ld6(w.v[i]) - qd * S;
-      st6(w.psdd[i], mcross(al, S) + mcross(vl, psd));
-    }
-  }
-}
-
-// ---- phase 2: per-body spatial inertia and force (items = bodies) --------------------------------------------------------------
-HD void dynPhaseInertia(Par P, const WbDeviceModel& m, DynWs& w) {
-  for (int i = P.tid; i < NB; i += P.nt) {
-    const double* R = w.R[i];
-    const V3 c = ld3(w.p[i]) + mv(R, ld3(m.com[i]));
+    st6(w.psd[i], psd);
+    st6(w.psdd[i], psdd);
+    // spatial inertia about the pelvis origin and the body force f = I a + v x* I v
+    const V3 c = p + mv(R, ld3(m.com[i]));
     double T[9], Ir[9];
-    // R Icom R'
+#pragma unroll
     for (int r = 0; r < 3; ++r)
+#pragma unroll
       for (int k = 0; k < 3; ++k) T[3 * r + k] = R[3 * r] * m.Icom[i][k] + R[3 * r + 1] * m.Icom[i][3 + k] + R[3 * r + 2] * m.Icom[i][6 + k];
+#pragma unroll
     for (int r = 0; r < 3; ++r)
+#pragma unroll
       for (int k = 0; k < 3; ++k) Ir[3 * r + k] = T[3 * r] * R[3 * k] + T[3 * r + 1] * R[3 * k + 1] + T[3 * r + 2] * R[3 * k + 2];
     const double ms = m.mass[i];
     const double C[9] = {0, -c.z, c.y, c.z, 0, -c.x, -c.y, c.x, 0};
     double* I = w.I[i];
+#pragma unroll
     for (int r = 0; r < 3; ++r)
+#pragma unroll
       for (int k = 0; k < 3; ++k) {
-        double cc = C[3 * r] * C[k] + C[3 * r + 1] * C[3 + k] + C[3 * r + 2] * C[6 + k];
+        const double cc = C[3 * r] * C[k] + C[3 * r + 1] * C[3 + k] + C[3 * r + 2] * C[6 + k];
         I[6 * r + k] = (r == k) ? ms : 0.0;
         I[6 * r + 3 + k] = -ms * C[3 * r + k];
         I[6 * (3 + r) + k] = ms * C[3 * r + k];
         I[6 * (3 + r) + 3 + k] = Ir[3 * r + k] - ms * cc;
       }
-    const V6 v = ld6(w.v[i]), a = ld6(w.a[i]);
-    const V6 h = m6v(I, v);
-    st6(w.f[i], m6v(I, a) + fcross(v, h));
+    // f = I a + v x* (I v), with I = [m 1, -m c^ ; m c^, Ic] applied in closed form
+    const V3 hl = ms * (v.l - cross(c, v.a)), ha = ms * cross(c, v.l) + mvIr(Ir, ms, c, v.a);
+    const V3 fl = ms * (a.l - cross(c, a.a)), fa = ms * cross(c, a.l) + mvIr(Ir, ms, c, a.a);
+    st6(w.f[i], V6{fl, fa} + fcross(v, V6{hl, ha}));
   }
 }
 
@@ -321,8 +289,19 @@ HD void baseAccTangent(const WbDeviceModel& m, const DynWs& w, V6 dN, const doub
 }
 
 // ---- phase 6: G = d(qdd_b)/d[x;u]  (6 x 93, column-major with leading dimension 6; one item per column) ------------------------------
+// Items are laid out so that the lanes of one warp differentiate the same kind of variable: items 0-31 joint positions, 32-63 joint
+// velocities, 64-95 joint accelerations, 96-127 the 24 base / wrench columns (each group padded to 32).
 HD void dynPhaseJacobian(Par P, const WbDeviceModel& m, const DynWs& w, double* G) {
-  for (int d = P.tid; d < NZ; d += P.nt) {
+  for (int it = P.tid; it < 128; it += P.nt) {
+    const int grp = it >> 5, l = it & 31;
+    int d;
+    if (grp < 3) {
+      if (l >= NJ) continue;
+      d = (grp == 0 ? 6 : (grp == 1 ? NV + 6 : NX + 12)) + l;
+    } else {
+      if (l >= 24) continue;
+      d = l < 6 ? l : (l < 12 ? NV + (l - 6) : NX + (l - 12));
+    }
     double* col = G + 6 * d;
     if (d < 3) {  // base position: no dependence
       for (int k = 0; k < 6; ++k) col[k] = 0.0;

@@ -78,9 +78,14 @@ HD void footPhaseValues(Par P, const WbDeviceModel& m, const double* x, const Dy
 }
 
 // ---- foot values + local tangents: items (c, l) ; JFl[c][k + FQ*l], FV[c][k] -----------------------------------------------------------
+// Item layout: three groups padded to one warp each, so that a warp mixes at most three kinds of direction:
+//   items 0-23 leg joint positions / velocities, 32-55 leg joint accelerations / base-acceleration directions, 64-87 base pose / base twist.
 HD void footPhaseLocalTangents(Par P, const WbDeviceModel& m, const double* x, const DynWs& w, double* FV, double* JFl) {
-  for (int it = P.tid; it < 2 * FLOC; it += P.nt) {
-    const int c = it / FLOC, l = it % FLOC;
+  for (int it = P.tid; it < 96; it += P.nt) {
+    const int grp = it >> 5, q = it & 31;
+    if (q >= 24) continue;
+    const int c = q & 1, h = q >> 1;   // h in 0..11
+    const int l = (grp == 0) ? (h < 6 ? 6 + h : 12 + h) : ((grp == 1) ? 24 + h : (h < 6 ? h : 6 + h));
     const int b = m.frameBody[3 * c];
     const V3 z3 = mk(0, 0, 0);
     const double zero9[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};

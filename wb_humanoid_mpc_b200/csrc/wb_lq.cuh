@@ -43,7 +43,7 @@ struct Mid {
   static constexpr int HDG = E + NC_MAX;                 // Hessian diagonal (93), not yet multiplied by dt
   static constexpr int GQ = HDG + NZ;                    // cost gradient (93)
   static constexpr int FRIC = GQ + NZ;                   // 2 x (3 x 3) friction-cone Hessian blocks
-  static constexpr int JS = FRIC + 18;                   // dense weighted rows (ld JS_MAX) x 93
+  static constexpr int JS = FRIC + 18;                   // dense weighted rows x 93, leading dimension = their count (15 or 30)
   static constexpr int JU = JS + JS_MAX * NZ;            // structured weighted rows (ld JU_MAX) x NUC compact columns
   static constexpr int META = JU + JU_MAX * NUC;         // nc, swing rows, structured rows, dt, dt*cost
   static constexpr int SIZE = META + 6;
@@ -117,6 +117,7 @@ struct PjWs {
   double *gq, *bvec;             // 93, 58
   double *Xt, *Kt;               // nc x 59 (ld 14): [X | x0] ; nc x nut (ld 14)
   double* AB12;                  // 12 x 93 (ld 12)
+  double* JU;                    // structured rows, JU_MAX x NUC (ld JU_MAX)
   double* scratch;
   int* iw;                       // rowOf[16] colOf[36] posOf[36]
   // phase-1 views (projection)
@@ -130,7 +131,7 @@ struct PjWs {
 };
 constexpr int PJ_SCRATCH = 3856;
 HD size_t pjWsDoubles() {
-  return NX * NX + NU * NX + NU * NU + 1 + NZ + 1 + NX + NC_MAX * (NX + 1) + NC_MAX * NUT_MAX + 12 * NZ + PJ_SCRATCH + 48;
+  return NX * NX + NU * NX + NU * NU + 1 + NZ + 1 + NX + NC_MAX * (NX + 1) + NC_MAX * NUT_MAX + 12 * NZ + JU_MAX * NUC + PJ_SCRATCH + 48;
 }
 HD void pjWsMap(double* base, PjWs& s) {
   s.Q = base;
@@ -141,7 +142,8 @@ HD void pjWsMap(double* base, PjWs& s) {
   s.Xt = s.bvec + NX;
   s.Kt = s.Xt + NC_MAX * (NX + 1);
   s.AB12 = s.Kt + NC_MAX * NUT_MAX;
-  s.scratch = s.AB12 + 12 * NZ;
+  s.JU = s.AB12 + 12 * NZ;
+  s.scratch = s.JU + JU_MAX * NUC;
   s.iw = reinterpret_cast<int*>(s.scratch + PJ_SCRATCH);
   // phase 1 (projection): CD | e | LU | triangular-solve workspace
   s.CD = s.scratch;                          // 14 x 93 = 1302
@@ -551,7 +553,7 @@ HD void footPhaseColumns(Par P, const WbDeviceModel& m, const NodeIn& n, const d
 #pragma unroll
       for (int lr = 0; lr < 6; ++lr) cd[lr] = (d == NX + 6 * c + lr) ? 1.0 : 0.0;            // ZeroWrenchConstraint
       cd[6] = m.gPosZ * col[2] + m.gLinVelZ * col[8] + m.gLinAccZ * col[14];                 // SwingLegVerticalConstraintCppAd
-      double* js = JS + ((c && !n.contact[0]) ? 15 : 0) + JS_MAX * d;                        // EndEffectorDynamicsFootCost rows 3..17
+      double* js = JS + ((c && !n.contact[0]) ? 15 : 0) + swingRows(n) * d;                  // EndEffectorDynamicsFootCost rows 3..17 (ld = row count)
 #pragma unroll
       for (int r = 3; r < FQ; ++r) {
         const double sw = m.footSqrtW[r] * n.impact[c];
