@@ -143,6 +143,17 @@ int b200sqp_reset(b200sqp_handle h);
 /* SqpSolver::runImpl for every instance; asynchronous on `stream`. */
 int b200sqp_solve(b200sqp_handle h, void* stream);
 
+/* Global-step mode (settings.global_step = 1; SURVEY.md section 8e, not a reference semantic): one line-search step size per SQP iteration
+ * for the whole, possibly multi-GPU, batch.  Per iteration b200sqp_solve evaluates the fixed ladder alpha_j = alpha_decay^j >= alpha_min
+ * for every active instance with the reference's filter test (FilterLinesearch.cpp:34-57) and leaves
+ *   stats[j] = { #instances that accept alpha_j, sum of their trial merits, max trial constraint violation, #active instances }
+ * in DEVICE memory.  The callback combines the statistics of all ranks (one small collective on `stream`) and returns the index of the
+ * chosen candidate, or -1 for a zero step; every rank must return the same index.  Without a callback the local statistics decide:
+ * the largest alpha_j accepted by every active instance.  b200sqp_global_ladder reports the candidates. */
+typedef int (*b200sqp_global_step_fn)(void* user, double* stats_device /* [n_alpha][4] */, int n_alpha, void* stream);
+int b200sqp_set_global_step_callback(b200sqp_handle h, b200sqp_global_step_fn fn, void* user);
+int b200sqp_global_ladder(b200sqp_handle h, double* alpha /* [32] */, int32_t* n_alpha);
+
 /* per-instance iteration record: mirrors sqp::LogEntry / PerformanceIndex (SqpLogging.h, PerformanceIndex.h) */
 typedef struct b200sqp_iter_log {
   double base_merit, base_cost, base_dyn_sse, base_eq_sse;

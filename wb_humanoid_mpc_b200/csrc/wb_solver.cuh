@@ -41,6 +41,7 @@ struct WbDev {
   int* flags;        // [B][F_NF]
   int* pending;      // number of instances whose line search is still running
   double* mid;       // K1a -> K1b records [B][N][Mid::SIZE]
+  double* gstats;    // global-step mode: per-candidate statistics [32][4]
   double* raw;       // optional [B][N][rawPer]
   long long rawPer;
   b200sqp_iter_log* log;  // [B][maxIter]
@@ -405,16 +406,16 @@ __global__ void __launch_bounds__(RO_THREADS) rollout_kernel(WbDev d) {
 #include "wb_rollout_body.inc"
 }
 
-// FilterLinesearch::acceptStep + takeStep bookkeeping + checkConvergence for one instance (SqpSolver.cpp:484-602, FilterLinesearch.cpp:34-57)
-__global__ void __launch_bounds__(256) accept_kernel(WbDev d) {
-  const int b = blockIdx.x;
-  int* fl = d.flags + b * F_NF;
-  if (fl[F_CONVERGED] || fl[F_LSDONE]) return;
-  __shared__ double sh[256];
-  __shared__ int decision;  // 0 continue, 1 accepted, 2 give up (zero step)
+// trial PerformanceIndex of one instance at its current alpha (sums over the per-node results of K3) and the filter test
+// (FilterLinesearch::acceptStep, FilterLinesearch.cpp:34-57)
+struct TrialEval {
+  double cost, dyn, eq, merit, g1;
+  bool acc;
+  int type;
+};
+__device__ __forceinline__ TrialEval evalTrial(const WbDev& d, int b, double alpha, double* sh) {
   const int N = d.N;
-  double* in = d.inst + b * I_ND;
-  const double alpha = in[I_ALPHA];
+  const double* in = d.inst + b * I_ND;
   const double* src = d.lsNode + static_cast<size_t>(b) * (N + 1) * 4;
   double a0 = 0, a1 = 0, a2 = 0;
   for (int k = threadIdx.x; k <= N; k += blockDim.x) {
@@ -433,37 +434,57 @@ __global__ void __launch_bounds__(256) accept_kernel(WbDev d) {
   a2 = blockSum(a2, sh);
   x0d = blockSum(x0d, sh);
   const b200sqp_settings& st = d.st;
+  TrialEval t;
+  t.cost = a0;
+  t.dyn = a1 + x0d;
+  t.eq = a2;
+  t.merit = a0;
+  const double g0 = sqrt(in[I_BASE_DYN] + in[I_BASE_EQ]);
+  t.g1 = sqrt(t.dyn + t.eq);
+  const double arm = alpha * in[I_ARMIJO];
+  if (d.flags[b * F_NF + F_STATUS]) {  // QP failure: never accept
+    t.acc = false;
+    t.type = 0;
+  } else if (t.g1 > st.g_max) {
+    t.acc = t.g1 < (1.0 - st.gamma_c) * g0;
+    t.type = 1;  // CONSTRAINT
+  } else if (t.g1 < st.g_min && g0 < st.g_min && arm < 0.0) {
+    t.acc = t.merit < in[I_BASE_MERIT] + st.armijo_factor * arm;
+    t.type = 3;  // COST
+  } else {
+    t.acc = t.merit < in[I_BASE_MERIT] - st.gamma_c * g0 || t.g1 < (1.0 - st.gamma_c) * g0;
+    t.type = 2;  // DUAL
+  }
+  return t;
+}
+
+// FilterLinesearch::acceptStep + takeStep bookkeeping + checkConvergence for one instance (SqpSolver.cpp:484-602).
+// forced = 0: per-instance back-tracking (reference semantics); 1: take the current (globally chosen) alpha; 2: take a zero step.
+__global__ void __launch_bounds__(256) accept_kernel(WbDev d, int forced) {
+  const int b = blockIdx.x;
+  int* fl = d.flags + b * F_NF;
+  if (fl[F_CONVERGED] || fl[F_LSDONE]) return;
+  __shared__ double sh[256];
+  __shared__ int decision;  // 0 continue, 1 accepted, 2 give up (zero step)
+  const int N = d.N;
+  double* in = d.inst + b * I_ND;
+  const double alpha = in[I_ALPHA];
+  const TrialEval t = evalTrial(d, b, alpha, sh);
+  const b200sqp_settings& st = d.st;
   if (threadIdx.x == 0) {
-    const double cost = a0, dyn = a1 + x0d, eq = a2, merit = a0;
-    const double g0 = sqrt(in[I_BASE_DYN] + in[I_BASE_EQ]), g1 = sqrt(dyn + eq);
-    const double arm = alpha * in[I_ARMIJO];
-    bool acc;
-    int type;
-    if (fl[F_STATUS]) {  // QP failure: never accept
-      acc = false;
-      type = 0;
-    } else if (g1 > st.g_max) {
-      acc = g1 < (1.0 - st.gamma_c) * g0;
-      type = 1;  // CONSTRAINT
-    } else if (g1 < st.g_min && g0 < st.g_min && arm < 0.0) {
-      acc = merit < in[I_BASE_MERIT] + st.armijo_factor * arm;
-      type = 3;  // COST
-    } else {
-      acc = merit < in[I_BASE_MERIT] - st.gamma_c * g0 || g1 < (1.0 - st.gamma_c) * g0;
-      type = 2;  // DUAL
-    }
     int dec = 0;
-    if (acc) {
+    const bool take = (forced == 1) ? !fl[F_STATUS] : (forced == 2 ? false : t.acc);
+    if (take) {
       dec = 1;
       in[I_STEP] = alpha;
-      in[I_STEPTYPE] = type;
-      in[I_NEW_MERIT] = merit;
-      in[I_NEW_COST] = cost;
-      in[I_NEW_DYN] = dyn;
-      in[I_NEW_EQ] = eq;
+      in[I_STEPTYPE] = t.type;
+      in[I_NEW_MERIT] = t.merit;
+      in[I_NEW_COST] = t.cost;
+      in[I_NEW_DYN] = t.dyn;
+      in[I_NEW_EQ] = t.eq;
     } else {
       const double next = alpha * st.alpha_decay;
-      if (fl[F_STATUS] || (next * in[I_DXN] < st.delta_tol && next * in[I_DUN] < st.delta_tol) || !(next >= st.alpha_min)) {
+      if (forced || fl[F_STATUS] || (next * in[I_DXN] < st.delta_tol && next * in[I_DUN] < st.delta_tol) || !(next >= st.alpha_min)) {
         dec = 2;
         in[I_STEP] = 0.0;
         in[I_STEPTYPE] = 4;  // ZERO
@@ -522,6 +543,33 @@ __global__ void __launch_bounds__(256) accept_kernel(WbDev d) {
     fl[F_ITER] = iter + 1;
     fl[F_CONVCODE] = conv;
     if (conv) fl[F_CONVERGED] = 1;
+  }
+}
+
+// ---- global-step mode ------------------------------------------------------------------------------------------------
+// every active instance gets the same trial step size
+__global__ void __launch_bounds__(256) set_alpha_kernel(WbDev d, double alpha) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= d.B || d.flags[b * F_NF + F_CONVERGED]) return;
+  d.inst[b * I_ND + I_ALPHA] = alpha;
+  d.flags[b * F_NF + F_LSDONE] = 0;
+}
+// candidate j of the ladder: filter test of every active instance, no state change; statistics accumulated with atomics
+__global__ void __launch_bounds__(256) ladder_eval_kernel(WbDev d, int j) {
+  const int b = blockIdx.x;
+  const int* fl = d.flags + b * F_NF;
+  if (fl[F_CONVERGED] || fl[F_STATUS]) return;
+  __shared__ double sh[256];
+  const TrialEval t = evalTrial(d, b, d.inst[b * I_ND + I_ALPHA], sh);
+  if (threadIdx.x == 0) {
+    double* s = d.gstats + 4 * j;
+    if (t.acc) {
+      atomicAdd(s, 1.0);
+      atomicAdd(s + 1, t.merit);
+    }
+    // max of non-negative doubles = max of their bit patterns
+    atomicMax(reinterpret_cast<unsigned long long*>(s + 2), static_cast<unsigned long long>(__double_as_longlong(t.g1)));
+    atomicAdd(s + 3, 1.0);
   }
 }
 

@@ -53,6 +53,50 @@ class B200SqpSolver:
             _l.check(L.b200sqp_stage_doubles(self._h, C.c_int(0), C.byref(per)))
             self._raw_per = per.value
         self.batch = self.n_nodes = 0
+        self._gs_cb = None
+        self.global_step_log = []   # (chosen index, combined statistics) per SQP iteration of the last solves (global-step mode)
+
+    # -- global-step mode --------------------------------------------------------------------------------
+    def enable_global_step(self, quorum: float = 1.0):
+        """Register the cross-rank combiner of the global-step mode (settings.global_step must be 1).  The per-candidate statistics stay
+        in device memory; with an initialised torch.distributed process group they are combined with ONE all_gather (NCCL over NVLink),
+        and every rank picks the same candidate: the largest alpha accepted by >= quorum of all active instances."""
+        import torch
+        import torch.distributed as dist
+
+        solver = self
+
+        class _DevView:  # zero-copy view of the statistics the library keeps in device memory
+            def __init__(self, ptr, n):
+                self.__cuda_array_interface__ = {"shape": (n, 4), "typestr": "<f8", "data": (ptr, False), "version": 3}
+
+        def combine(_user, stats_ptr, n_alpha, _stream):
+            try:
+                t = torch.as_tensor(_DevView(stats_ptr, n_alpha), device="cuda")
+                if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+                    allr = torch.empty((dist.get_world_size(), n_alpha, 4), dtype=torch.float64, device=t.device)
+                    dist.all_gather_into_tensor(allr, t.contiguous())
+                    glob = torch.stack([allr[:, :, 0].sum(0), allr[:, :, 1].sum(0), allr[:, :, 2].amax(0), allr[:, :, 3].sum(0)], dim=1)
+                else:
+                    glob = t.clone()
+                g = glob.cpu().numpy()
+                ok = np.nonzero(g[:, 0] >= quorum * g[:, 3] - 1e-9)[0]
+                idx = int(ok[0]) if len(ok) and g[0, 3] > 0 else -1
+                solver.global_step_log.append((idx, g))
+                return idx
+            except Exception as e:  # never unwind through the C frame
+                print(f"b200sqp global-step combiner failed: {e!r}", flush=True)
+                return -1
+
+        CB = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p)
+        self._gs_cb = CB(combine)
+        _l.check(_l.lib().b200sqp_set_global_step_callback(self._h, self._gs_cb, None))
+
+    def global_ladder(self) -> np.ndarray:
+        a = np.zeros(32)
+        n = C.c_int32()
+        _l.check(_l.lib().b200sqp_global_ladder(self._h, _p(a), C.byref(n)))
+        return a[: n.value]
 
     def close(self):
         if self._h:
