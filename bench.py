@@ -128,16 +128,18 @@ def main():
     ap.add_argument("--gait", default="walk")
     ap.add_argument("--cpu-sample", type=int, default=0, help="instances in the CPU-baseline sample (0 = 2 x cores)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--sqp-iteration", type=int, default=1, help="sqpIteration (1 = the shipped real-time iteration; 10 = the secondary number)")
+    ap.add_argument("--global-step", action="store_true", help="one line-search step per iteration for the whole multi-GPU batch (NCCL)")
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     model = model_loader.load_packaged_model()
-    settings = abi.default_settings(model, sqp_iteration=1)
+    settings = abi.default_settings(model, sqp_iteration=args.sqp_iteration, global_step=int(args.global_step))
     cores = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
     n_int = int(round(args.horizon / model["sqp"]["dt"]))
-    workload = f"G1 whole-body MPC (nx=58, nu=35), dt=0.035 s x {n_int} intervals, gait={args.gait}, batch={args.batch}/GPU, sqpIteration=1, cold start"
+    workload = f"G1 whole-body MPC (nx=58, nu=35), dt=0.035 s x {n_int} intervals, gait={args.gait}, batch={args.batch}/GPU, sqpIteration={args.sqp_iteration}, cold start" + (", global line-search step" if args.global_step else "")
 
     if args.impl == "reference":
         # the reference's own CPU implementation of the path cannot be built here (no Eigen/Pinocchio/HPIPM): the arm
@@ -180,6 +182,8 @@ def main():
     batch = stack_instances(insts)
     n_nodes = batch["t_nodes"].shape[1]
     solver = B200SqpSolver(model, settings, device=local_rank)
+    if args.global_step:
+        solver.enable_global_step()
 
     # pinned host staging buffers for the end-to-end path
     def pin(a):
@@ -250,44 +254,66 @@ def main():
     value = total_solves / dev_s
     e2e = total_solves / e2e_s
 
-    # ---- roofline of the dominant kernel -------------------------------------------------------------------------------------------
+    # ---- per-kernel roofline -------------------------------------------------------------------------------------------
+    # Device ms per stage are CUDA events recorded by the library on the launching stream (b200sqp_get_stage_times): ms[0] = K1a + K1b,
+    # ms[3] = K1b alone, ms[1] = K2 (+ remap), ms[2] = the line search = n_ls x (K3 + accept).
     stage_ms = stage_acc / args.steps
-    names = ["lq_kernel (K1)", "riccati_kernel (K2)", "rollout_kernel (K3)"]
-    dom = int(np.argmax(stage_ms[:3]))
     N = n_nodes - 1
     nut = 23
-    # algorithmic bytes per launch: projected stage record out of K1 / into K2, plus the per-node inputs and solution
-    rec = 8 * (58 * 58 + 58 * nut + 58 + 58 * 58 + nut * 58 + nut * nut + 58 + nut)            # A B b Q S R q r
-    proj = 8 * (35 * nut + 35 * 58 + 35)                                                    # Pu Px u0
-    node_in = 8 * (58 + 35 + 58 + 58 + 6 + 2 + 1 + 1) + 3
-    alg = {0: B * N * (rec + proj + node_in), 1: B * N * (rec + 8 * (nut * 58 + nut + 58 + nut)), 2: B * N * (8 * (3 * 58 + 35 + 58 + 35) + 32)}
+    n_ls = max(1.0, (launches / args.steps - 8 - (1 if settings.create_value_function else 0)) / 2.0)   # K3 launches per solve
+    k_ms = {"lq_dyn_kernel (K1a)": stage_ms[0] - stage_ms[3], "lq_proj_kernel (K1b)": stage_ms[3], "riccati_kernel (K2)": stage_ms[1],
+            "rollout_kernel (K3)": stage_ms[2] / n_ls}
+    k_share = {"lq_dyn_kernel (K1a)": k_ms["lq_dyn_kernel (K1a)"], "lq_proj_kernel (K1b)": stage_ms[3], "riccati_kernel (K2)": stage_ms[1],
+               "rollout_kernel (K3)": stage_ms[2]}
+    # algorithmic bytes per launch: what each kernel must read + write given the kernel split (doubles x 8)
+    rec = 8 * (58 * 58 + 58 * nut + 58 + 58 * 58 + nut * 58 + nut * nut + 58 + nut)            # projected stage record A B b Q S R q r
+    proj = 8 * (35 * nut + 35 * 58 + 35)                                                    # Pu Px u0 (read by the remap)
+    node_in = 8 * (58 + 35 + 58 + 58 + 6 + 2 + 1 + 1) + 3                                   # x u x+ xref swing impact arm t, flags
+    swing_rows = 15.0 * float((1 - batch["contact_flags"][:, :-1, :].astype(np.float64)).sum()) / (B * N)   # mean dense cost rows / node
+    mid = 8 * (12 * 93 + 58 + 14 * 93 + 14 + 93 + 93 + 18 + 24 * 27 + 6 + swing_rows * 93)   # K1a -> K1b record (struct Mid)
+    alg = {"lq_dyn_kernel (K1a)": B * N * (node_in + mid), "lq_proj_kernel (K1b)": B * N * (mid + rec + proj),
+           "riccati_kernel (K2)": B * N * (rec + 8 * (nut * 58 + nut + 58 + nut)), "rollout_kernel (K3)": B * N * (8 * (3 * 58 + 35 + 58 + 35) + 32)}
     peaks = {}
     try:
         peaks = json.loads((ROOT / "MEASURED_PEAKS.json").read_text())
     except Exception:
         pass
     peak = peaks.get("hbm_gbs", 6650.0)
-    achieved = alg[dom] / (stage_ms[dom] * 1e-3) / 1e9
-    # measured DRAM traffic of the same kernel from the latest committed `ncu --set full` capture (taken at batch 64), scaled per stage
-    traffic = None
-    try:
-        short = ["lq", "ric", "ro"][dom]
-        raws = sorted((ROOT / "profiles").glob(f"ncu_{short}_*_raw.json"))
-        if raws:
+    fp64_peak = 40.0   # TFLOP/s, nominal B200 fp64 (vector and DMMA); MEASURED_PEAKS.json carries bf16 only
+    short = {"lq_dyn_kernel (K1a)": "lqa", "lq_proj_kernel (K1b)": "lqb", "riccati_kernel (K2)": "ric", "rollout_kernel (K3)": "ro"}
+    kernels = {}
+    for name, ms in k_ms.items():
+        e = {"ms_per_launch": ms, "ms_per_step": k_share[name], "algorithmic_bytes_per_launch": alg[name],
+             "hbm_gbs": alg[name] / (ms * 1e-3) / 1e9, "hbm_frac": alg[name] / (ms * 1e-3) / 1e9 / peak}
+        try:   # counters of the latest committed `ncu --set full` capture of this kernel (taken at batch 64), scaled to this launch
+            raws = sorted((ROOT / "profiles").glob(f"ncu_{short[name]}_*_raw.json"))
             raw = json.loads(raws[-1].read_text())
-            per_stage = (float(raw["dram__bytes_read.sum"]) + float(raw["dram__bytes_write.sum"])) * 1e6 / (64 * N)
-            traffic = per_stage * B * N
-    except Exception:
-        traffic = None
-    roofline = {"kernel": names[dom], "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "traffic": traffic, "peak_source": "MEASURED_PEAKS.json (measured)" if peaks else "fallback 6.65 TB/s",
-                "algorithmic_bytes_per_launch": alg[dom], "stage_ms": {"lq": stage_ms[0], "qp": stage_ms[1], "linesearch": stage_ms[2]},
-                "note": "fp64-pipe bound, not HBM bound: see DESIGN.md; the per-stage device times are CUDA events on the launching stream"}
+            scale = B / 64.0
+            e["ncu_capture"] = raws[-1].name
+            e["traffic"] = (float(raw["dram_bytes_read_B"]) + float(raw["dram_bytes_write_B"])) * scale
+            tflop = float(raw.get("sm__ops_path_tensor_src_fp64.sum", 0.0)) * scale
+            e["dmma_tflops"] = tflop / (ms * 1e-3) / 1e12
+            e["dmma_frac_of_nominal_fp64"] = e["dmma_tflops"] / fp64_peak
+            e["ncu_pipe_pct"] = {"fp64": float(raw["sm__pipe_fp64_cycles_active.avg.pct_of_peak_sustained_active"]),
+                                 "dmma": float(raw["sm__pipe_tensor_subpipe_dmma_cycles_active.avg.pct_of_peak_sustained_active"])}
+        except Exception:
+            e["traffic"] = None
+        kernels[name] = e
+    dom = max(k_share, key=k_share.get)
+    kd = kernels[dom]
+    roofline = {"kernel": dom, "bound": "hbm", "achieved": kd["hbm_gbs"], "peak": peak, "unit": "GB/s", "frac": kd["hbm_frac"],
+                "traffic": kd.get("traffic"), "peak_source": "MEASURED_PEAKS.json (measured)" if peaks else "fallback 6.65 TB/s",
+                "algorithmic_bytes_per_launch": kd["algorithmic_bytes_per_launch"],
+                "stage_ms": {"lq": stage_ms[0], "lq_projection_share": stage_ms[3], "qp": stage_ms[1], "linesearch": stage_ms[2]},
+                "kernels": kernels, "fp64_peak_tflops_nominal": fp64_peak,
+                "note": "north_star asks for the HBM fraction; none of the kernels is HBM bound (DESIGN.md §6): K2's contractions run at the "
+                        "DMMA rate shown, K1a/K1b/K3 are barrier/latency bound.  Times are CUDA events on the launching stream."}
+    rec_gb = B * N * (rec + proj + mid) / 1e9
 
     line = {"metric": METRIC, "value": value, "unit": "solves/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": 1e3 * dev_s / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
             "data": "synthetic",
-            "config": {"workload": workload, "n_nodes": int(n_nodes), "batch_per_gpu": args.batch, "l2": "stage blocks (%.1f GB/GPU) exceed the 126 MB L2; no flush needed" % (B * N * (rec + proj) / 1e9),
+            "config": {"workload": workload, "n_nodes": int(n_nodes), "batch_per_gpu": args.batch, "l2": "stage records (%.1f GB/GPU) exceed the 126 MB L2; no flush needed" % rec_gb,
                        "accepted_step_sizes": {str(a): int((alphas == a).sum()) for a in np.unique(alphas)}},
             "e2e": {"value": e2e, "unit": "solves/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h)},
             "gpu_launches": int(launches), "roofline": roofline, "clocks": clocks}

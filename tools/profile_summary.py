@@ -59,7 +59,18 @@ for short, name in kernels:
             vals[n] = v[i]
             out.append(f"| {n} | {units[i]} | {v[i]} |")
     out.append("")
-    (PR / f"ncu_{short}_{tag}_raw.json").write_text(json.dumps({n: v[i] for i, n in enumerate(h)}, indent=0))
+    rawd = {n: v[i] for i, n in enumerate(h)}
+    # unit-normalised copies of the byte counters (ncu picks Kbyte / Mbyte / Gbyte per value)
+    mult = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9, "Tbyte": 1e12}
+    for n in ("dram__bytes_read.sum", "dram__bytes_write.sum"):
+        if n in h:
+            i = h.index(n)
+            rawd[n.replace("__bytes_", "_bytes_").replace(".sum", "") + "_B"] = float(v[i].replace(",", "")) * mult.get(units[i], 1.0)
+    tmult = {"ns": 1e-6, "us": 1e-3, "ms": 1.0, "s": 1e3}
+    if "gpu__time_duration.sum" in h:
+        i = h.index("gpu__time_duration.sum")
+        rawd["gpu_time_ms"] = float(v[i].replace(",", "")) * tmult.get(units[i], 1.0)
+    (PR / f"ncu_{short}_{tag}_raw.json").write_text(json.dumps(rawd, indent=0))
 bench = GO / f"bench_{tag}.json"
 if bench.exists():
     line = bench.read_text().strip().splitlines()[-1]
