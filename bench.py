@@ -44,6 +44,7 @@ def build_batch(model, batch, rank, horizon, gaits):
         x0[6 + nj:] += rng.uniform(-0.2, 0.2, 6 + nj)
         cmd = [rng.uniform(-0.5, 1.0), rng.uniform(-0.3, 0.3), model["reference"]["defaultBaseHeight"], rng.uniform(-0.5, 0.5)]
         insts.append(references.build_instance(model, x0, t0=0.0, horizon=horizon, gait=gaits[i % len(gaits)], cmd=cmd))
+        insts[-1]["cmd"], insts[-1]["gait"] = cmd, gaits[i % len(gaits)]
     return insts
 
 
@@ -254,6 +255,36 @@ def main():
     value = total_solves / dev_s
     e2e = total_solves / e2e_s
 
+    # ---- the same through the C++ host layer (b200sqp::host::SqpSolver::run, the mirror of ocs2::SqpSolver::run): per-instance reference
+    # managers, time grids and cold-start initial guesses are built on host threads inside the timed region, then upload + solve + download
+    host_api = None
+    try:
+        from wb_humanoid_mpc_b200 import host_lib
+
+        hm = host_lib.HostModel()
+        hs = host_lib.HostSqpSolver(hm, settings, args.batch, device=local_rank)
+        x0s = np.array([i["x0"] for i in insts])
+        for b, i in enumerate(insts):
+            hs.set_gait(b, i["gait"], 0.0, 3 * args.horizon)
+            hs.set_command(b, 0.0, i["x0"], i["cmd"], args.horizon)
+        for _ in range(min(args.warmup, 2)):
+            hs.reset()
+            hs.run(0.0, x0s, args.horizon)
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            hs.reset()   # cold start every step, like the other legs
+            hs.run(0.0, x0s, args.horizon)
+        host_s = max_over_ranks(time.perf_counter() - t0)
+        barrier()
+        dx = max(float(np.abs(hs.primal_solution(b)["x"] - sol["x"][b]).max()) for b in range(0, args.batch, max(1, args.batch // 8)))
+        host_api = {"value": total_solves / host_s, "unit": "solves/s", "call": "b200sqp::host::SqpSolver::run (C++ host layer, instances built on host threads)",
+                    "max_abs_diff_x_vs_c_abi_path": dx}
+        hs.close()
+        hm.close()
+    except Exception as e:   # the host layer is optional for the bench line
+        host_api = {"unavailable": repr(e)}
+
     # ---- per-kernel roofline -------------------------------------------------------------------------------------------
     # Device ms per stage are CUDA events recorded by the library on the launching stream (b200sqp_get_stage_times): ms[0] = K1a + K1b,
     # ms[3] = K1b alone, ms[1] = K2 (+ remap), ms[2] = the line search = n_ls x (K3 + accept).
@@ -315,7 +346,7 @@ def main():
             "data": "synthetic",
             "config": {"workload": workload, "n_nodes": int(n_nodes), "batch_per_gpu": args.batch, "l2": "stage records (%.1f GB/GPU) exceed the 126 MB L2; no flush needed" % rec_gb,
                        "accepted_step_sizes": {str(a): int((alphas == a).sum()) for a in np.unique(alphas)}},
-            "e2e": {"value": e2e, "unit": "solves/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h)},
+            "e2e": {"value": e2e, "unit": "solves/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h), "host_api": host_api},
             "gpu_launches": int(launches), "roofline": roofline, "clocks": clocks}
 
     if rank == 0 and world == 1 and not args.no_cpu_baseline:

@@ -1,0 +1,68 @@
+"""b200sqp::host::SqpSolver (C++ mirror of ocs2::SqpSolver over the C ABI) against the Python harness: same instances -> same primal
+(the two instance builders agree to 1e-13, not bitwise, so the solutions agree to solver conditioning: 1e-9 on x)
+solution, iteration log and warm-started second solve; mixed gaits exercise the grouping by node count."""
+import numpy as np
+import pytest
+
+from wb_humanoid_mpc_b200 import abi, host_lib, model_loader, references
+
+pytestmark = pytest.mark.gpu
+
+
+def test_host_solver_matches_python_harness_cold_and_warm():
+    from wb_humanoid_mpc_b200.solver import LOG_FIELDS, B200SqpSolver
+
+    model = model_loader.load_packaged_model()
+    hm = host_lib.HostModel()
+    rng = np.random.default_rng(3)
+    B, horizon = 5, 1.1
+    gaits = ["walk", "stance", "walk", "trot", "stance"]
+    cmds = [[rng.uniform(-0.3, 0.8), rng.uniform(-0.2, 0.2), model["reference"]["defaultBaseHeight"], rng.uniform(-0.3, 0.3)] for _ in range(B)]
+    x0s = []
+    for _ in range(B):
+        x0 = np.array(model["x_init"], float)
+        x0[2] = model["reference"]["defaultBaseHeight"]
+        x0[3:6] += rng.uniform(-0.05, 0.05, 3)
+        x0[6:29] += rng.uniform(-0.05, 0.05, 23)
+        x0s.append(x0)
+    st = abi.default_settings(model, sqp_iteration=2)
+    host = host_lib.HostSqpSolver(hm, st, B)
+    for b in range(B):
+        host.set_gait(b, gaits[b], 0.0, 3 * horizon)
+        host.set_command(b, 0.0, x0s[b], cmds[b], horizon)
+    host.run(0.0, np.array(x0s), horizon)
+
+    prev = []
+    for b in range(B):
+        inst = references.build_instance(model, x0s[b], t0=0.0, horizon=horizon, gait=gaits[b], cmd=cmds[b])
+        py = B200SqpSolver(model, st)
+        r = py.run([inst])
+        p = host.primal_solution(b)
+        assert np.array_equal(p["t"], inst["t_nodes"])
+        dx = float(np.abs(p["x"] - r["x"][0]).max())
+        print("instance", b, gaits[b], "max |dx| host vs python", dx)
+        assert dx < 1e-6, (b, dx)
+        ref_u = references.to_primal_solution(inst["t_nodes"], inst["node_event"], r["x"][0], r["u"][0])["u"]
+        assert np.allclose(p["u"], ref_u, rtol=0, atol=1e-4 * max(1.0, np.abs(ref_u).max())), float(np.abs(p["u"] - ref_u).max())
+        lg = host.iterations_log(b)
+        assert lg.shape[0] == r["n_iter"][0]
+        assert np.allclose(lg[:, 6], r["log"][0, : lg.shape[0], LOG_FIELDS.index("step_size")])
+        assert np.allclose(lg[:, 3], r["log"][0, : lg.shape[0], LOG_FIELDS.index("merit")], rtol=1e-7)
+        prev.append((py, references.to_primal_solution(inst["t_nodes"], inst["node_event"], r["x"][0], r["u"][0])))
+    assert host.benchmarks()[0] > 0.0
+
+    # receding horizon: second solve 3 nodes later, warm-started from the previous primal solution on both sides
+    t1 = 3 * model["sqp"]["dt"]
+    x1s = [prev[b][1]["x"][3] for b in range(B)]
+    for b in range(B):
+        host.set_command(b, t1, x1s[b], cmds[b], horizon)
+    host.run(t1, np.array(x1s), t1 + horizon)
+    for b in range(B):
+        inst = references.build_instance(model, x1s[b], t0=t1, horizon=horizon, gait=gaits[b], gait_start=0.0, cmd=cmds[b], previous=prev[b][1])
+        r = prev[b][0].run([inst])
+        p = host.primal_solution(b)
+        dx = float(np.abs(p["x"] - r["x"][0]).max())
+        print("warm instance", b, "max |dx|", dx)
+        assert dx < 1e-6, (b, dx)
+    host.close()
+    hm.close()

@@ -5,7 +5,7 @@ import sys
 from pathlib import Path
 
 sys.path.insert(0, str(Path(__file__).resolve().parents[1]))
-from wb_humanoid_mpc_b200.model_loader import DATA_DIR, build_g1_wb_from_reference  # noqa: E402
+from wb_humanoid_mpc_b200.model_loader import DATA_DIR, build_g1_wb_from_reference, write_flat  # noqa: E402
 
 if __name__ == "__main__":
     root = sys.argv[1] if len(sys.argv) > 1 else "/root/reference"
@@ -13,4 +13,5 @@ if __name__ == "__main__":
     DATA_DIR.mkdir(exist_ok=True)
     out = DATA_DIR / "g1_wb_model.json"
     out.write_text(json.dumps(m, indent=1))
+    write_flat(m, DATA_DIR / "g1_wb_model.txt")   # the same data for the C++ host layer
     print("wrote", out, "total mass", sum(m["mass"]))

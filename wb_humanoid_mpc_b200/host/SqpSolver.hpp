@@ -1,0 +1,246 @@
+// Host layer: the reference's solver interface (ocs2::SqpSolver, lib/ocs2_ros2/ocs2_sqp/ocs2_sqp/include/ocs2_sqp/SqpSolver.h:60-103 and
+// SolverBase.h:78-140) for a BATCH of independent humanoid whole-body MPC instances, implemented over the C ABI of libb200sqp.so.
+//
+//   SqpSolver(settings, optimalControlProblem, initializer)   ->  SqpSolver(model, settings, batch, device)
+//   reset()                                                   ->  reset()                 drops every instance's primal solution
+//   run(initTime, initState, finalTime)                       ->  run(initTime, initStates[B], finalTime)
+//   getReferenceManager()                                     ->  getReferenceManager(b)  per-instance gait / target trajectories
+//   getPrimalSolution(finalTime, PrimalSolution*)             ->  primalSolution(b)
+//   getPerformanceIndeces() / getIterationsLog()              ->  getIterationsLog(b)
+//   getNumIterations()                                        ->  getNumIterations(b)
+//   getBenchmarks()                                           ->  getBenchmarks()
+//   getValueFunction(t, x)                                    ->  getValueFunction(b, t, x)   (settings.create_value_function)
+//   getHamiltonian / getStateInputEqualityConstraintLagrangian / getIntermediateDualSolution throw, as in the reference (SqpSolver.h:82-92)
+// Errors are C++ exceptions as in the reference: std::runtime_error on a failed QP or a failing library call (SqpSolver.cpp:166,306-308).
+//
+// Instances whose time grids have different numbers of shooting nodes (different gait phases put different numbers of event nodes inside
+// the horizon) are grouped by node count; each group owns one library handle and is solved with one b200sqp_solve.
+// The per-instance host work (reference manager, time grid, warm start) runs on a pool of std::threads.
+#pragma once
+#include <map>
+#include <memory>
+#include <thread>
+
+#include "references.hpp"
+
+namespace b200sqp::host {
+
+struct PerformanceIndex {  // ocs2_oc/include/ocs2_oc/oc_data/PerformanceIndex.h:42-98 (the fields the SQP path fills)
+  double merit = 0, cost = 0, dynamicsViolationSSE = 0, equalityConstraintsSSE = 0;
+};
+struct StepInfo {  // sqp::StepInfo (SqpSolverStatus.h:42-57)
+  double stepSize = 0;
+  int stepType = 0;  // FilterLinesearch::StepType: 0 UNKNOWN 1 CONSTRAINT 2 DUAL 3 COST 4 ZERO
+  double dx_norm = 0, du_norm = 0, armijoDescentMetric = 0;
+  PerformanceIndex baseline, performanceAfterStep;
+  int convergence = 0;  // sqp::Convergence: 0 FALSE 1 ITERATIONS 2 STEPSIZE 3 METRICS 4 PRIMAL
+};
+struct Benchmarks {  // SqpSolver::getBenchmarks (ms of the last run, summed over node-count groups)
+  double linearQuadraticApproximation = 0, solveQp = 0, linesearch = 0, projectionShareOfLq = 0;
+};
+struct ValueFunction {  // ScalarFunctionQuadraticApproximation of getValueFunction: dfdxx (nx*nx, column-major), dfdx
+  vector_t dfdxx, dfdx;
+};
+
+class SqpSolver {
+ public:
+  SqpSolver(const HostModel& model, const b200sqp_settings& settings, int batch, int device = 0, int hostThreads = 0)
+      : model_(model), settings_(settings), device_(device), batch_(batch) {
+    if (batch < 1) throw std::invalid_argument("[b200sqp::host::SqpSolver] batch must be >= 1");
+    for (int b = 0; b < batch; ++b) rm_.emplace_back(model_);
+    primal_.resize(batch);
+    log_.resize(batch);
+    groupOf_.assign(batch, -1);
+    slotOf_.assign(batch, -1);
+    const unsigned hw = std::thread::hardware_concurrency();
+    threads_ = hostThreads > 0 ? hostThreads : static_cast<int>(std::max(1u, std::min(hw ? hw : 1u, 64u)));
+  }
+  ~SqpSolver() {
+    for (auto& g : groups_)
+      if (g.second.h) b200sqp_destroy(g.second.h);
+  }
+  SqpSolver(const SqpSolver&) = delete;
+  SqpSolver& operator=(const SqpSolver&) = delete;
+
+  int batch() const { return batch_; }
+  SwitchedModelReferenceManager& getReferenceManager(int b) { return rm_.at(b); }
+
+  void reset() {  // SqpSolver::reset (SqpSolver.cpp:96-106): forget the previous solutions -> the next run is a cold start
+    for (auto& p : primal_) p.clear();
+    for (auto& l : log_) l.clear();
+  }
+
+  // SolverBase::run(initTime, initState, finalTime) for all instances: preRun (reference managers), runImpl on the GPU, postRun bookkeeping
+  void run(double initTime, const std::vector<vector_t>& initStates, double finalTime) {
+    if (static_cast<int>(initStates.size()) != batch_) throw std::invalid_argument("[b200sqp::host::SqpSolver] run: one initial state per instance");
+    std::vector<Instance> inst(batch_);
+    parallelFor(batch_, [&](int b) {
+      rm_[b].preSolverRun(initTime, finalTime);
+      const PrimalSolution* prev = primal_[b].timeTrajectory_.empty() ? nullptr : &primal_[b];
+      inst[b] = buildInstance(model_, rm_[b], initTime, initStates[b], finalTime, model_.dt, prev);
+    });
+    // group by node count
+    std::map<int, std::vector<int>> members;
+    for (int b = 0; b < batch_; ++b) members[inst[b].n_nodes()].push_back(b);
+    bench_ = Benchmarks();
+    for (auto& kv : members) solveGroup(kv.first, kv.second, inst);
+  }
+
+  const PrimalSolution& primalSolution(int b) const { return primal_.at(b); }
+  const std::vector<StepInfo>& getIterationsLog(int b) const {
+    if (log_.at(b).empty()) throw std::runtime_error("[SqpSolver]: No performance log yet, no problem solved yet?");  // SqpSolver.cpp:174
+    return log_[b];
+  }
+  size_t getNumIterations(int b) const { return log_.at(b).size(); }
+  Benchmarks getBenchmarks() const { return bench_; }
+
+  // getValueFunction(time, state) (SqpSolver.cpp:172-191): P, p interpolated in time, then re-centred at `state`
+  ValueFunction getValueFunction(int b, double time, const vector_t& state) const {
+    if (!settings_.create_value_function) throw std::runtime_error("[SqpSolver] createValueFunction is false");
+    const int g = groupOf_.at(b);
+    if (g < 0) throw std::runtime_error("[SqpSolver] getValueFunction: no problem solved yet");
+    const Group& G = groups_.at(g);
+    const int nx = model_.nx, n = G.nNodes, s = slotOf_[b];
+    const vector_t& tt = primal_[b].timeTrajectory_;
+    // LinearInterpolation over the node times
+    const int index = static_cast<int>(lowerBoundIndex(tt, time)) - 1, last = n - 1;
+    int idx = 0;
+    double alpha = 1.0;
+    if (index >= 0 && index < last) {
+      const double len = tt[index + 1] - tt[index], till = tt[index + 1] - time;
+      idx = index;
+      alpha = len > 2.0 * kWeakEps ? till / len : (till < 0.5 * len ? 0.0 : 1.0);
+    } else if (index >= last) {
+      idx = std::max(last - 1, 0);
+      alpha = 0.0;
+    }
+    ValueFunction v;
+    v.dfdxx.resize(static_cast<size_t>(nx) * nx);
+    v.dfdx.resize(nx);
+    const double* P0 = G.P.data() + (static_cast<size_t>(s) * n + idx) * nx * nx;
+    const double* p0 = G.p.data() + (static_cast<size_t>(s) * n + idx) * nx;
+    for (int i = 0; i < nx * nx; ++i) v.dfdxx[i] = alpha * P0[i] + (1 - alpha) * P0[i + nx * nx];
+    for (int i = 0; i < nx; ++i) v.dfdx[i] = alpha * p0[i] + (1 - alpha) * p0[i + nx];
+    for (int i = 0; i < nx; ++i)
+      for (int j = 0; j < nx; ++j) v.dfdx[i] += v.dfdxx[i + nx * j] * state[j];   // dfdx += dfdxx * x
+    return v;
+  }
+  [[noreturn]] void getHamiltonian() const { throw std::runtime_error("[SqpSolver] getHamiltonian() not available yet."); }
+  [[noreturn]] void getStateInputEqualityConstraintLagrangian() const {
+    throw std::runtime_error("[SqpSolver] getStateInputEqualityConstraintLagrangian() not available yet.");
+  }
+  [[noreturn]] void getIntermediateDualSolution() const { throw std::runtime_error("[SqpSolver] getIntermediateDualSolution() not available yet."); }
+
+ private:
+  struct Group {
+    b200sqp_handle h = nullptr;
+    int nNodes = 0, capacity = 0;
+    vector_t P, p;
+  };
+  static void check(int rc) {
+    if (rc != 0) throw std::runtime_error(std::string("[SqpSolver] ") + b200sqp_last_error());
+  }
+  template <class F>
+  void parallelFor(int n, F f) {
+    const int nt = std::min(threads_, n);
+    if (nt <= 1) {
+      for (int i = 0; i < n; ++i) f(i);
+      return;
+    }
+    std::vector<std::thread> pool;
+    std::vector<std::exception_ptr> err(nt);
+    for (int t = 0; t < nt; ++t)
+      pool.emplace_back([&, t] {
+        try {
+          for (int i = t; i < n; i += nt) f(i);
+        } catch (...) {
+          err[t] = std::current_exception();
+        }
+      });
+    for (auto& th : pool) th.join();
+    for (auto& e : err)
+      if (e) std::rethrow_exception(e);
+  }
+
+  void solveGroup(int nNodes, const std::vector<int>& members, const std::vector<Instance>& inst) {
+    Group& G = groups_[nNodes];
+    const int Bg = static_cast<int>(members.size()), nx = model_.nx, nu = model_.nu, n = nNodes;
+    if (!G.h) check(b200sqp_create(&model_.desc, &settings_, device_, &G.h));
+    if (G.capacity != Bg || G.nNodes != n) {
+      check(b200sqp_set_batch(G.h, Bg, n));
+      G.capacity = Bg;
+      G.nNodes = n;
+    }
+    // pack (host staging; the C ABI copies from plain host pointers)
+    vector_t x0(static_cast<size_t>(Bg) * nx), xi(static_cast<size_t>(Bg) * n * nx), ui(static_cast<size_t>(Bg) * (n - 1) * nu),
+        tn(static_cast<size_t>(Bg) * n), sw(static_cast<size_t>(Bg) * n * 6), imp(static_cast<size_t>(Bg) * n * 2), arm(static_cast<size_t>(Bg) * n),
+        xr(static_cast<size_t>(Bg) * n * nx);
+    std::vector<uint8_t> ev(static_cast<size_t>(Bg) * n), cf(static_cast<size_t>(Bg) * n * 2);
+    parallelFor(Bg, [&](int s) {
+      const Instance& I = inst[members[s]];
+      std::copy(I.x0.begin(), I.x0.end(), x0.begin() + static_cast<size_t>(s) * nx);
+      std::copy(I.x_init.begin(), I.x_init.end(), xi.begin() + static_cast<size_t>(s) * n * nx);
+      std::copy(I.u_init.begin(), I.u_init.end(), ui.begin() + static_cast<size_t>(s) * (n - 1) * nu);
+      std::copy(I.t_nodes.begin(), I.t_nodes.end(), tn.begin() + static_cast<size_t>(s) * n);
+      std::copy(I.node_event.begin(), I.node_event.end(), ev.begin() + static_cast<size_t>(s) * n);
+      std::copy(I.contact_flags.begin(), I.contact_flags.end(), cf.begin() + static_cast<size_t>(s) * n * 2);
+      std::copy(I.swing_ref.begin(), I.swing_ref.end(), sw.begin() + static_cast<size_t>(s) * n * 6);
+      std::copy(I.impact_factor.begin(), I.impact_factor.end(), imp.begin() + static_cast<size_t>(s) * n * 2);
+      std::copy(I.arm_phase.begin(), I.arm_phase.end(), arm.begin() + static_cast<size_t>(s) * n);
+      std::copy(I.x_ref.begin(), I.x_ref.end(), xr.begin() + static_cast<size_t>(s) * n * nx);
+    });
+    check(b200sqp_upload_instances(G.h, x0.data(), xi.data(), ui.data(), tn.data(), ev.data(), cf.data(), sw.data(), imp.data(), arm.data(), xr.data()));
+    check(b200sqp_solve(G.h, nullptr));
+    vector_t x(static_cast<size_t>(Bg) * n * nx), u(static_cast<size_t>(Bg) * (n - 1) * nu);
+    const int iters = settings_.sqp_iteration;
+    std::vector<b200sqp_iter_log> log(static_cast<size_t>(Bg) * iters);
+    std::vector<int32_t> nIter(Bg), status(Bg);
+    check(b200sqp_download(G.h, x.data(), u.data(), nullptr, log.data(), nIter.data(), status.data()));
+    if (settings_.create_value_function) {
+      G.P.resize(static_cast<size_t>(Bg) * n * nx * nx);
+      G.p.resize(static_cast<size_t>(Bg) * n * nx);
+      check(b200sqp_download_value_function(G.h, G.P.data(), G.p.data()));
+    }
+    float ms[4];
+    check(b200sqp_get_stage_times(G.h, ms));
+    bench_.linearQuadraticApproximation += ms[0];
+    bench_.solveQp += ms[1];
+    bench_.linesearch += ms[2];
+    bench_.projectionShareOfLq += ms[3];
+    for (int s = 0; s < Bg; ++s)
+      if (status[s] != 0) throw std::runtime_error("[SqpSolver] Failed to solve QP");  // SqpSolver.cpp:306-308
+    const int gid = nNodes;
+    parallelFor(Bg, [&](int s) {
+      const int b = members[s];
+      groupOf_[b] = gid;
+      slotOf_[b] = s;
+      primal_[b] = toPrimalSolution(inst[b], x.data() + static_cast<size_t>(s) * n * nx, u.data() + static_cast<size_t>(s) * (n - 1) * nu, nx, nu);
+      log_[b].clear();
+      for (int it = 0; it < nIter[s]; ++it) {
+        const b200sqp_iter_log& L = log[static_cast<size_t>(s) * iters + it];
+        StepInfo si;
+        si.stepSize = L.step_size;
+        si.stepType = static_cast<int>(L.step_type);
+        si.dx_norm = L.dx_norm;
+        si.du_norm = L.du_norm;
+        si.armijoDescentMetric = L.armijo;
+        si.baseline = PerformanceIndex{L.base_merit, L.base_cost, L.base_dyn_sse, L.base_eq_sse};
+        si.performanceAfterStep = PerformanceIndex{L.merit, L.cost, L.dyn_sse, L.eq_sse};
+        si.convergence = static_cast<int>(L.convergence);
+        log_[b].push_back(si);
+      }
+    });
+  }
+
+  HostModel model_;
+  b200sqp_settings settings_;
+  int device_, batch_, threads_ = 1;
+  std::vector<SwitchedModelReferenceManager> rm_;
+  std::vector<PrimalSolution> primal_;
+  std::vector<std::vector<StepInfo>> log_;
+  std::map<int, Group> groups_;
+  std::vector<int> groupOf_, slotOf_;
+  Benchmarks bench_;
+};
+
+}  // namespace b200sqp::host

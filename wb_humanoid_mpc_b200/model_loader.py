@@ -428,3 +428,41 @@ if __name__ == "__main__":
     m = build_g1_wb_from_reference(sys.argv[1] if len(sys.argv) > 1 else "/root/reference")
     print(json.dumps({k: m[k] for k in ("nj", "nx", "nu", "joint_names", "parent")}, indent=1))
     print("total mass", sum(m["mass"]))
+
+
+def write_flat(model: dict, path) -> None:
+    """Flat text form of the model dictionary for the C++ host layer (host/model_file.hpp): one `key count values...` record per line,
+    numbers with 17 significant digits (round-trip exact); gaits as `gait <name> <n> <modes...> <n+1 switching times>`."""
+    import numpy as np
+
+    def rec(key, vals):
+        v = np.asarray(vals, dtype=float).reshape(-1)
+        return f"{key} {len(v)} " + " ".join(repr(float(x)) for x in v)
+
+    L = [f"name 1 {model['name']}"]
+    for k in ("nj", "nx", "nu", "gravity"):
+        L.append(rec(k, [model[k]]))
+    for k in ("parent", "joint_R", "joint_p", "joint_axis", "mass", "com", "inertia", "q_lower", "q_upper", "frame_body", "frame_p", "contact_rect",
+              "Q_diag", "R_diag", "Qf_diag", "x_init", "foot_cost_weights", "arm_swing_joints"):
+        L.append(rec(k, model[k]))
+    g = model["foot_gains"]
+    L.append(rec("foot_gains", [g[k] for k in ("pos_z", "ori", "linvel_z", "linvel_xy", "angvel", "linacc_z", "linacc_xy", "angacc")]))
+    f = model["friction"]
+    L.append(rec("friction", [f[k] for k in ("mu_fric", "mu", "delta", "regularization", "hessian_shift")]))
+    L.append(rec("moment_xy", [model["moment_xy"]["mu"], model["moment_xy"]["delta"]]))
+    L.append(rec("joint_limits", [model["joint_limits"]["mu"], model["joint_limits"]["delta"]]))
+    c = model["collision"]
+    L.append(rec("collision", [c["mu"], c["delta"], c["r_foot"], c["r_knee"]]))
+    sw = model["swing"]
+    L.append(rec("swing", [sw[k] for k in ("liftOffVelocity", "touchDownVelocity", "swingHeight", "touchDownHeightOffset", "swingTimeScale",
+                                           "ipfLiftOffVelocity", "ipfTouchDownVelocity", "ipfMidPointValue")]))
+    sq = model["sqp"]
+    L.append(rec("sqp", [sq[k] for k in ("dt", "sqpIteration", "deltaTol", "g_max", "g_min", "timeHorizon")]))
+    r = model["reference"]
+    L.append(rec("default_base_height", [r["defaultBaseHeight"]]))
+    L.append(rec("default_joint_state", r["defaultJointState"]))
+    for name, gt in model["gaits"].items():
+        L.append(f"gait {name} {len(gt['modeSequence'])} " + " ".join(gt["modeSequence"]) + " " + " ".join(repr(float(t)) for t in gt["switchingTimes"]))
+    from pathlib import Path
+
+    Path(path).write_text("\n".join(L) + "\n")

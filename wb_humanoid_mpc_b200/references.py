@@ -192,7 +192,10 @@ class SwingTrajectoryPlanner:
 def phase_variable(ms: ModeSchedule, t: float) -> float:
     ev = ms.event_times
     it = bisect.bisect_right(ev, t)
-    nxt, prv = ev[it], ev[it - 1]
+    # the reference dereferences both neighbours unchecked (SwitchedModelReferenceManager.cpp:63-65); outside the event range the phase is a
+    # STANCE phase and only `prv` is used, for a mode lookup: any time before the first event gives the same answer
+    nxt = ev[it] if it < len(ev) else ev[-1]
+    prv = ev[it - 1] if it > 0 else ev[0] - 1.0
     m = ms.mode_at(t)
     if m == LF:
         return 0.5 * (t - prv) / (nxt - prv)
