@@ -171,6 +171,14 @@ int b200sqp_download(b200sqp_handle h, double* x, double* u, double* K, b200sqp_
  * re-centred on the linearisation trajectory as in extractValueFunction (dfdx -= dfdxx * x):  P [B][n_nodes][nx*nx], p [B][n_nodes][nx]. */
 int b200sqp_download_value_function(b200sqp_handle h, double* P, double* p);
 
+/* Centroidal flow map of the humanoid centroidal MPC (PinocchioCentroidalDynamicsAD::getValueCppAd,
+ * lib/ocs2_ros2/ocs2_pinocchio/ocs2_centroidal_model/src/PinocchioCentroidalDynamicsAD.cpp:75-94) and its Jacobians
+ * (SystemDynamicsBaseAD::linearApproximation), batched; the centroidal model shares the kinematic tree and contact frames of `model`.
+ *   x [B][12+nj] = (normalized momentum 6, base position 3, Euler ZYX 3, joints nj); u [B][12+nj] = (wrench_l 6, wrench_r 6, joint velocities nj)
+ *   xdot [B][12+nj]; dfdx [B][(12+nj)^2], dfdu [B][(12+nj)^2] column-major, either may be NULL.  Host pointers. */
+int b200sqp_centroidal_flow_map(const b200sqp_model_desc* model, int batch, const double* x, const double* u, double* xdot, double* dfdx,
+                                double* dfdu, int device);
+
 /* Stage blocks of the last LQ approximation, for block-level parity tests:
  *   which = 0 raw (before projection): A [nx*nx] B [nx*nu] b [nx] Q S(nu x nx) R q r C(nc_max x nx) D(nc_max x nu) e nc
  *   see b200sqp_stage_layout for offsets. */

@@ -8,6 +8,7 @@
 #include "test_problems.hpp"
 #ifdef ORC_WITH_WB
 #include "wb_problem.hpp"
+#include "cen_dynamics.hpp"
 #endif
 
 using namespace orc;

@@ -226,6 +226,24 @@ class WbOracle:
         self.L.orc_wb_flow_map_lin(self.h, _p(F(x)), _p(F(u)), _p(f), _p(A), _p(B))
         return f, A.T.copy(), B.T.copy()
 
+    # -- centroidal flow map (oracle/cen_dynamics.hpp) ---------------------------------------------------------------------
+    def centroidal_map(self, q):
+        nv = 6 + self.nj
+        Ag, com = np.zeros((6, nv)), np.zeros(3)
+        self.L.orc_cen_centroidal_map(self.h, _p(F(q)), _p(Ag), _p(com))
+        return Ag, com
+
+    def cen_flow_map(self, x, u):
+        xd = np.zeros(12 + self.nj)
+        self.L.orc_cen_flow_map(self.h, _p(F(x)), _p(F(u)), _p(xd))
+        return xd
+
+    def cen_flow_map_lin(self, x, u):
+        nx = nu = 12 + self.nj
+        f, A, B = np.zeros(nx), np.zeros((nx, nx)), np.zeros((nu, nx))
+        self.L.orc_cen_flow_map_lin(self.h, _p(F(x)), _p(F(u)), _p(f), _p(A), _p(B))
+        return f, A.T.copy(), B.T.copy()
+
     def cost(self, k, x, u):
         return self.L.orc_wb_cost(self.h, C.c_int(k), _p(F(x)), _p(F(u)))
 

@@ -13,6 +13,7 @@
 #include "riccati.cuh"
 #ifdef B200SQP_WITH_WB
 #include "wb_solver.cuh"
+#include "cen_dynamics.cuh"
 #endif
 
 namespace {
