@@ -121,7 +121,7 @@ struct PjWs {
   double* scratch;
   int* iw;                       // rowOf[16] colOf[36] posOf[36]
   // phase-1 views (projection)
-  double *CD, *ev, *LU, *Uinv, *Linv, *PC, *T;
+  double *CD, *ev, *LU;
   // dynamics views
   double *B1, *D12;              // 12 x nc (ld 12) ; 12 x (59 + nut) (ld 12)
   // Hessian view
@@ -129,7 +129,7 @@ struct PjWs {
   // cost change-of-variables views
   double *T11, *T12, *R11, *R21, *W, *V, *rr;   // nc x 58 (ld 14), nut x 58 (ld 23), nc x nc (ld 14), nut x nc (ld 23), nc x nut (ld 14), nut x nut (ld 23), 35 + 35
 };
-constexpr int PJ_SCRATCH = 3856;
+constexpr int PJ_SCRATCH = 3600;   // max over the phases: 1806 (projection), 1152 (dynamics), 2790 (swing rows), 3585 (cost change of variables)
 HD size_t pjWsDoubles() {
   return NX * NX + NU * NX + NU * NU + 1 + NZ + 1 + NX + NC_MAX * (NX + 1) + NC_MAX * NUT_MAX + 12 * NZ + JU_MAX * NUC + PJ_SCRATCH + 48;
 }
@@ -149,10 +149,6 @@ HD void pjWsMap(double* base, PjWs& s) {
   s.CD = s.scratch;                          // 14 x 93 = 1302
   s.ev = s.CD + NC_MAX * NZ;                 // 14
   s.LU = s.ev + NC_MAX;                      // 14 x 35 = 490
-  s.Uinv = s.LU + NC_MAX * NU;               // 196
-  s.Linv = s.Uinv + NC_MAX * NC_MAX;         // 196
-  s.PC = s.Linv + NC_MAX * NC_MAX;           // 14 x 59 = 826
-  s.T = s.PC + NC_MAX * (NX + 1);            // 826   (ends at 3850)
   // dynamics change of variables
   s.B1 = s.scratch;                          // 12 x 14 = 168
   s.D12 = s.B1 + 12 * NC_MAX;                // 12 x 82 = 984
@@ -683,58 +679,48 @@ HD void luPhaseFactor(Par P, int nc, double* LU, int* rowOf, int* colOf) {
   }
 #endif
 }
-// Px = -D^+ C (35 x 58), u0 = -D^+ e, Pu = kernel (35 x nut), from the LU factors, as small triangular inverses + GEMMs:
-//   phase A: columns of U_rr^-1 and L_rr^-1 (2*nc items) ; PC = row-permuted [C | e] (nc x 59)
-//   phase B: T = L^-1 PC
-//   phase C: Xt = -U^-1 T (nc x 59) ; Kt = -U^-1 U_rk (nc x nut)
-//   phase D: scatter through the column permutation
-struct LuSolveWs {
-  double *Uinv, *Linv, *PC, *T, *Xt, *Kt;  // each <= 14 x 59, leading dimension NC_MAX
-};
-HD void luPhaseSolveA(Par P, int nc, const double* LU, const int* rowOf, const double* CD, const double* ev, LuSolveWs ws) {
-  for (int it = P.tid; it < 2 * nc; it += P.nt) {
-    const int c = it % nc;
-    if (it < nc) {  // column c of U^-1 (upper triangular)
-      double z[NC_MAX];
+// Px = -D^+ C (35 x 58), u0 = -D^+ e, Pu = kernel (35 x nut), from the LU factors (Eigen: particular solution with the free variables
+// at zero, kernel basis from the pivoted U):
+// [X | x0] = -U^-1 L^-1 P [C | e]  (nc x 59)  and  K = -U^-1 U_rk  (nc x nut), one right-hand side per work item: the column lives in
+// registers through the unit-lower forward and the upper backward substitution (replaces explicit triangular inverses + two GEMMs).
+HD void luPhaseSolveDirect(Par P, int nc, const double* LU, const int* rowOf, const double* CD, const double* ev, double* Xt, double* Kt) {
+  const int nut = NU - nc;
+  for (int it = P.tid; it < NX + 1 + nut; it += P.nt) {
+    double z[NC_MAX];
+    if (it <= NX) {
 #pragma unroll
-      for (int i = 0; i < NC_MAX; ++i) z[i] = 0.0;
+      for (int i = 0; i < NC_MAX; ++i) z[i] = (i < nc) ? (it < NX ? CD[rowOf[i] + NC_MAX * it] : ev[rowOf[i]]) : 0.0;
 #pragma unroll
-      for (int i = NC_MAX - 1; i >= 0; --i) {
-        if (i <= c && i < nc) {
-          double s = (i == c) ? 1.0 : 0.0;
+      for (int i = 1; i < NC_MAX; ++i) {
+        if (i < nc) {
+          double s = z[i];
 #pragma unroll
-          for (int j = i + 1; j < NC_MAX; ++j)
-            if (j <= c) s = fma(-LU[i + NC_MAX * j], z[j], s);
-          z[i] = s / LU[i + NC_MAX * i];
-        }
-      }
-#pragma unroll
-      for (int i = 0; i < NC_MAX; ++i)
-        if (i < nc) ws.Uinv[i + NC_MAX * c] = z[i];
-    } else {  // column c of L^-1 (unit lower triangular)
-      double z[NC_MAX];
-#pragma unroll
-      for (int i = 0; i < NC_MAX; ++i) z[i] = 0.0;
-#pragma unroll
-      for (int i = 0; i < NC_MAX; ++i) {
-        if (i >= c && i < nc) {
-          double s = (i == c) ? 1.0 : 0.0;
-#pragma unroll
-          for (int j = 0; j < i; ++j)
-            if (j >= c) s = fma(-LU[i + NC_MAX * j], z[j], s);
+          for (int j = 0; j < i; ++j) s = fma(-LU[i + NC_MAX * j], z[j], s);
           z[i] = s;
         }
       }
+    } else {
+      const int kk = it - NX - 1;
 #pragma unroll
-      for (int i = 0; i < NC_MAX; ++i)
-        if (i < nc) ws.Linv[i + NC_MAX * c] = z[i];
+      for (int i = 0; i < NC_MAX; ++i) z[i] = (i < nc) ? LU[i + NC_MAX * (nc + kk)] : 0.0;
     }
-  }
-  for (int it = P.tid; it < nc * (NX + 1); it += P.nt) {
-    const int i = it % nc, j = it / nc;
-    ws.PC[i + NC_MAX * j] = (j < NX) ? CD[rowOf[i] + NC_MAX * j] : ev[rowOf[i]];
+#pragma unroll
+    for (int i = NC_MAX - 1; i >= 0; --i) {
+      if (i < nc) {
+        double s = z[i];
+#pragma unroll
+        for (int j = i + 1; j < NC_MAX; ++j)
+          if (j < nc) s = fma(-LU[i + NC_MAX * j], z[j], s);
+        z[i] = s / LU[i + NC_MAX * i];
+      }
+    }
+    double* dst = (it <= NX) ? Xt + NC_MAX * it : Kt + NC_MAX * (it - NX - 1);
+#pragma unroll
+    for (int i = 0; i < NC_MAX; ++i)
+      if (i < nc) dst[i] = -z[i];
   }
 }
+
 // scatter the solution through the column permutation to the layout the remap kernel reads (global memory):
 //   Px (35 x 58), u0 (35), Pu (35 x nut)
 HD void luPhaseInversePerm(Par P, const int* colOf, int* posOf) {
