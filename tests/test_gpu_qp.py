@@ -115,3 +115,38 @@ def test_riccati_failure_is_reported():
     with pytest.raises(B200SqpError) as ei:
         qp.download()
     assert ei.value.code == -4
+
+
+def test_kkt_residual_full_size():
+    """north_star parity list: the KKT residual of the GPU QP solution, assembled stage-wise as in OcpToKkt (no oracle involved):
+    with costates lambda_k = P_k dx_k + p_k,
+        stationarity in dx_k : Q dx + S' du + q + A' lambda_{k+1} - lambda_k = 0,   in du_k : S dx + R du + r + B' lambda_{k+1} = 0,
+        dynamics            : dx_{k+1} = A dx + B du + b,   dx_0 given."""
+    from wb_humanoid_mpc_b200.qp import BatchedQp
+
+    rng = np.random.default_rng(21)
+    nx, numax, N, Bn = 58, 23, 115, 3
+    pattern = np.array([23 if k % 7 else 21 for k in range(N)], dtype=np.int32)
+    data, nu, dx0 = _random_batch(rng, Bn, N, nx, numax, nu_pattern=pattern)
+    A, Bm, b, Q, S, R, q, r = data
+    qp = BatchedQp(Bn, N, nx, numax)
+    qp.upload(*data, dx0, nu)
+    qp.solve()
+    sol = qp.download()
+    for i in range(Bn):
+        dx, du, P, p = sol["dx"][i], sol["du"][i], sol["P"][i], sol["p"][i]
+        lam = np.einsum("kij,kj->ki", P, dx) + p
+        assert np.allclose(dx[0], dx0[i], atol=1e-13)
+        worst = 0.0
+        for k in range(N):
+            m = nu[i, k]
+            uk = du[k, :m]
+            Bk, Sk, Rk = Bm[i, k][:, :m], S[i, k][:m, :], R[i, k][:m, :m]
+            dyn = A[i, k] @ dx[k] + Bk @ uk + b[i, k] - dx[k + 1]
+            sx = Q[i, k] @ dx[k] + Sk.T @ uk + q[i, k] + A[i, k].T @ lam[k + 1] - lam[k]
+            su = Sk @ dx[k] + Rk @ uk + r[i, k][:m] + Bk.T @ lam[k + 1]
+            scale = max(1.0, np.abs(lam[k]).max())
+            worst = max(worst, np.abs(dyn).max(), np.abs(sx).max() / scale, np.abs(su).max() / scale)
+        term = Q[i, N] @ dx[N] + q[i, N] - lam[N]
+        worst = max(worst, np.abs(term).max() / max(1.0, np.abs(lam[N]).max()))
+        assert worst < 1e-9, worst
