@@ -18,6 +18,7 @@
 #ifndef B200SQP_H
 #define B200SQP_H
 
+#include <stddef.h>
 #include <stdint.h>
 
 #ifdef __cplusplus
@@ -135,6 +136,11 @@ int b200sqp_set_batch(b200sqp_handle h, int batch, int n_nodes);
 int b200sqp_upload_instances(b200sqp_handle h, const double* x0, const double* x_init, const double* u_init, const double* t_nodes,
                              const uint8_t* node_event, const uint8_t* contact_flags, const double* swing_ref,
                              const double* impact_factor, const double* arm_phase, const double* x_ref);
+
+/* Page-locked host staging memory for the upload / download arrays (plain malloc-like interface so that hosts without CUDA headers can use
+ * it); NULL on failure.  Arrays passed to b200sqp_upload_instances / b200sqp_download may live anywhere; pinned ones copy faster. */
+void* b200sqp_host_alloc(size_t bytes);
+void b200sqp_host_free(void* p);
 
 /* SqpSolver::reset() (SqpSolver.h:62): drop the current iterate; the next solve starts again from the uploaded initial guess
  * (device-to-device restore, no host traffic). */

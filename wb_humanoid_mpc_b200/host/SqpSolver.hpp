@@ -56,8 +56,10 @@ class SqpSolver {
     threads_ = hostThreads > 0 ? hostThreads : static_cast<int>(std::max(1u, std::min(hw ? hw : 1u, 64u)));
   }
   ~SqpSolver() {
-    for (auto& g : groups_)
+    for (auto& g : groups_) {
+      g.second.st.release();
       if (g.second.h) b200sqp_destroy(g.second.h);
+    }
   }
   SqpSolver(const SqpSolver&) = delete;
   SqpSolver& operator=(const SqpSolver&) = delete;
@@ -132,11 +134,30 @@ class SqpSolver {
   [[noreturn]] void getIntermediateDualSolution() const { throw std::runtime_error("[SqpSolver] getIntermediateDualSolution() not available yet."); }
 
  private:
+  // page-locked staging arrays of one node-count group, allocated once per (batch, node count) and reused by every run
+  struct Staging {
+    double *x0 = nullptr, *xi = nullptr, *ui = nullptr, *tn = nullptr, *sw = nullptr, *imp = nullptr, *arm = nullptr, *xr = nullptr, *x = nullptr, *u = nullptr;
+    uint8_t *ev = nullptr, *cf = nullptr;
+    void release() {
+      for (void* p : {static_cast<void*>(x0), static_cast<void*>(xi), static_cast<void*>(ui), static_cast<void*>(tn), static_cast<void*>(sw),
+                      static_cast<void*>(imp), static_cast<void*>(arm), static_cast<void*>(xr), static_cast<void*>(x), static_cast<void*>(u),
+                      static_cast<void*>(ev), static_cast<void*>(cf)})
+        b200sqp_host_free(p);
+      *this = Staging();
+    }
+  };
   struct Group {
     b200sqp_handle h = nullptr;
     int nNodes = 0, capacity = 0;
+    Staging st;
     vector_t P, p;
   };
+  template <class T>
+  static T* pinned(size_t count) {
+    T* p = static_cast<T*>(b200sqp_host_alloc(count * sizeof(T)));
+    if (!p) throw std::runtime_error(std::string("[SqpSolver] ") + b200sqp_last_error());
+    return p;
+  }
   static void check(int rc) {
     if (rc != 0) throw std::runtime_error(std::string("[SqpSolver] ") + b200sqp_last_error());
   }
@@ -166,36 +187,48 @@ class SqpSolver {
     Group& G = groups_[nNodes];
     const int Bg = static_cast<int>(members.size()), nx = model_.nx, nu = model_.nu, n = nNodes;
     if (!G.h) check(b200sqp_create(&model_.desc, &settings_, device_, &G.h));
+    const size_t B_ = static_cast<size_t>(Bg), n_ = static_cast<size_t>(n);
     if (G.capacity != Bg || G.nNodes != n) {
       check(b200sqp_set_batch(G.h, Bg, n));
       G.capacity = Bg;
       G.nNodes = n;
+      G.st.release();
+      Staging& S = G.st;
+      S.x0 = pinned<double>(B_ * nx);
+      S.xi = pinned<double>(B_ * n_ * nx);
+      S.ui = pinned<double>(B_ * (n_ - 1) * nu);
+      S.tn = pinned<double>(B_ * n_);
+      S.sw = pinned<double>(B_ * n_ * 6);
+      S.imp = pinned<double>(B_ * n_ * 2);
+      S.arm = pinned<double>(B_ * n_);
+      S.xr = pinned<double>(B_ * n_ * nx);
+      S.x = pinned<double>(B_ * n_ * nx);
+      S.u = pinned<double>(B_ * (n_ - 1) * nu);
+      S.ev = pinned<uint8_t>(B_ * n_);
+      S.cf = pinned<uint8_t>(B_ * n_ * 2);
     }
-    // pack (host staging; the C ABI copies from plain host pointers)
-    vector_t x0(static_cast<size_t>(Bg) * nx), xi(static_cast<size_t>(Bg) * n * nx), ui(static_cast<size_t>(Bg) * (n - 1) * nu),
-        tn(static_cast<size_t>(Bg) * n), sw(static_cast<size_t>(Bg) * n * 6), imp(static_cast<size_t>(Bg) * n * 2), arm(static_cast<size_t>(Bg) * n),
-        xr(static_cast<size_t>(Bg) * n * nx);
-    std::vector<uint8_t> ev(static_cast<size_t>(Bg) * n), cf(static_cast<size_t>(Bg) * n * 2);
+    double *x0 = G.st.x0, *xi = G.st.xi, *ui = G.st.ui, *tn = G.st.tn, *sw = G.st.sw, *imp = G.st.imp, *arm = G.st.arm, *xr = G.st.xr;
+    uint8_t *ev = G.st.ev, *cf = G.st.cf;
     parallelFor(Bg, [&](int s) {
       const Instance& I = inst[members[s]];
-      std::copy(I.x0.begin(), I.x0.end(), x0.begin() + static_cast<size_t>(s) * nx);
-      std::copy(I.x_init.begin(), I.x_init.end(), xi.begin() + static_cast<size_t>(s) * n * nx);
-      std::copy(I.u_init.begin(), I.u_init.end(), ui.begin() + static_cast<size_t>(s) * (n - 1) * nu);
-      std::copy(I.t_nodes.begin(), I.t_nodes.end(), tn.begin() + static_cast<size_t>(s) * n);
-      std::copy(I.node_event.begin(), I.node_event.end(), ev.begin() + static_cast<size_t>(s) * n);
-      std::copy(I.contact_flags.begin(), I.contact_flags.end(), cf.begin() + static_cast<size_t>(s) * n * 2);
-      std::copy(I.swing_ref.begin(), I.swing_ref.end(), sw.begin() + static_cast<size_t>(s) * n * 6);
-      std::copy(I.impact_factor.begin(), I.impact_factor.end(), imp.begin() + static_cast<size_t>(s) * n * 2);
-      std::copy(I.arm_phase.begin(), I.arm_phase.end(), arm.begin() + static_cast<size_t>(s) * n);
-      std::copy(I.x_ref.begin(), I.x_ref.end(), xr.begin() + static_cast<size_t>(s) * n * nx);
+      std::copy(I.x0.begin(), I.x0.end(), x0 + static_cast<size_t>(s) * nx);
+      std::copy(I.x_init.begin(), I.x_init.end(), xi + static_cast<size_t>(s) * n * nx);
+      std::copy(I.u_init.begin(), I.u_init.end(), ui + static_cast<size_t>(s) * (n - 1) * nu);
+      std::copy(I.t_nodes.begin(), I.t_nodes.end(), tn + static_cast<size_t>(s) * n);
+      std::copy(I.node_event.begin(), I.node_event.end(), ev + static_cast<size_t>(s) * n);
+      std::copy(I.contact_flags.begin(), I.contact_flags.end(), cf + static_cast<size_t>(s) * n * 2);
+      std::copy(I.swing_ref.begin(), I.swing_ref.end(), sw + static_cast<size_t>(s) * n * 6);
+      std::copy(I.impact_factor.begin(), I.impact_factor.end(), imp + static_cast<size_t>(s) * n * 2);
+      std::copy(I.arm_phase.begin(), I.arm_phase.end(), arm + static_cast<size_t>(s) * n);
+      std::copy(I.x_ref.begin(), I.x_ref.end(), xr + static_cast<size_t>(s) * n * nx);
     });
-    check(b200sqp_upload_instances(G.h, x0.data(), xi.data(), ui.data(), tn.data(), ev.data(), cf.data(), sw.data(), imp.data(), arm.data(), xr.data()));
+    check(b200sqp_upload_instances(G.h, x0, xi, ui, tn, ev, cf, sw, imp, arm, xr));
     check(b200sqp_solve(G.h, nullptr));
-    vector_t x(static_cast<size_t>(Bg) * n * nx), u(static_cast<size_t>(Bg) * (n - 1) * nu);
+    double *x = G.st.x, *u = G.st.u;
     const int iters = settings_.sqp_iteration;
     std::vector<b200sqp_iter_log> log(static_cast<size_t>(Bg) * iters);
     std::vector<int32_t> nIter(Bg), status(Bg);
-    check(b200sqp_download(G.h, x.data(), u.data(), nullptr, log.data(), nIter.data(), status.data()));
+    check(b200sqp_download(G.h, x, u, nullptr, log.data(), nIter.data(), status.data()));
     if (settings_.create_value_function) {
       G.P.resize(static_cast<size_t>(Bg) * n * nx * nx);
       G.p.resize(static_cast<size_t>(Bg) * n * nx);
@@ -214,7 +247,7 @@ class SqpSolver {
       const int b = members[s];
       groupOf_[b] = gid;
       slotOf_[b] = s;
-      primal_[b] = toPrimalSolution(inst[b], x.data() + static_cast<size_t>(s) * n * nx, u.data() + static_cast<size_t>(s) * (n - 1) * nu, nx, nu);
+      primal_[b] = toPrimalSolution(inst[b], x + static_cast<size_t>(s) * n * nx, u + static_cast<size_t>(s) * (n - 1) * nu, nx, nu);
       log_[b].clear();
       for (int it = 0; it < nIter[s]; ++it) {
         const b200sqp_iter_log& L = log[static_cast<size_t>(s) * iters + it];

@@ -84,8 +84,14 @@ def lib() -> C.CDLL:
             fn = getattr(L, name)
         except AttributeError:  # reported by tests/test_abi.py; do not mask the symbols that do exist
             continue
-        if name not in ("b200sqp_last_error", "b200sqp_version", "b200sqp_qp_destroy", "b200sqp_destroy", "b200sqp_default_settings"):
+        if name not in ("b200sqp_last_error", "b200sqp_version", "b200sqp_qp_destroy", "b200sqp_destroy", "b200sqp_default_settings",
+                        "b200sqp_host_alloc", "b200sqp_host_free"):
             fn.restype = C.c_int
+    if hasattr(L, "b200sqp_host_alloc"):
+        L.b200sqp_host_alloc.restype = C.c_void_p
+        L.b200sqp_host_alloc.argtypes = [C.c_size_t]
+        L.b200sqp_host_free.restype = None
+        L.b200sqp_host_free.argtypes = [C.c_void_p]
     for name in ("b200sqp_qp_destroy", "b200sqp_destroy", "b200sqp_default_settings"):
         if hasattr(L, name):
             getattr(L, name).restype = None
@@ -113,6 +119,8 @@ EXPORTED_SYMBOLS = [
     "b200sqp_destroy",
     "b200sqp_set_batch",
     "b200sqp_upload_instances",
+    "b200sqp_host_alloc",
+    "b200sqp_host_free",
     "b200sqp_reset",
     "b200sqp_solve",
     "b200sqp_set_global_step_callback",
