@@ -66,3 +66,35 @@ def test_host_solver_matches_python_harness_cold_and_warm():
         assert dx < 1e-6, (b, dx)
     host.close()
     hm.close()
+
+
+def test_receding_horizon_converges():
+    """closed loop with perfect tracking (tools/bench_receding.py in small): the real-time-iteration scheme warm-started from the previous
+    primal solution drives the dynamics / constraint violations of the plan down over the MPC cycles and reaches full steps"""
+    model = model_loader.load_packaged_model()
+    hm = host_lib.HostModel()
+    st = abi.default_settings(model, sqp_iteration=1)
+    B, T, dt = 4, 1.1, model["sqp"]["dt"]
+    host = host_lib.HostSqpSolver(hm, st, B)
+    rng = np.random.default_rng(8)
+    x = np.array([np.array(model["x_init"], float) for _ in range(B)])
+    x[:, 2] = model["reference"]["defaultBaseHeight"]
+    x[:, 6:29] += rng.uniform(-0.05, 0.05, (B, 23))
+    cmds = [[0.4, 0.0, model["reference"]["defaultBaseHeight"], 0.1]] * B
+    for b in range(B):
+        host.set_gait(b, "walk", 0.0, 20 * dt + 3 * T)
+    t, viol, steps = 0.0, [], []
+    for c in range(10):
+        for b in range(B):
+            host.set_command(b, t, x[b], cmds[b], T)
+        host.run(t, x, t + T)
+        logs = np.array([host.iterations_log(b)[0] for b in range(B)])
+        assert np.all(np.isfinite(logs))
+        viol.append(float((logs[:, 4] + logs[:, 5]).mean()))
+        steps.append(float(logs[:, 6].mean()))
+        x = np.array([host.primal_solution(b)["x"][1] for b in range(B)])
+        t += dt
+    assert viol[-1] < 0.2 * viol[0] and all(b < a * 1.5 for a, b in zip(viol, viol[1:])), viol
+    assert steps[-1] >= steps[0] and steps[-1] > 0.7, steps
+    host.close()
+    hm.close()
