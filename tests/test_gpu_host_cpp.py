@@ -48,7 +48,7 @@ def test_host_solver_matches_python_harness_cold_and_warm():
         assert lg.shape[0] == r["n_iter"][0]
         assert np.allclose(lg[:, 6], r["log"][0, : lg.shape[0], LOG_FIELDS.index("step_size")])
         assert np.allclose(lg[:, 3], r["log"][0, : lg.shape[0], LOG_FIELDS.index("merit")], rtol=1e-7)
-        prev.append((py, references.to_primal_solution(inst["t_nodes"], inst["node_event"], r["x"][0], r["u"][0])))
+        prev.append((py, references.to_primal_solution(inst["t_nodes"], inst["node_event"], r["x"][0], r["u"][0], inst["mode_schedule"])))
     assert host.benchmarks()[0] > 0.0
 
     # receding horizon: second solve 3 nodes later, warm-started from the previous primal solution on both sides
@@ -68,14 +68,18 @@ def test_host_solver_matches_python_harness_cold_and_warm():
     hm.close()
 
 
-def test_receding_horizon_converges():
+@pytest.mark.parametrize("spread", [True, False])
+def test_receding_horizon_converges(spread):
     """closed loop with perfect tracking (tools/bench_receding.py in small): the real-time-iteration scheme warm-started from the previous
-    primal solution drives the dynamics / constraint violations of the plan down over the MPC cycles and reaches full steps"""
+    primal solution drives the dynamics / constraint violations of the plan down over the MPC cycles and reaches full steps.
+    spread=True is the reference behaviour: trajectorySpread moves the time stamp of the sample after every event (its convention clash with
+    the SQP's primal solution), which distorts the warm start next to events and slows the decrease; spread=False keeps the stamps."""
     model = model_loader.load_packaged_model()
     hm = host_lib.HostModel()
     st = abi.default_settings(model, sqp_iteration=1)
     B, T, dt = 4, 1.1, model["sqp"]["dt"]
     host = host_lib.HostSqpSolver(hm, st, B)
+    host.set_trajectory_spread(spread)
     rng = np.random.default_rng(8)
     x = np.array([np.array(model["x_init"], float) for _ in range(B)])
     x[:, 2] = model["reference"]["defaultBaseHeight"]
@@ -94,7 +98,10 @@ def test_receding_horizon_converges():
         steps.append(float(logs[:, 6].mean()))
         x = np.array([host.primal_solution(b)["x"][1] for b in range(B)])
         t += dt
-    assert viol[-1] < 0.2 * viol[0] and all(b < a * 1.5 for a, b in zip(viol, viol[1:])), viol
-    assert steps[-1] >= steps[0] and steps[-1] > 0.7, steps
+    if spread:
+        assert min(viol) < 0.25 * viol[0] and viol[-1] < 0.5 * viol[0], viol
+    else:
+        assert viol[-1] < 0.2 * viol[0] and all(b < a * 1.5 for a, b in zip(viol, viol[1:])), viol
+        assert steps[-1] >= steps[0] and steps[-1] > 0.7, steps
     host.close()
     hm.close()

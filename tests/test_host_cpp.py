@@ -75,3 +75,62 @@ def test_errors_are_reported(hmodel):
         hmodel.build_instance(np.zeros(58), gait="moonwalk")
     with pytest.raises(RuntimeError, match="not found"):
         host_lib.HostModel("/nonexistent/model.txt")
+
+
+# ---- trajectorySpread (SqpSolver.cpp:211-213; ocs2_oc TrajectorySpreading) ----------------------------------------------------------------
+def _rollout_like(ms, t0, tf, dt, eps=1e-9):
+    """time trajectory in the OCS2 rollout convention (pre-event sample at t_e, post-event sample at t_e + eps) tagged with the active mode"""
+    t, tags = [], []
+    events = [e for e in ms.event_times if t0 < e < tf]
+    grid = sorted(set(np.round(np.arange(t0, tf + 1e-12, dt), 12).tolist() + [tf]))
+    for a in grid:
+        t.append(a)
+    for e in events:
+        t += [e, e + eps]
+    t = sorted(set(t))
+    for a in t:
+        tags.append(ms.mode_sequence[np.searchsorted(ms.event_times, a, side="left")])
+    return np.array(t), np.array(tags, float)[:, None]
+
+
+@pytest.mark.parametrize("seed", range(8))
+def test_trajectory_spread_matches_python_and_reproduces_the_new_mode_sequence(seed):
+    """the reference's own test idea (ocs2_oc/test/trajectory_adjustment/TrajectorySpreadingTest.cpp): tag every sample with its mode, spread
+    to a perturbed schedule, and the tags must follow the new schedule wherever the matched window covers; C++ and Python must agree exactly"""
+    rng = np.random.default_rng(seed)
+    n_ev = int(rng.integers(2, 6))
+    ev = np.sort(rng.uniform(0.3, 2.7, n_ev))
+    modes = [int(m) for m in rng.permutation(8)[: n_ev + 1]]
+    old = references.ModeSchedule(list(ev), modes)
+    shifted = np.sort(np.clip(ev + rng.uniform(-0.12, 0.12, n_ev), 0.05, 2.95))
+    new_modes = list(modes)
+    if seed % 3 == 2:
+        new_modes[-1] = 9                        # the tail mode changes: truncation
+    new = references.ModeSchedule(list(shifted), new_modes)
+    t, tags = _rollout_like(old, 0.0, 3.0, 0.1)
+    prim = dict(t=t, x=tags, u=tags.copy())
+    py = references.trajectory_spread(old, new, prim)
+    ct, cx, cu, trunc, spread = host_lib.trajectory_spread(old.event_times, old.mode_sequence, new.event_times, new.mode_sequence, t, tags, tags)
+    assert np.array_equal(py["t"], ct) and np.array_equal(py["x"], cx) and np.array_equal(py["u"], cu)
+    assert (py["will_truncate"], py["will_spread"]) == (trunc, spread)
+    # property: after spreading, every kept sample carries the mode the NEW schedule prescribes at its (adjusted) time
+    for a, tag in zip(ct, cx[:, 0]):
+        want = new.mode_sequence[np.searchsorted(new.event_times, a, side="left")]
+        assert int(tag) == want, (a, tag, want)
+
+
+def test_trajectory_spread_identical_schedules_sqp_time_convention(model):
+    """the SQP's primal solution keeps pre- and post-event samples at the same time, so the reference's spreading moves the time of the
+    sample after every event to event + eps even when nothing changed (documented quirk, reproduced by both restatements)"""
+    inst = references.build_instance(model, np.array(model["x_init"], float), t0=0.0, horizon=1.1, gait="walk")
+    n = len(inst["t_nodes"])
+    prim = references.to_primal_solution(inst["t_nodes"], inst["node_event"], np.zeros((n, 58)), np.zeros((n - 1, 35)), inst["mode_schedule"])
+    py = references.trajectory_spread(inst["mode_schedule"], inst["mode_schedule"], prim)
+    ms = inst["mode_schedule"]
+    ct, cx, cu, trunc, spread = host_lib.trajectory_spread(ms.event_times, ms.mode_sequence, ms.event_times, ms.mode_sequence, prim["t"], prim["x"], prim["u"])
+    assert np.array_equal(py["t"], ct) and not trunc and not spread and len(ct) == n
+    post = [i for i in range(1, n) if inst["node_event"][i] == 2]   # (an event at the initial time is outside the matched window)
+    assert post, "the walk gait puts events inside the horizon"
+    for i in post:
+        if i + 1 < n - 1:
+            assert abs(ct[i + 1] - (inst["t_nodes"][i] + 1e-9)) < 1e-15

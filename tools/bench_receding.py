@@ -23,6 +23,7 @@ def main():
     ap.add_argument("--cycles", type=int, default=20)
     ap.add_argument("--horizon", type=float, default=3.5)
     ap.add_argument("--gait", default="walk")
+    ap.add_argument("--no-spread", action="store_true", help="skip the reference's trajectorySpread of the previous solution")
     args = ap.parse_args()
     model = model_loader.load_packaged_model()
     hm = host_lib.HostModel()
@@ -30,6 +31,7 @@ def main():
     B, T, dt = args.batch, args.horizon, model["sqp"]["dt"]
     rng = np.random.default_rng(1234)
     solver = host_lib.HostSqpSolver(hm, st, B)
+    solver.set_trajectory_spread(not args.no_spread)
     lo, hi = np.array(model["q_lower"]), np.array(model["q_upper"])
     x, cmds = [], []
     for b in range(B):
@@ -63,7 +65,7 @@ def main():
     out = {"metric": "SQP solves/sec (G1 whole-body, N=100, batched), receding horizon through b200sqp::host::SqpSolver::run", "unit": "solves/s",
            "cold_start": rows[0]["solves_per_s"], "steady_state": float(np.mean([r["solves_per_s"] for r in steady])),
            "steady_stage_ms": [float(np.mean([r["stage_ms"][k] for r in steady])) for k in range(3)],
-           "config": {"batch": B, "cycles": args.cycles, "gait": args.gait, "horizon": T}, "cycles": rows}
+           "config": {"batch": B, "cycles": args.cycles, "gait": args.gait, "horizon": T, "trajectory_spread": not args.no_spread}, "cycles": rows}
     print(json.dumps(out))
 
 

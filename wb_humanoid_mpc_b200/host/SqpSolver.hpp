@@ -65,6 +65,9 @@ class SqpSolver {
   SqpSolver& operator=(const SqpSolver&) = delete;
 
   int batch() const { return batch_; }
+  // the reference always spreads the previous solution over the new mode schedule (SqpSolver.cpp:211-213); see trajectorySpread's note on the
+  // time-stamp convention clash it inherits -- switching it off keeps the previous solution's time stamps untouched
+  void setTrajectorySpread(bool on) { trajectorySpread_ = on; }
   SwitchedModelReferenceManager& getReferenceManager(int b) { return rm_.at(b); }
 
   void reset() {  // SqpSolver::reset (SqpSolver.cpp:96-106): forget the previous solutions -> the next run is a cold start
@@ -78,6 +81,8 @@ class SqpSolver {
     std::vector<Instance> inst(batch_);
     parallelFor(batch_, [&](int b) {
       rm_[b].preSolverRun(initTime, finalTime);
+      // Trajectory spread of primalSolution_ (SqpSolver.cpp:211-213)
+      if (trajectorySpread_ && !primal_[b].timeTrajectory_.empty()) trajectorySpread(primal_[b].modeSchedule_, rm_[b].getModeSchedule(), primal_[b]);
       const PrimalSolution* prev = primal_[b].timeTrajectory_.empty() ? nullptr : &primal_[b];
       inst[b] = buildInstance(model_, rm_[b], initTime, initStates[b], finalTime, model_.dt, prev);
     });
@@ -274,6 +279,7 @@ class SqpSolver {
   std::map<int, Group> groups_;
   std::vector<int> groupOf_, slotOf_;
   Benchmarks bench_;
+  bool trajectorySpread_ = true;
 };
 
 }  // namespace b200sqp::host

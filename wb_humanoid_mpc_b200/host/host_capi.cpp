@@ -88,6 +88,34 @@ int b200host_build_instance(void* model, double t0, const double* x0, double hor
   });
 }
 
+// trajectorySpread on a primal solution given as flat arrays (in place); returns the new length or -1
+int b200host_trajectory_spread(int n_old_ev, const double* old_ev, const int* old_modes, int n_new_ev, const double* new_ev, const int* new_modes, int n,
+                               int nx, int nu, double* t, double* x, double* u, int* flags /* willTruncate, willSpread */) {
+  return guarded([&] {
+    ModeSchedule oldMs, newMs;
+    oldMs.eventTimes.assign(old_ev, old_ev + n_old_ev);
+    oldMs.modeSequence.assign(old_modes, old_modes + n_old_ev + 1);
+    newMs.eventTimes.assign(new_ev, new_ev + n_new_ev);
+    newMs.modeSequence.assign(new_modes, new_modes + n_new_ev + 1);
+    PrimalSolution p;
+    p.timeTrajectory_.assign(t, t + n);
+    for (int i = 0; i < n; ++i) {
+      p.stateTrajectory_.emplace_back(x + static_cast<size_t>(i) * nx, x + static_cast<size_t>(i + 1) * nx);
+      p.inputTrajectory_.emplace_back(u + static_cast<size_t>(i) * nu, u + static_cast<size_t>(i + 1) * nu);
+    }
+    const auto st = trajectorySpread(oldMs, newMs, p);
+    const int m = static_cast<int>(p.timeTrajectory_.size());
+    std::copy(p.timeTrajectory_.begin(), p.timeTrajectory_.end(), t);
+    for (int i = 0; i < m; ++i) {
+      std::copy(p.stateTrajectory_[i].begin(), p.stateTrajectory_[i].end(), x + static_cast<size_t>(i) * nx);
+      std::copy(p.inputTrajectory_[i].begin(), p.inputTrajectory_[i].end(), u + static_cast<size_t>(i) * nu);
+    }
+    flags[0] = st.willTruncate;
+    flags[1] = st.willPerformTrajectorySpreading;
+    return m;
+  });
+}
+
 void* b200host_solver_create(void* model, const b200sqp_settings* st, int batch, int device, int threads) {
   try {
     return new SqpSolver(*static_cast<HostModel*>(model), *st, batch, device, threads);
@@ -110,6 +138,10 @@ int b200host_solver_set_command(void* s, void* model, int b, double t0, const do
         commandedVelocityToTargetTrajectories(M, t0, vector_t(x0, x0 + M.nx), {cmd[0], cmd[1], cmd[2], cmd[3]}, horizon));
     return 0;
   });
+}
+int b200host_solver_set_trajectory_spread(void* s, int on) {
+  static_cast<SqpSolver*>(s)->setTrajectorySpread(on != 0);
+  return 0;
 }
 int b200host_solver_reset(void* s) {
   return guarded([&] {

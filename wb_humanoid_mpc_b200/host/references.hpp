@@ -349,6 +349,118 @@ struct PrimalSolution {  // ocs2_oc/include/ocs2_oc/oc_data/PrimalSolution.h:43-
   void clear() { *this = PrimalSolution(); }
 };
 
+// ocs2::TrajectorySpreading (ocs2_oc/src/trajectory_adjustment/TrajectorySpreading.cpp:49-166,268-369; templates in
+// include/ocs2_oc/trajectory_adjustment/TrajectorySpreading.h:124-183): adapts trajectories computed for an old mode schedule to a new one
+// by spreading the values next to the moved event times and truncating where the mode sequences stop matching.
+class TrajectorySpreading {
+ public:
+  struct Status {
+    bool willTruncate = false, willPerformTrajectorySpreading = false;
+  };
+  Status set(const ModeSchedule& oldMs, const ModeSchedule& newMs, const vector_t& oldTime) {
+    const double t0 = oldTime.front(), tf = oldTime.back();
+    const int oldFirst = static_cast<int>(upperBoundIndex(oldMs.eventTimes, t0)), oldLast = static_cast<int>(upperBoundIndex(oldMs.eventTimes, tf));
+    const int newFirst = static_cast<int>(upperBoundIndex(newMs.eventTimes, t0)), newLast = static_cast<int>(upperBoundIndex(newMs.eventTimes, tf));
+    int oldStart = oldFirst;
+    const int newStart = newFirst;
+    int w = 0;
+    while (oldStart < static_cast<int>(oldMs.modeSequence.size())) {
+      w = 0;   // std::mismatch over [oldStart, oldLast] x [newStart, newLast]
+      while (oldStart + w <= oldLast && newStart + w <= newLast && oldMs.modeSequence[oldStart + w] == newMs.modeSequence[newStart + w]) ++w;
+      if (w > 0) break;
+      ++oldStart;
+    }
+    vector_t oldM, newM;
+    if (w > 0) {
+      oldM.assign(oldMs.eventTimes.begin() + oldStart, oldMs.eventTimes.begin() + oldStart + w - 1);
+      newM.assign(newMs.eventTimes.begin() + newStart, newMs.eventTimes.begin() + newStart + w - 1);
+    }
+    if (w > 0 && oldStart > oldFirst) {
+      oldM.insert(oldM.begin(), oldMs.eventTimes[oldStart - 1]);
+      newM.insert(newM.begin(), t0 - 1e-4);
+    }
+    const bool oldLastMatched = (oldStart + w - 1 == oldLast), newLastMatched = (newStart + w - 1 == newLast);
+    if (!oldLastMatched && (newLastMatched || oldMs.eventTimes[oldStart + w - 1] < newMs.eventTimes[newStart + w - 1])) {
+      oldM.push_back(oldMs.eventTimes[oldStart + w - 1]);
+      newM.push_back(newLastMatched ? tf + 1e-4 : newMs.eventTimes[newStart + w - 1]);
+    }
+    eraseFrom_ = oldTime.size();
+    if (w == 0) eraseFrom_ = 0;
+    else if (!newLastMatched) eraseFrom_ = lowerBoundIndex(oldTime, newMs.eventTimes[newStart + w - 1]);
+    computeSpreadingStrategy(oldTime, oldM, newM);
+    status_.willTruncate = eraseFrom_ < oldTime.size();
+    status_.willPerformTrajectorySpreading = !valueIdx_.empty();
+    return status_;
+  }
+  template <class T>
+  void adjustTrajectory(std::vector<T>& traj) const {
+    traj.erase(traj.begin() + eraseFrom_, traj.end());
+    std::vector<T> values;
+    for (size_t i : valueIdx_) values.push_back(traj[i]);
+    for (size_t i = 0; i < valueIdx_.size(); ++i)
+      for (size_t j = begin_[i]; j < end_[i]; ++j) traj[j] = values[i];
+  }
+  void adjustTimeTrajectory(vector_t& time) const {
+    time.erase(time.begin() + eraseFrom_, time.end());
+    for (size_t i = 0; i < postEventIndices_.size(); ++i) {
+      time[postEventIndices_[i] - 1] = matchedEventTimes_[i];
+      time[postEventIndices_[i]] = std::min(matchedEventTimes_[i] + kWeakEps, time.back());
+    }
+  }
+  const std::vector<size_t>& getPostEventIndices() const { return postEventIndices_; }
+
+ private:
+  static std::vector<size_t> findPostEventIndices(const vector_t& eventTimes, const vector_t& time) {
+    std::vector<size_t> out(eventTimes.size());
+    for (size_t i = 0; i < eventTimes.size(); ++i)
+      out[i] = (i == eventTimes.size() - 1 && eventTimes[i] == time.back()) ? time.size() - 1 : upperBoundIndex(time, eventTimes[i]);
+    return out;
+  }
+  void computeSpreadingStrategy(const vector_t& oldTime, const vector_t& oldM, const vector_t& newM) {
+    begin_.clear();
+    end_.clear();
+    valueIdx_.clear();
+    postEventIndices_.clear();
+    matchedEventTimes_.clear();
+    const auto oldPost = findPostEventIndices(oldM, oldTime), newPost = findPostEventIndices(newM, oldTime);
+    for (size_t j = 0; j < oldPost.size(); ++j) {
+      if (newPost[j] < oldPost[j]) {          // backward spreading
+        begin_.push_back(newPost[j]);
+        end_.push_back(std::min(oldPost[j], eraseFrom_));
+        valueIdx_.push_back(oldPost[j]);
+      } else if (newPost[j] > oldPost[j]) {   // forward spreading
+        begin_.push_back(j == 0 ? oldPost[j] : std::max(oldPost[j], newPost[j - 1]));
+        end_.push_back(newPost[j]);
+        valueIdx_.push_back(oldPost[j] - 1);
+      }
+      if (newPost[j] != 0 && newPost[j] < eraseFrom_) {
+        postEventIndices_.push_back(newPost[j]);
+        matchedEventTimes_.push_back(newM[j]);
+      }
+    }
+  }
+  Status status_;
+  size_t eraseFrom_ = 0;
+  std::vector<size_t> begin_, end_, valueIdx_, postEventIndices_;
+  vector_t matchedEventTimes_;
+};
+
+// trajectorySpread(oldModeSchedule, newModeSchedule, primalSolution) (TrajectorySpreadingHelperFunctions.h:124-143), called at the top of
+// SqpSolver::runImpl (SqpSolver.cpp:211-213).  Note the reference's convention clash, reproduced: the SQP's primal solution stores the
+// pre- and post-event samples at the SAME time (toPrimalSolution -> toTime), so the "post-event index" found by upper_bound is the sample
+// AFTER the post-event node and adjustTimeTrajectory moves that sample's time to event + eps, even when the schedules are identical.
+inline TrajectorySpreading::Status trajectorySpread(const ModeSchedule& oldMs, const ModeSchedule& newMs, PrimalSolution& primal,
+                                                   std::vector<size_t>* postEventIndices = nullptr) {
+  TrajectorySpreading ts;
+  const auto status = ts.set(oldMs, newMs, primal.timeTrajectory_);
+  primal.modeSchedule_ = newMs;
+  ts.adjustTrajectory(primal.stateTrajectory_);
+  ts.adjustTrajectory(primal.inputTrajectory_);
+  ts.adjustTimeTrajectory(primal.timeTrajectory_);
+  if (postEventIndices) *postEventIndices = ts.getPostEventIndices();
+  return status;
+}
+
 // One MPC instance in the layout of b200sqp_upload_instances
 struct Instance {
   vector_t x0, x_init, u_init, t_nodes, swing_ref, impact_factor, arm_phase, x_ref;

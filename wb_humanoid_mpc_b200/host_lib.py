@@ -120,6 +120,20 @@ class HostModel:
             self.h = None
 
 
+def trajectory_spread(old_events, old_modes, new_events, new_modes, t, x, u):
+    """C++ trajectorySpread on flat arrays -> (t, x, u, will_truncate, will_spread)"""
+    oe, ne = np.ascontiguousarray(old_events, dtype=np.float64), np.ascontiguousarray(new_events, dtype=np.float64)
+    om, nm = np.ascontiguousarray(old_modes, dtype=np.int32), np.ascontiguousarray(new_modes, dtype=np.int32)
+    t, x, u = (np.array(a, dtype=np.float64, order="C") for a in (t, x, u))
+    fl = np.zeros(2, dtype=np.int32)
+    ip = C.POINTER(C.c_int)
+    L = lib()
+    L.b200host_trajectory_spread.argtypes = [C.c_int, dp, ip, C.c_int, dp, ip, C.c_int, C.c_int, C.c_int, dp, dp, dp, ip]
+    m = _check(L.b200host_trajectory_spread(len(oe), _p(oe), om.ctypes.data_as(ip), len(ne), _p(ne), nm.ctypes.data_as(ip), len(t), x.shape[1], u.shape[1],
+                                            _p(t), _p(x), _p(u), fl.ctypes.data_as(ip)))
+    return t[:m], x[:m], u[:m], bool(fl[0]), bool(fl[1])
+
+
 class HostSqpSolver:
     """b200sqp::host::SqpSolver (C++) driven from Python: the reference-facing call path of bench.py's e2e number."""
 
@@ -135,6 +149,11 @@ class HostSqpSolver:
     def set_command(self, b, t0, x0, cmd, horizon):
         x0, cmd = np.ascontiguousarray(x0, dtype=np.float64), np.ascontiguousarray(cmd, dtype=np.float64)
         _check(lib().b200host_solver_set_command(self.h, self.model.h, b, t0, _p(x0), _p(cmd), horizon))
+
+    def set_trajectory_spread(self, on: bool):
+        L = lib()
+        L.b200host_solver_set_trajectory_spread.argtypes = [C.c_void_p, C.c_int]
+        L.b200host_solver_set_trajectory_spread(self.h, int(on))
 
     def reset(self):
         _check(lib().b200host_solver_reset(self.h))

@@ -308,7 +308,7 @@ def linear_interpolate(t, times, data):
     return alpha * np.asarray(data[idx], float) + (1.0 - alpha) * np.asarray(data[idx + 1], float)
 
 
-def to_primal_solution(t_nodes, events, x, u):
+def to_primal_solution(t_nodes, events, x, u, mode_schedule=None):
     """multiple_shooting::toPrimalSolution (ocs2_oc/src/multiple_shooting/Helpers.cpp:60-82): inputs at PreEvent nodes repeat the previous
     input and the last input is repeated so that time, state and input trajectories have equal length."""
     u = [np.array(r, float) for r in u]
@@ -316,7 +316,109 @@ def to_primal_solution(t_nodes, events, x, u):
         if events[i] == EV_PRE and i > 0:
             u[i] = u[i - 1].copy()
     u.append(u[-1].copy())
-    return dict(t=np.array(t_nodes, float), x=np.array(x, float), u=np.array(u))
+    out = dict(t=np.array(t_nodes, float), x=np.array(x, float), u=np.array(u))
+    if mode_schedule is not None:
+        out["mode_schedule"] = mode_schedule
+    return out
+
+
+class TrajectorySpreading:
+    """ocs2::TrajectorySpreading (ocs2_oc/src/trajectory_adjustment/TrajectorySpreading.cpp:49-166,268-369 and the templates in
+    include/ocs2_oc/trajectory_adjustment/TrajectorySpreading.h:124-183): adapts trajectories computed for an old mode schedule to a new one
+    by spreading the values next to the moved event times and truncating where the mode sequences stop matching."""
+
+    def set(self, old: ModeSchedule, new: ModeSchedule, old_time):
+        ub = lambda a, t: bisect.bisect_right(list(a), t)
+        lb = lambda a, t: bisect.bisect_left(list(a), t)
+        t0, tf = old_time[0], old_time[-1]
+        old_first, old_last = ub(old.event_times, t0), ub(old.event_times, tf)
+        new_first, new_last = ub(new.event_times, t0), ub(new.event_times, tf)
+        old_start, new_start = old_first, new_first
+        w = 0
+        while old_start < len(old.mode_sequence):
+            a = old.mode_sequence[old_start: old_last + 1]
+            b = new.mode_sequence[new_start: new_last + 1]
+            w = 0
+            while w < len(a) and w < len(b) and a[w] == b[w]:      # std::mismatch
+                w += 1
+            if w > 0:
+                break
+            old_start += 1
+        old_m, new_m = [], []
+        self.keep_event_data = (0, 0)
+        if w > 0:
+            old_m = list(old.event_times[old_start: old_start + w - 1])
+            new_m = list(new.event_times[new_start: new_start + w - 1])
+            self.keep_event_data = (old_start - old_first, old_start - old_first + w - 1)
+        if w > 0 and old_start > old_first:
+            old_m.insert(0, old.event_times[old_start - 1])
+            new_m.insert(0, t0 - 1e-4)
+        old_last_matched = (old_start + w - 1 == old_last)
+        new_last_matched = (new_start + w - 1 == new_last)
+        if (not old_last_matched) and (new_last_matched or old.event_times[old_start + w - 1] < new.event_times[new_start + w - 1]):
+            old_m.append(old.event_times[old_start + w - 1])
+            new_m.append(tf + 1e-4 if new_last_matched else new.event_times[new_start + w - 1])
+        self.erase_from = len(old_time)
+        if w == 0:
+            self.erase_from = 0
+        elif not new_last_matched:
+            self.erase_from = lb(old_time, new.event_times[new_start + w - 1])
+        self._strategy(list(old_time), old_m, new_m)
+        self.will_truncate = self.erase_from < len(old_time)
+        self.will_spread = len(self.value_idx) > 0
+        return self
+
+    @staticmethod
+    def _post_event_indices(event_times, time):
+        out = []
+        for i, e in enumerate(event_times):
+            if i == len(event_times) - 1 and e == time[-1]:
+                out.append(len(time) - 1)
+            else:
+                out.append(bisect.bisect_right(time, e))
+        return out
+
+    def _strategy(self, old_time, old_m, new_m):
+        self.begin, self.end, self.value_idx, self.post_event_indices, self.matched_event_times = [], [], [], [], []
+        old_post = self._post_event_indices(old_m, old_time)
+        new_post = self._post_event_indices(new_m, old_time)
+        for j in range(len(old_post)):
+            if new_post[j] < old_post[j]:        # backward spreading
+                self.begin.append(new_post[j])
+                self.end.append(min(old_post[j], self.erase_from))
+                self.value_idx.append(old_post[j])
+            elif new_post[j] > old_post[j]:      # forward spreading
+                self.begin.append(old_post[j] if j == 0 else max(old_post[j], new_post[j - 1]))
+                self.end.append(new_post[j])
+                self.value_idx.append(old_post[j] - 1)
+            if new_post[j] != 0 and new_post[j] < self.erase_from:
+                self.post_event_indices.append(new_post[j])
+                self.matched_event_times.append(new_m[j])
+
+    def adjust_trajectory(self, traj):
+        traj = [np.array(v, float) for v in traj][: self.erase_from]
+        values = [traj[i].copy() for i in self.value_idx]
+        for b, e, v in zip(self.begin, self.end, values):
+            for j in range(b, e):
+                traj[j] = v.copy()
+        return traj
+
+    def adjust_time_trajectory(self, time):
+        time = list(time)[: self.erase_from]
+        for i, te in zip(self.post_event_indices, self.matched_event_times):
+            time[i - 1] = te
+            time[i] = min(te + WEAK_EPS, time[-1])
+        return time
+
+
+def trajectory_spread(old_ms: ModeSchedule, new_ms: ModeSchedule, primal: dict) -> dict:
+    """trajectorySpread(oldModeSchedule, newModeSchedule, primalSolution)
+    (include/ocs2_oc/trajectory_adjustment/TrajectorySpreadingHelperFunctions.h:124-143), called by SqpSolver::runImpl (SqpSolver.cpp:211-213)"""
+    ts = TrajectorySpreading().set(old_ms, new_ms, primal["t"])
+    out = dict(x=np.array(ts.adjust_trajectory(primal["x"])), u=np.array(ts.adjust_trajectory(primal["u"])),
+               t=np.array(ts.adjust_time_trajectory(primal["t"])), post_event_indices=list(ts.post_event_indices), mode_schedule=new_ms,
+               will_truncate=ts.will_truncate, will_spread=ts.will_spread)
+    return out
 
 
 def initialize_state_input_trajectories(model, x0, t_nodes, events, contact, previous=None):
@@ -382,6 +484,8 @@ def build_instance(model: dict, x0, t0=0.0, horizon=None, dt=None, gait="stance"
             impact[i, c] = planner.impact_factor(c, t)
         arm[i] = math.sin(2 * math.pi * (phase_variable(ms, t) - 0.15))
         xref[i] = interp_targets(tt, ts, t)
+    if previous is not None and previous.get("mode_schedule") is not None:
+        previous = trajectory_spread(previous["mode_schedule"], ms, previous)   # SqpSolver.cpp:211-213
     x_init, u_init = initialize_state_input_trajectories(model, x0, t_nodes, events, contact, previous)
     return dict(x0=x0, x_init=x_init, u_init=u_init, t_nodes=t_nodes, node_event=events, contact_flags=contact, swing_ref=swing,
                 impact_factor=impact, arm_phase=arm, x_ref=xref, mode_schedule=ms)
