@@ -49,3 +49,61 @@ def test_large_batch_properties():
     g = np.array([0, 0, -9.81, 0, 0, 0])
     assert np.allclose(f2[:, :6] - g, 2.0 * (f0[:, :6] - g), atol=1e-9)
     assert np.allclose(f2[:, 6:], f0[:, 6:], atol=1e-12)
+
+
+def test_centroidal_lq_n100_gpu_vs_cpu():
+    """BASELINE configs[1] in the form this round supports: G1 full centroidal dynamics, N = 100, batch 1, fp64, GPU against the CPU oracle.
+    The LQ problem is the RK4 transcription of the centroidal flow map along a nominal stance trajectory (dt = 0.02 s of the centroidal
+    task.info, wrenches held at weight compensation, joint velocities as the 23 free inputs -- the projected input dimension of the real
+    problem) with the centroidal Q / R / Q_final weights.  GPU side: Jacobians from b200sqp_centroidal_flow_map, QP by the Riccati kernel;
+    CPU side: oracle Jacobians (70-wide duals) and the oracle Riccati recursion.  The centroidal cost / constraint terms are not built yet
+    (DESIGN.md §7), so this is the dynamics + QP part of that configuration."""
+    from wb_humanoid_mpc_b200.qp import BatchedQp
+
+    model = model_loader.load_packaged_model()
+    cen = model["centroidal"]
+    wb = orc.WbOracle(model)
+    N, nx, nu, dt = 100, 35, 23, cen["dt"]
+    rng = np.random.default_rng(4)
+    m = sum(model["mass"])
+    X = np.tile(np.array(cen["x_init"], float), (N, 1))
+    X[:, 12:] += 0.05 * np.sin(np.linspace(0, 6, N))[:, None] * rng.uniform(-1, 1, 23)[None, :]
+    U = np.zeros((N, 35))
+    U[:, 2] = U[:, 8] = m * 9.81 / 2
+    U[:, 12:] = 0.2 * np.cos(np.linspace(0, 6, N))[:, None] * rng.uniform(-1, 1, 23)[None, :]
+    f_g, A_g, B_g = centroidal.flow_map(model, X, U)
+    Q, R, Qf = np.diag(cen["Q_diag"]), np.diag(cen["R_diag"][12:]), np.diag(cen["Qf_diag"])
+    xt = np.array(cen["x_init"], float)
+    xt[6] += 0.1     # track a pose 10 cm ahead
+
+    def transcribe(Ac, Bc, f):
+        A, B, b = np.zeros((N, nx, nx)), np.zeros((N, nx, nu)), np.zeros((N, nx))
+        for k in range(N):
+            Ad, Bd, _, _ = orc.rk4_sensitivity_linear(Ac[k], Bc[k][:, 12:], np.zeros(nx), np.zeros(nu), dt)
+            A[k], B[k] = Ad, Bd
+            xn = X[k + 1] if k + 1 < N else X[k]
+            b[k] = X[k] + dt * f[k] - xn      # defect of the nominal trajectory (first order in dt is enough for a parity problem)
+        return A, B, b
+
+    Qs = np.tile(Q, (N + 1, 1, 1))
+    Qs[N] = Qf
+    Ss = np.zeros((N, nu, nx))
+    Rs = np.tile(R, (N, 1, 1))
+    qs = np.array([Qs[k] @ ((X[min(k, N - 1)]) - xt) for k in range(N + 1)])
+    rs = np.array([R @ U[k, 12:] for k in range(N)])
+    dx0 = np.zeros(nx)
+    dx0[6:9] = [0.01, -0.01, 0.005]
+    Ag, Bg, bg = transcribe(A_g, B_g, f_g)
+    # oracle side
+    lin = [wb.cen_flow_map_lin(X[k], U[k]) for k in range(N)]
+    Ao, Bo, bo = transcribe(np.array([l[1] for l in lin]), np.array([l[2] for l in lin]), np.array([l[0] for l in lin]))
+    ref = orc.riccati(Ao, Bo, bo, Qs, Ss, Rs, qs, rs, dx0)
+    qp = BatchedQp(1, N, nx, nu)
+    qp.upload(Ag[None], Bg[None], bg[None], Qs[None], Ss[None], Rs[None], qs[None], rs[None], dx0[None], np.full((1, N), nu, dtype=np.int32))
+    qp.solve()
+    sol = qp.download()
+    for key, tol in (("dx", 1e-8), ("du", 1e-8), ("K", 1e-8), ("P", 1e-8), ("p", 1e-8)):
+        a, b_ = sol[key][0], ref[key]
+        err = np.max(np.abs(a - b_)) / max(1.0, np.max(np.abs(b_)))
+        assert err < tol, (key, err)
+    assert np.max(np.abs(sol["dx"][0][0] - dx0)) < 1e-14 and np.max(np.abs(sol["dx"][0])) > 1e-3

@@ -259,6 +259,7 @@ G1_REL = dict(
     task="robot_models/unitree_g1/g1_wb_mpc/config/mpc/task.info",
     reference="robot_models/unitree_g1/g1_wb_mpc/config/command/reference.info",
     gait="humanoid_nmpc/humanoid_common_mpc/config/command/gait.info",
+    centroidal_task="robot_models/unitree_g1/g1_centroidal_mpc/config/mpc/task.info",
 )
 
 
@@ -409,9 +410,28 @@ def build_wb_model(urdf_path, task_path, reference_path=None, gait_path=None) ->
     return model
 
 
+def centroidal_settings(task_path, nj: int) -> dict:
+    """The centroidal MPC's weights and grid (robot_models/unitree_g1/g1_centroidal_mpc/config/mpc/task.info): state = (h/m 6, base pose 6,
+    joints nj), input = (wrench_l 6, wrench_r 6, joint velocities nj).  Same kinematic tree and contact frames as the whole-body model."""
+    task = parse_info(task_path)
+    nx = nu = 12 + nj
+    return dict(
+        nx=nx, nu=nu,
+        Q_diag=np.diag(info_matrix(task, "Q", nx, nx)).tolist(),
+        R_diag=np.diag(info_matrix(task, "R", nu, nu)).tolist(),
+        Qf_diag=(np.diag(info_matrix(task, "Q_final", nx, nx)) * info_float(task, "terminalCostScaling")).tolist(),
+        x_init=info_matrix(task, "initialState", nx, 1)[:, 0].tolist(),
+        dt=info_float(task, "multiple_shooting.dt"),
+        timeHorizon=info_float(task, "mpc.timeHorizon"),
+        centroidalModelType=int(info_float(task, "centroidalModelType")),
+    )
+
+
 def build_g1_wb_from_reference(reference_root="/root/reference") -> dict:
     r = Path(reference_root)
-    return build_wb_model(r / G1_REL["urdf"], r / G1_REL["task"], r / G1_REL["reference"], r / G1_REL["gait"])
+    m = build_wb_model(r / G1_REL["urdf"], r / G1_REL["task"], r / G1_REL["reference"], r / G1_REL["gait"])
+    m["centroidal"] = centroidal_settings(r / G1_REL["centroidal_task"], m["nj"])
+    return m
 
 
 DATA_DIR = Path(__file__).resolve().parent / "data"
