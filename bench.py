@@ -278,8 +278,10 @@ def main():
         host_s = max_over_ranks(time.perf_counter() - t0)
         barrier()
         dx = max(float(np.abs(hs.primal_solution(b)["x"] - sol["x"][b]).max()) for b in range(0, args.batch, max(1, args.batch // 8)))
+        hb = hs.benchmarks()
         host_api = {"value": total_solves / host_s, "unit": "solves/s", "call": "b200sqp::host::SqpSolver::run (C++ host layer, instances built on host threads)",
-                    "max_abs_diff_x_vs_c_abi_path": dx}
+                    "max_abs_diff_x_vs_c_abi_path": dx,
+                    "last_run_ms": dict(zip(["pre_run", "pack", "upload", "solve", "download", "unpack"], [round(float(v), 3) for v in hb[4:10]]))}
         hs.close()
         hm.close()
     except Exception as e:   # the host layer is optional for the bench line

@@ -17,6 +17,7 @@
 // the horizon) are grouped by node count; each group owns one library handle and is solved with one b200sqp_solve.
 // The per-instance host work (reference manager, time grid, warm start) runs on a pool of std::threads.
 #pragma once
+#include <chrono>
 #include <map>
 #include <memory>
 #include <thread>
@@ -37,6 +38,9 @@ struct StepInfo {  // sqp::StepInfo (SqpSolverStatus.h:42-57)
 };
 struct Benchmarks {  // SqpSolver::getBenchmarks (ms of the last run, summed over node-count groups)
   double linearQuadraticApproximation = 0, solveQp = 0, linesearch = 0, projectionShareOfLq = 0;
+  // host wall-clock split of the last run(): preRun (reference managers, time grids, warm start), packing into the staging arrays,
+  // b200sqp_upload_instances, b200sqp_solve, b200sqp_download, unpacking into PrimalSolution / iteration logs
+  double hostPreRun = 0, hostPack = 0, upload = 0, solve = 0, download = 0, hostUnpack = 0;
 };
 struct ValueFunction {  // ScalarFunctionQuadraticApproximation of getValueFunction: dfdxx (nx*nx, column-major), dfdx
   vector_t dfdxx, dfdx;
@@ -79,6 +83,8 @@ class SqpSolver {
   void run(double initTime, const std::vector<vector_t>& initStates, double finalTime) {
     if (static_cast<int>(initStates.size()) != batch_) throw std::invalid_argument("[b200sqp::host::SqpSolver] run: one initial state per instance");
     std::vector<Instance> inst(batch_);
+    bench_ = Benchmarks();
+    const auto tPre = now();
     parallelFor(batch_, [&](int b) {
       rm_[b].preSolverRun(initTime, finalTime);
       // Trajectory spread of primalSolution_ (SqpSolver.cpp:211-213)
@@ -89,7 +95,7 @@ class SqpSolver {
     // group by node count
     std::map<int, std::vector<int>> members;
     for (int b = 0; b < batch_; ++b) members[inst[b].n_nodes()].push_back(b);
-    bench_ = Benchmarks();
+    bench_.hostPreRun = since(tPre);
     for (auto& kv : members) solveGroup(kv.first, kv.second, inst);
   }
 
@@ -163,6 +169,9 @@ class SqpSolver {
     if (!p) throw std::runtime_error(std::string("[SqpSolver] ") + b200sqp_last_error());
     return p;
   }
+  using clock_t_ = std::chrono::steady_clock;
+  static clock_t_::time_point now() { return clock_t_::now(); }
+  static double since(clock_t_::time_point t) { return std::chrono::duration<double, std::milli>(now() - t).count(); }
   static void check(int rc) {
     if (rc != 0) throw std::runtime_error(std::string("[SqpSolver] ") + b200sqp_last_error());
   }
@@ -214,6 +223,7 @@ class SqpSolver {
     }
     double *x0 = G.st.x0, *xi = G.st.xi, *ui = G.st.ui, *tn = G.st.tn, *sw = G.st.sw, *imp = G.st.imp, *arm = G.st.arm, *xr = G.st.xr;
     uint8_t *ev = G.st.ev, *cf = G.st.cf;
+    auto tm = now();
     parallelFor(Bg, [&](int s) {
       const Instance& I = inst[members[s]];
       std::copy(I.x0.begin(), I.x0.end(), x0 + static_cast<size_t>(s) * nx);
@@ -227,8 +237,14 @@ class SqpSolver {
       std::copy(I.arm_phase.begin(), I.arm_phase.end(), arm + static_cast<size_t>(s) * n);
       std::copy(I.x_ref.begin(), I.x_ref.end(), xr + static_cast<size_t>(s) * n * nx);
     });
+    bench_.hostPack += since(tm);
+    tm = now();
     check(b200sqp_upload_instances(G.h, x0, xi, ui, tn, ev, cf, sw, imp, arm, xr));
+    bench_.upload += since(tm);
+    tm = now();
     check(b200sqp_solve(G.h, nullptr));
+    bench_.solve += since(tm);
+    tm = now();
     double *x = G.st.x, *u = G.st.u;
     const int iters = settings_.sqp_iteration;
     std::vector<b200sqp_iter_log> log(static_cast<size_t>(Bg) * iters);
@@ -239,6 +255,8 @@ class SqpSolver {
       G.p.resize(static_cast<size_t>(Bg) * n * nx);
       check(b200sqp_download_value_function(G.h, G.P.data(), G.p.data()));
     }
+    bench_.download += since(tm);
+    tm = now();
     float ms[4];
     check(b200sqp_get_stage_times(G.h, ms));
     bench_.linearQuadraticApproximation += ms[0];
@@ -268,6 +286,7 @@ class SqpSolver {
         log_[b].push_back(si);
       }
     });
+    bench_.hostUnpack += since(tm);
   }
 
   HostModel model_;

@@ -203,6 +203,12 @@ int b200host_solver_benchmarks(void* s, double* ms) {
   ms[1] = b.solveQp;
   ms[2] = b.linesearch;
   ms[3] = b.projectionShareOfLq;
+  ms[4] = b.hostPreRun;
+  ms[5] = b.hostPack;
+  ms[6] = b.upload;
+  ms[7] = b.solve;
+  ms[8] = b.download;
+  ms[9] = b.hostUnpack;
   return 0;
 }
 int b200host_solver_value_function(void* s, int b, double t, const double* x, int nx, double* dfdxx, double* dfdx) {

@@ -175,7 +175,8 @@ class HostSqpSolver:
         return out[:k]
 
     def benchmarks(self):
-        ms = np.zeros(4)
+        """ms: [LQ, QP, line search, projection share | host preRun, pack, upload, solve, download, unpack]"""
+        ms = np.zeros(10)
         lib().b200host_solver_benchmarks(self.h, _p(ms))
         return ms
 
