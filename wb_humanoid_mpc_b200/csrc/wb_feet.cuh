@@ -137,24 +137,6 @@ HD void footPhaseLocalTangents(Par P, const WbDeviceModel& m, const double* x, c
   }
 }
 
-// ---- dense foot Jacobians: JF[c][k + FQ*d] = scatter(JFl) + J_fb * G   (items = (c, d)) ----------------------------------------------
-HD void footPhaseAssemble(Par P, const WbDeviceModel& m, const double* JFl, const double* G /*6 x 93, ld 6*/, double* JF) {
-  for (int it = P.tid; it < 2 * NZ; it += P.nt) {
-    const int c = it / NZ, d = it % NZ;
-    double col[FQ];
-    for (int k = 0; k < FQ; ++k) col[k] = 0.0;
-    for (int l = 0; l < 30; ++l)
-      if (footLocalToZ(m, c, l) == d)
-        for (int k = 0; k < FQ; ++k) col[k] += JFl[(c * FLOC + l) * FQ + k];
-    for (int j = 0; j < 6; ++j) {
-      const double g = G[j + 6 * d];
-      const double* jb = JFl + (c * FLOC + 30 + j) * FQ;
-      for (int k = 12; k < FQ; ++k) col[k] = fma(jb[k], g, col[k]);
-    }
-    for (int k = 0; k < FQ; ++k) JF[(c * NZ + d) * FQ + k] = col[k];
-  }
-}
-
 // all operational-frame positions in world coordinates (value-only: FP[f][3]) and, optionally, their tangents w.r.t. th(3) and the
 // 12 leg joints: DFP[f][15][3]  (base translation cancels in all pairwise distances)
 template <bool DERIV>
