@@ -27,40 +27,6 @@ HD void par_copy(Par P, double* __restrict__ dst, const double* __restrict__ src
   for (; i < n; i += P.nt) dst[i] = src[i];
 }
 
-// C(MxN, ldc) = (ACC ? C : 0) + alpha * op(A) * B ; op(A) = A (MxK, lda) or A^T (A stored KxM, lda) ; B is KxN (ldb)
-template <int TM, int TN, bool TRANS_A, bool ACC, class PAR>
-HD void par_gemm(PAR P, int M, int N, int K, double alpha, const double* __restrict__ A, int lda, const double* __restrict__ B, int ldb,
-                 double* __restrict__ C, int ldc) {
-  const int tilesM = (M + TM - 1) / TM, tilesN = (N + TN - 1) / TN;
-  for (int t = P.tid; t < tilesM * tilesN; t += P.nt) {
-    const int i0 = (t % tilesM) * TM, j0 = (t / tilesM) * TN;
-    double acc[TM][TN];
-#pragma unroll
-    for (int i = 0; i < TM; ++i)
-#pragma unroll
-      for (int j = 0; j < TN; ++j) acc[i][j] = 0.0;
-    for (int k = 0; k < K; ++k) {
-      double a[TM], b[TN];
-#pragma unroll
-      for (int i = 0; i < TM; ++i) a[i] = (i0 + i < M) ? (TRANS_A ? A[k + (i0 + i) * lda] : A[(i0 + i) + k * lda]) : 0.0;
-#pragma unroll
-      for (int j = 0; j < TN; ++j) b[j] = (j0 + j < N) ? B[k + (j0 + j) * ldb] : 0.0;
-#pragma unroll
-      for (int i = 0; i < TM; ++i)
-#pragma unroll
-        for (int j = 0; j < TN; ++j) acc[i][j] = fma(a[i], b[j], acc[i][j]);
-    }
-#pragma unroll
-    for (int i = 0; i < TM; ++i)
-#pragma unroll
-      for (int j = 0; j < TN; ++j)
-        if (i0 + i < M && j0 + j < N) {
-          double* c = &C[(i0 + i) + (j0 + j) * ldc];
-          *c = ACC ? fma(alpha, acc[i][j], *c) : alpha * acc[i][j];
-        }
-  }
-}
-
 // y(M) = (ACC ? y : 0) + alpha * op(A) x
 template <bool TRANS_A, bool ACC, class PAR>
 HD void par_gemv(PAR P, int M, int K, double alpha, const double* __restrict__ A, int lda, const double* __restrict__ x, double* __restrict__ y) {
@@ -75,7 +41,7 @@ HD void par_gemv(PAR P, int M, int K, double alpha, const double* __restrict__ A
 
 namespace b200sqp {
 
-// Tensor-core variant of par_gemm: fp64 DMMA (mma.sync.aligned.m8n8k4.f64) on column-major operands in shared or global memory.
+// C(MxN, ldc) = (ACC ? C : 0) + alpha * op(A) * B ; op(A) = A (MxK, lda) or A^T (A stored KxM, lda) ; B is KxN (ldb), on the fp64 tensor path: DMMA (mma.sync.aligned.m8n8k4.f64) on column-major operands in shared or global memory.
 // One work item = one 8-row strip x NG column tiles, so the A fragment is loaded once per k-step and reused NG times.
 // Edges are handled by predicated (zero-filled) fragment loads and predicated stores; no padding requirements on the operands.
 // On the host (development harness) the same contraction runs as scalar loops.
