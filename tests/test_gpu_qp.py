@@ -150,3 +150,35 @@ def test_kkt_residual_full_size():
         term = Q[i, N] @ dx[N] + q[i, N] - lam[N]
         worst = max(worst, np.abs(term).max() / max(1.0, np.abs(lam[N]).max()))
         assert worst < 1e-9, worst
+
+
+def test_cluster_variant_is_bitwise_identical_and_deterministic():
+    """K2 dispatches small batches to the cluster variant (4 SMs per instance, exchanges through distributed shared memory).  It performs the
+    same tile arithmetic as the one-CTA kernel, so every output must agree BIT FOR BIT, on every repetition (a lost or reordered remote store
+    would show up as a difference)."""
+    import os
+
+    from wb_humanoid_mpc_b200.qp import BatchedQp
+
+    rng = np.random.default_rng(33)
+    nx, numax, N, Bn = 58, 23, 115, 8
+    pattern = np.array([23 if k % 5 else (0 if k % 10 == 0 else 21) for k in range(N)], dtype=np.int32)   # includes nu = 0 (event) stages
+    data, nu, dx0 = _random_batch(rng, Bn, N, nx, numax, nu_pattern=pattern)
+    qp = BatchedQp(Bn, N, nx, numax)
+    qp.upload(*data, dx0, nu)
+    old = os.environ.get("B200SQP_NO_CLUSTER")
+    try:
+        os.environ["B200SQP_NO_CLUSTER"] = "1"
+        qp.solve()
+        ref = qp.download()
+        os.environ["B200SQP_NO_CLUSTER"] = "0"
+        for rep in range(25):
+            qp.solve()
+            sol = qp.download()
+            for key in ("dx", "du", "K", "k", "P", "p"):
+                assert np.array_equal(sol[key], ref[key]), (rep, key, np.abs(sol[key] - ref[key]).max())
+    finally:
+        if old is None:
+            os.environ.pop("B200SQP_NO_CLUSTER", None)
+        else:
+            os.environ["B200SQP_NO_CLUSTER"] = old

@@ -5,12 +5,14 @@
 
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <new>
 #include <string>
 #include <vector>
 
 #include "riccati.cuh"
+#include "riccati_cluster.cuh"
 #ifdef B200SQP_WITH_WB
 #include "wb_solver.cuh"
 #include "cen_dynamics.cuh"
@@ -41,6 +43,27 @@ int select_device(int device) {
   if (device < 0 || device >= n) return fail(B200SQP_EINVAL, "device %d out of range (%d devices)", device, n);
   CUDA_TRY(cudaSetDevice(device));
   return 0;
+}
+
+// K2 dispatch: the cluster variant (RC SMs per instance) for small batches, else one CTA per instance.
+// B200SQP_NO_CLUSTER=1 forces the one-CTA kernel (tests exercise both).
+void launch_riccati(const b200sqp::QpDeviceView& v, cudaStream_t st) {
+  static int sms = 0;
+  if (sms == 0) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  }
+  const char* no = std::getenv("B200SQP_NO_CLUSTER");
+  // measured on B200: the cluster variant wins while at most ~half of the SMs are taken by clusters
+  const bool cluster = !(no && no[0] == '1') && v.B * b200sqp::RC * 2 <= sms;
+  if (cluster) {
+    const size_t smem = b200sqp::riccati_cluster_smem_doubles(v.nx, v.numax) * sizeof(double);
+    b200sqp::riccati_cluster_kernel<<<v.B * b200sqp::RC, 256, smem, st>>>(v);
+  } else {
+    const size_t smem = b200sqp::riccati_smem_doubles(v.nx, v.numax) * sizeof(double);
+    b200sqp::riccati_kernel<<<v.B, 256, smem, st>>>(v);
+  }
 }
 }  // namespace
 
@@ -98,6 +121,9 @@ int b200sqp_qp_create(int device, int batch, int N, int nx, int nu_max, b200sqp_
   A_(cudaEventCreate(&qp->ev1));
   if (e == cudaSuccess)
     e = cudaFuncSetAttribute(b200sqp::riccati_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
+  if (e == cudaSuccess)
+    e = cudaFuncSetAttribute(b200sqp::riccati_cluster_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                             static_cast<int>(b200sqp::riccati_cluster_smem_doubles(nx, nu_max) * sizeof(double)));
   if (e != cudaSuccess) {
     b200sqp_qp_destroy(qp);
     return fail(e == cudaErrorMemoryAllocation ? B200SQP_ENOMEM : B200SQP_ENODEV, "qp_create: %s", cudaGetErrorString(e));
@@ -178,8 +204,7 @@ int b200sqp_qp_solve(b200sqp_qp qp, double reg_prim, int keep_P, void* stream) {
   CUDA_TRY(cudaEventRecord(qp->ev0, st));
   CUDA_TRY(cudaMemsetAsync(qp->K, 0, bn * qp->numax * qp->nx * sizeof(double), st));
   CUDA_TRY(cudaMemsetAsync(qp->kff, 0, bn * qp->numax * sizeof(double), st));
-  const size_t smem = b200sqp::riccati_smem_doubles(qp->nx, qp->numax) * sizeof(double);
-  b200sqp::riccati_kernel<<<qp->B, 256, smem, st>>>(v);
+  launch_riccati(v, st);
   CUDA_TRY(cudaGetLastError());
   CUDA_TRY(cudaEventRecord(qp->ev1, st));
   qp->solved = true;
