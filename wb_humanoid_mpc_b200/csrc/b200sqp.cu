@@ -45,6 +45,18 @@ int select_device(int device) {
   return 0;
 }
 
+cudaError_t set_riccati_smem_attributes(int nx, int numax) {
+  const int one = static_cast<int>(b200sqp::riccati_smem_doubles(nx, numax) * sizeof(double));
+  const int clu = static_cast<int>(b200sqp::riccati_cluster_smem_doubles(nx, numax) * sizeof(double));
+  cudaError_t e = cudaFuncSetAttribute(b200sqp::riccati_kernel<0, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, one);
+  if (e == cudaSuccess) e = cudaFuncSetAttribute(b200sqp::riccati_cluster_kernel<0, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, clu);
+  if (nx == 58 && numax == 23) {
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(b200sqp::riccati_kernel<58, 23>, cudaFuncAttributeMaxDynamicSharedMemorySize, one);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(b200sqp::riccati_cluster_kernel<58, 23>, cudaFuncAttributeMaxDynamicSharedMemorySize, clu);
+  }
+  return e;
+}
+
 // K2 dispatch: the cluster variant (RC SMs per instance) for small batches, else one CTA per instance.
 // B200SQP_NO_CLUSTER=1 forces the one-CTA kernel (tests exercise both).
 void launch_riccati(const b200sqp::QpDeviceView& v, cudaStream_t st) {
@@ -57,12 +69,15 @@ void launch_riccati(const b200sqp::QpDeviceView& v, cudaStream_t st) {
   const char* no = std::getenv("B200SQP_NO_CLUSTER");
   // measured on B200: the cluster variant wins while at most ~half of the SMs are taken by clusters
   const bool cluster = !(no && no[0] == '1') && v.B * b200sqp::RC * 2 <= sms;
+  const bool wb = (v.nx == 58 && v.numax == 23);   // the whole-body sizes have a compile-time instantiation
   if (cluster) {
     const size_t smem = b200sqp::riccati_cluster_smem_doubles(v.nx, v.numax) * sizeof(double);
-    b200sqp::riccati_cluster_kernel<<<v.B * b200sqp::RC, 256, smem, st>>>(v);
+    if (wb) b200sqp::riccati_cluster_kernel<58, 23><<<v.B * b200sqp::RC, 256, smem, st>>>(v);
+    else b200sqp::riccati_cluster_kernel<0, 0><<<v.B * b200sqp::RC, 256, smem, st>>>(v);
   } else {
     const size_t smem = b200sqp::riccati_smem_doubles(v.nx, v.numax) * sizeof(double);
-    b200sqp::riccati_kernel<<<v.B, 256, smem, st>>>(v);
+    if (wb) b200sqp::riccati_kernel<58, 23><<<v.B, 256, smem, st>>>(v);
+    else b200sqp::riccati_kernel<0, 0><<<v.B, 256, smem, st>>>(v);
   }
 }
 }  // namespace
@@ -120,10 +135,7 @@ int b200sqp_qp_create(int device, int batch, int N, int nx, int nu_max, b200sqp_
   A_(cudaEventCreate(&qp->ev0));
   A_(cudaEventCreate(&qp->ev1));
   if (e == cudaSuccess)
-    e = cudaFuncSetAttribute(b200sqp::riccati_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
-  if (e == cudaSuccess)
-    e = cudaFuncSetAttribute(b200sqp::riccati_cluster_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                             static_cast<int>(b200sqp::riccati_cluster_smem_doubles(nx, nu_max) * sizeof(double)));
+    e = set_riccati_smem_attributes(nx, nu_max);
   if (e != cudaSuccess) {
     b200sqp_qp_destroy(qp);
     return fail(e == cudaErrorMemoryAllocation ? B200SQP_ENOMEM : B200SQP_ENODEV, "qp_create: %s", cudaGetErrorString(e));

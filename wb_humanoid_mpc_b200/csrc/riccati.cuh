@@ -76,10 +76,13 @@ __device__ __forceinline__ void async_copy(double* dst, const double* src, int n
   }
 }
 
+// NXT / NMT > 0: sizes fixed at compile time (the whole-body instantiation <58, 23>: index arithmetic folds to shifts and multiplies);
+// 0: read from the view (generic QP interface)
+template <int NXT, int NMT>
 __global__ void __launch_bounds__(256, 1) riccati_kernel(QpDeviceView v) {
   extern __shared__ double sm[];
   const int inst = blockIdx.x;
-  const int nx = v.nx, nm = v.numax, N = v.N, nx1 = nx + 1;
+  const int nx = NXT ? NXT : v.nx, nm = NMT ? NMT : v.numax, N = v.N, nx1 = nx + 1;
   const RicLayout L = riccati_layout(nx, nm);
   double* PQ[2] = {sm, sm + L.pq};
   double* AB[2] = {sm + 2 * L.pq, sm + 2 * L.pq + L.ab};

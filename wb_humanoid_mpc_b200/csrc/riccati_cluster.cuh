@@ -40,12 +40,13 @@ __device__ __forceinline__ void gather_columns(cg::cluster_group& cluster, doubl
   }
 }
 
+template <int NXT, int NMT>
 __global__ void __cluster_dims__(RC, 1, 1) __launch_bounds__(256, 1) riccati_cluster_kernel(QpDeviceView v) {
   extern __shared__ double sm[];
   cg::cluster_group cluster = cg::this_cluster();
   const int rank = static_cast<int>(cluster.block_rank());
   const int inst = blockIdx.x / RC;
-  const int nx = v.nx, nm = v.numax, N = v.N, nx1 = nx + 1;
+  const int nx = NXT ? NXT : v.nx, nm = NMT ? NMT : v.numax, N = v.N, nx1 = nx + 1;
   const RicLayout L = riccati_layout(nx, nm);
   double* PQ[2] = {sm, sm + L.pq};
   double* AB[2] = {sm + 2 * L.pq, sm + 2 * L.pq + L.ab};
