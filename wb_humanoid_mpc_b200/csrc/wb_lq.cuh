@@ -443,8 +443,9 @@ HD void costPhaseRowScalars(Par P, const WbDeviceModel& m, const NodeIn& n, cons
 // weighted row entries over the compact column support, one item per (row, compact column)
 HD void costPhaseRowEntries(Par P, const WbDeviceModel& m, const NodeIn& n, const DynWs& w, const double* DFP, RowWs rw, double* JU) {
   const int nm0 = momRows(n, 0), nm = nm0 + momRows(n, 1), nr = nm + collRows(n);
-  for (int it = P.tid; it < nr * NUC; it += P.nt) {
-    const int r = it % nr, i = it / nr;
+  for (int it = P.tid; it < JU_MAX * NUC; it += P.nt) {
+    const int r = it % JU_MAX, i = it / JU_MAX;   // compile-time divisors; rows beyond the active count are skipped
+    if (r >= nr) continue;
     double e = 0.0;
     if (r < nm) {
       const int c = (r < nm0) ? 0 : 1, lr = r - (c ? nm0 : 0);
