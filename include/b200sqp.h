@@ -185,6 +185,28 @@ int b200sqp_download_value_function(b200sqp_handle h, double* P, double* p);
 int b200sqp_centroidal_flow_map(const b200sqp_model_desc* model, int batch, const double* x, const double* u, double* xdot, double* dfdx,
                                 double* dfdu, int device);
 
+/* ------------------------------------------------------------------------------------------------------------------
+ * (3) Centroidal SQP solver: replaces ocs2::SqpSolver for the humanoid centroidal OCP
+ *     (OCP wiring humanoid_nmpc/humanoid_centroidal_mpc/src/CentroidalMpcInterface.cpp:150-237; BASELINE configs 0-1).
+ *     The handle is a b200sqp_handle: set_batch / upload_instances / reset / solve / download / download_value_function /
+ *     download_stage_blocks / get_stage_times work on it unchanged, with nx = nu = 12 + nj in every array of the ABI
+ *     (x = normalized momentum 6, base position 3, Euler ZYX 3, joints nj; u = wrench_l 6, wrench_r 6, joint velocities nj).
+ *     `model` is filled from the centroidal task.info: Q_diag / R_diag / Qf_diag hold 12+nj entries, foot_cost_w[0..11] is
+ *     EndEffectorKinematicsWeights::toVector() (position, orientation, linear velocity, angular velocity), foot_gain_pos_z / foot_gain_ori
+ *     configure the stance twist and swing normal-velocity constraints, frame `torso_frame` of the frame table is the task-space link.
+ *     swing_ref[..][2] (the swing-z acceleration) is ignored by this OCP.
+ * ------------------------------------------------------------------------------------------------------------------ */
+typedef struct b200sqp_cen_desc {
+  int32_t torso_frame;          /* index into model.frame_body / frame_p: link of the EndEffectorKinematicsQuadraticCost (task_space_costs) */
+  double torso_R[9];            /* rotation of that link frame in its body's joint frame, row-major */
+  double torso_w[12];           /* its EndEffectorKinematicsWeights */
+  double icp_weight;            /* icp_cost_weights.icpErrorWeight */
+  int32_t torque_joint[2][6];   /* ExternalTorqueQuadraticCostAD: active joints (0-based joint indices) per contact ... */
+  double torque_w[2][6];        /* ... and their weights (left_leg_torque_cost / right_leg_torque_cost) */
+} b200sqp_cen_desc;
+int b200sqp_cen_create(const b200sqp_model_desc* model, const b200sqp_cen_desc* cen, const b200sqp_settings* settings, int device,
+                       b200sqp_handle* out);
+
 /* Stage blocks of the last LQ approximation, for block-level parity tests:
  *   which = 0 raw (before projection): A [nx*nx] B [nx*nu] b [nx] Q S(nu x nx) R q r C(nc_max x nx) D(nc_max x nu) e nc
  *   see b200sqp_stage_layout for offsets. */

@@ -9,6 +9,7 @@
 #ifdef ORC_WITH_WB
 #include "wb_problem.hpp"
 #include "cen_dynamics.hpp"
+#include "cen_problem.hpp"
 #endif
 
 using namespace orc;

@@ -299,6 +299,43 @@ class WbOracle:
         return [unpack_raw_blocks(out[i], self.nx, self.nu) for i in range(n_nodes - 1)]
 
 
+class CenOracle(WbOracle):
+    """One centroidal OCP instance on the CPU oracle (oracle/cen_problem.hpp).  cost / cost_quad / eq_constraint(_lin) / sqp / last_* are the
+    generic entry points of the base class; the whole-body-only queries are not available."""
+
+    def __init__(self, model: dict):
+        from wb_humanoid_mpc_b200 import abi
+
+        assert model.get("kind") == "centroidal"
+        self.model = model
+        self.desc = abi.model_desc(model)
+        self.cdesc = abi.cen_desc(model)
+        self.nx, self.nu, self.nj = model["nx"], model["nu"], model["nj"]
+        L = lib()
+        L.orc_cen_create.restype = C.c_void_p
+        L.orc_wb_total_mass.restype = C.c_double
+        L.orc_wb_cost.restype = C.c_double
+        L.orc_wb_cost_quad.restype = C.c_double
+        self.h = C.c_void_p(L.orc_cen_create(C.byref(self.desc), C.byref(self.cdesc)))
+        self.L = L
+        self.n_nodes = 0
+
+    def flow_map(self, x, u):
+        return self.flow_map_lin(x, u)[0]
+
+    def task_space(self, x, u):
+        feet, torso, com, v = np.zeros((2, 12)), np.zeros(13), np.zeros(3), np.zeros(6 + self.nj)
+        self.L.orc_cen_task_space(self.h, _p(F(x)), _p(F(u)), _p(feet), _p(torso), _p(com), _p(v))
+        fs = [dict(pos=f[0:3], oriErr=f[3:6], vlin=f[6:9], vang=f[9:12]) for f in feet]
+        return fs, dict(pos=torso[0:3], quat=torso[3:7], vlin=torso[7:10], vang=torso[10:13]), com, v
+
+    def residuals(self, k, x, u, jacobian=True):
+        nz = self.nx + self.nu
+        r, J = np.zeros(64), np.zeros((64, nz))
+        n = self.L.orc_cen_residuals(self.h, C.c_int(k), _p(F(x)), _p(F(u)), _p(r), _p(J) if jacobian else None)
+        return r[:n].copy(), J[:n].copy()
+
+
 def unpack_raw_blocks(p, nx, nu):
     """Layout shared by the oracle (orc_wb_last_raw_blocks) and the CUDA path (b200sqp_download_stage_blocks which=0)."""
     o = 0

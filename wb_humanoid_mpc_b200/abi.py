@@ -55,6 +55,17 @@ class ModelDesc(C.Structure):
     ]
 
 
+class CenDesc(C.Structure):
+    _fields_ = [
+        ("torso_frame", C.c_int32),
+        ("torso_R", C.c_double * 9),
+        ("torso_w", C.c_double * 12),
+        ("icp_weight", C.c_double),
+        ("torque_joint", (C.c_int32 * 6) * 2),
+        ("torque_w", (C.c_double * 6) * 2),
+    ]
+
+
 class Settings(C.Structure):
     _fields_ = [
         ("sqp_iteration", C.c_int32),
@@ -117,6 +128,13 @@ def model_desc(model: dict) -> ModelDesc:
         d.frame_body[f] = model["frame_body"][f]
         for k in range(3):
             d.frame_p[f][k] = model["frame_p"][f][k]
+    if model.get("kind") == "centroidal":  # the task-space link rides as one more frame of the table
+        ts = model["task_space_cost"]
+        f = d.n_frames
+        d.frame_body[f] = ts["body"]
+        for k in range(3):
+            d.frame_p[f][k] = ts["p"][k]
+        d.n_frames = f + 1
     d.gravity = model["gravity"]
     for k in range(4):
         d.contact_rect[k] = model["contact_rect"][k]
@@ -141,3 +159,22 @@ def model_desc(model: dict) -> ModelDesc:
     for i in range(4):
         d.arm_swing_joint[i] = model["arm_swing_joints"][i]
     return d
+
+
+def cen_desc(model: dict) -> CenDesc:
+    """Centroidal model dictionary (model_loader.build_g1_centroidal_from_reference) -> b200sqp_cen_desc."""
+    assert model.get("kind") == "centroidal"
+    c = CenDesc()
+    ts = model["task_space_cost"]
+    c.torso_frame = len(model["frame_body"])
+    R = np.asarray(ts["R"]).reshape(9)
+    for k in range(9):
+        c.torso_R[k] = R[k]
+    for k in range(12):
+        c.torso_w[k] = ts["weights"][k]
+    c.icp_weight = model["icp_weight"]
+    for s in range(2):
+        for k in range(6):
+            c.torque_joint[s][k] = model["leg_torque_cost"][s]["joints"][k]
+            c.torque_w[s][k] = model["leg_torque_cost"][s]["weights"][k]
+    return c

@@ -260,15 +260,18 @@ G1_REL = dict(
     reference="robot_models/unitree_g1/g1_wb_mpc/config/command/reference.info",
     gait="humanoid_nmpc/humanoid_common_mpc/config/command/gait.info",
     centroidal_task="robot_models/unitree_g1/g1_centroidal_mpc/config/mpc/task.info",
+    centroidal_reference="robot_models/unitree_g1/g1_centroidal_mpc/config/command/reference.info",
 )
 
 
-def build_wb_model(urdf_path, task_path, reference_path=None, gait_path=None) -> dict:
-    """Flat whole-body (WB) model description. All matrices row-major nested lists."""
+def build_wb_model(urdf_path, task_path, reference_path=None, gait_path=None, kind="wb") -> dict:
+    """Flat model description of the whole-body (kind="wb") or the centroidal (kind="centroidal") MPC. All matrices row-major nested lists.
+    Both MPCs use the same reduced kinematic tree, contact frames and per-node reference data; they differ in the state/input layout
+    (WBAccelMpcRobotModel.h:76-241 / CentroidalMpcRobotModel.h:52-160), the weights and the task-space terms."""
     task = parse_info(task_path)
     links, joints = parse_urdf(urdf_path)
     fixed = set(info_list(task, "model_settings.fixedJointNames"))
-    bodies, _ = reduce_tree(links, joints, fixed)
+    bodies, link_body = reduce_tree(links, joints, fixed)
     nj = len(bodies) - 1
     joint_names = [b["joint"] for b in bodies[1:]]
     jidx = {n: i for i, n in enumerate(joint_names)}
@@ -290,7 +293,7 @@ def build_wb_model(urdf_path, task_path, reference_path=None, gait_path=None) ->
         jn = info_get(task, cc + key)
         frames.append((jn, jidx[jn] + 1, np.zeros(3)))
 
-    nx, nu = 2 * (6 + nj), 12 + nj
+    nx, nu = (2 * (6 + nj), 12 + nj) if kind == "wb" else (12 + nj, 12 + nj)
     Q = info_matrix(task, "Q", nx, nx)
     R = info_matrix(task, "R", nu, nu)
     Qf = info_matrix(task, "Q_final", nx, nx) * info_float(task, "terminalCostScaling")
@@ -311,9 +314,13 @@ def build_wb_model(urdf_path, task_path, reference_path=None, gait_path=None) ->
             [0.01] * 3,
         ]
     )
+    if kind == "centroidal":
+        # EndEffectorKinematicsWeights::toVector(): position, orientation, linear velocity, angular velocity (12 entries; the rest unused)
+        foot_w = np.concatenate([_ee_kinematics_weights(task, w), np.zeros(6)])
 
     model = dict(
-        name="g1_wb",
+        name="g1_wb" if kind == "wb" else "g1_centroidal",
+        kind=kind,
         nj=nj,
         nx=nx,
         nu=nu,
@@ -389,6 +396,26 @@ def build_wb_model(urdf_path, task_path, reference_path=None, gait_path=None) ->
             timeHorizon=info_float(task, "mpc.timeHorizon"),
         ),
     )
+    if kind == "centroidal":
+        model["sqp"]["timeHorizon"] = info_float(task, "mpc.timeHorizon")
+        model["centroidalModelType"] = int(info_float(task, "centroidalModelType"))
+        # task_space_costs: one EndEffectorKinematicsQuadraticCost per listed link (CentroidalMpcInterface.cpp:331-362); G1 lists the torso lidar link
+        costs = []
+        for cname, blk in task["task_space_costs"].items():
+            link = blk["link_name"]
+            b, R, p = link_body[link]
+            costs.append(dict(name=cname, link=link, body=b, R=np.asarray(R).tolist(), p=np.asarray(p).tolist(),
+                              weights=_ee_kinematics_weights(task, f"task_space_costs.{cname}.weights.").tolist()))
+        assert len(costs) == 1, "the device path carries exactly one task-space link cost (G1: torso)"
+        model["task_space_cost"] = costs[0]
+        model["icp_weight"] = info_float(task, "icp_cost_weights.icpErrorWeight")
+        # ExternalTorqueQuadraticCostAD (HumanoidCostConstraintFactory.cpp:234-245)
+        tq = []
+        for side in ("left_leg_torque_cost", "right_leg_torque_cost"):
+            names = info_list(task, side + ".activeJointNames")
+            wts = info_matrix(task[side], "weights", len(names), 1)[:, 0]
+            tq.append(dict(joints=[jidx[n] for n in names], weights=wts.tolist()))
+        model["leg_torque_cost"] = tq
     if reference_path is not None:
         ref = parse_info(reference_path)
         model["reference"] = dict(
@@ -408,6 +435,17 @@ def build_wb_model(urdf_path, task_path, reference_path=None, gait_path=None) ->
                 )
         model["gaits"] = gaits
     return model
+
+
+def _ee_kinematics_weights(task, prefix) -> np.ndarray:
+    """EndEffectorKinematicsWeights::getWeights + toVector (humanoid_common_mpc/src/cost/EndEffectorKinematicCostHelpers.cpp)"""
+    return np.array([info_float(task, prefix + f"{k}_{a}") for k in ("pos", "orientation", "lin_velocity", "ang_velocity") for a in "xyz"])
+
+
+def build_g1_centroidal_from_reference(reference_root="/root/reference") -> dict:
+    r = Path(reference_root)
+    return build_wb_model(r / G1_REL["urdf"], r / G1_REL["centroidal_task"], r / G1_REL["centroidal_reference"], r / G1_REL["gait"],
+                          kind="centroidal")
 
 
 def centroidal_settings(task_path, nj: int) -> dict:

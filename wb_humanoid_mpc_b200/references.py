@@ -265,6 +265,44 @@ def velocity_command_targets(model: dict, t0, x0, cmd, horizon):
     return np.array([t0, t0 + t_mid, t0 + horizon]), np.array(states)
 
 
+def velocity_command_targets_centroidal(model: dict, t0, x0, cmd, horizon, base_vel=None):
+    """CentroidalMpcTargetTrajectoriesCalculator::commandedVelocityToTargetTrajectories (humanoid_centroidal_mpc/src/command/
+    CentroidalMpcTargetTrajectoriesCalculator.cpp:82-160).  base_vel = Ab^-1 * x0[:6] (the reference multiplies the inverse base block of
+    the centroidal momentum matrix with the NORMALIZED momentum, i.e. flow_map(x0, u = 0)[6:12] / mass); it may be omitted for x0[:6] = 0.
+    The yaw average uses base_vel[5] -- the roll rate in the ZYX ordering -- as the reference does."""
+    nj = model["nj"]
+    x0 = np.asarray(x0, float)
+    if base_vel is None:
+        if np.any(x0[:6] != 0.0):
+            raise ValueError("base_vel = Ab^-1 * x0[:6] is needed for a non-zero initial momentum (centroidal.base_velocity)")
+        base_vel = np.zeros(6)
+    pose = np.array(x0[6:12], float)
+    pose[4] = pose[5] = 0.0
+    yaw = pose[3]
+    vg = np.array(cmd, float)
+    vg[0] = math.cos(yaw) * cmd[0] - math.sin(yaw) * cmd[1]
+    vg[1] = math.sin(yaw) * cmd[0] + math.cos(yaw) * cmd[1]
+    momentum = np.array([vg[0], vg[1], 0.0, 0.0, 0.0, vg[3] / sum(model["mass"])])
+    t_mid = 0.7 * horizon
+    avg = np.array([(base_vel[0] + vg[0]) / 2, (base_vel[1] + vg[1]) / 2, (base_vel[5] + vg[3]) / 2])
+    pose[2] = vg[2]
+
+    def integrate(p, av, h, dT):
+        q = p.copy()
+        q[0] += av[0] * dT
+        q[1] += av[1] * dT
+        q[2] = h
+        q[3] += av[2] * dT
+        q[4] = q[5] = 0.0
+        return q
+
+    mid = integrate(pose, avg, vg[2], t_mid)
+    fin = integrate(mid, np.array([vg[0], vg[1], vg[3]]), vg[2], horizon - t_mid)
+    joints = np.array(model["reference"]["defaultJointState"])
+    states = [np.concatenate([momentum, p, joints]) for p in (pose, mid, fin)]
+    return np.array([t0, t0 + t_mid, t0 + horizon]), np.array(states)
+
+
 def interp_targets(times, states, t):
     """LinearInterpolation::interpolate with clamping (TargetTrajectories::getDesiredState)"""
     if t <= times[0]:
@@ -449,9 +487,11 @@ def initialize_state_input_trajectories(model, x0, t_nodes, events, contact, pre
     return np.array(xs), np.array(us)
 
 
-def build_instance(model: dict, x0, t0=0.0, horizon=None, dt=None, gait="stance", gait_start=None, cmd=None, previous=None):
+def build_instance(model: dict, x0, t0=0.0, horizon=None, dt=None, gait="stance", gait_start=None, cmd=None, previous=None, base_vel=None):
     """One MPC instance -> dict of per-node arrays in the layout of b200sqp_upload_instances.
-    `previous` = to_primal_solution(...) of the last solve enables the reference's warm start; None is a cold start."""
+    `previous` = to_primal_solution(...) of the last solve enables the reference's warm start; None is a cold start.
+    model["kind"] == "centroidal" selects the centroidal target-trajectory rule (base_vel: see velocity_command_targets_centroidal); the
+    schedule, swing planner, time grid and initializer are shared by both MPCs (CentroidalWeightCompInitializer keeps the momentum)."""
     sq = model["sqp"]
     horizon = sq["timeHorizon"] if horizon is None else horizon
     dt = sq["dt"] if dt is None else dt
@@ -468,7 +508,10 @@ def build_instance(model: dict, x0, t0=0.0, horizon=None, dt=None, gait="stance"
     t_nodes, events = time_discretization_with_events(t0, tf, dt, ms.event_times)
     n = len(t_nodes)
     cmd = [0.0, 0.0, model["reference"]["defaultBaseHeight"], 0.0] if cmd is None else list(cmd)
-    tt, ts = velocity_command_targets(model, t0, x0, cmd, horizon)
+    if model.get("kind") == "centroidal":
+        tt, ts = velocity_command_targets_centroidal(model, t0, x0, cmd, horizon, base_vel)
+    else:
+        tt, ts = velocity_command_targets(model, t0, x0, cmd, horizon)
     nx, nu = model["nx"], model["nu"]
     contact = np.zeros((n, 2), dtype=np.uint8)
     swing = np.zeros((n, 2, 3))
