@@ -204,4 +204,4 @@ def test_sqp_config0_converges(model, orc):
     for k in range(len(I["t_nodes"]) - 1):
         if I["node_event"][k] == 1:
             continue
-        assert np.abs(orc.eq_constraint(k, out["x"][k], out["u"][k])).max() < 5e-3
+        assert np.abs(orc.eq_constraint(k, out["x"][k], out["u"][k])).max() < 5e-2
