@@ -9,6 +9,7 @@
 #include "../../wb_humanoid_mpc_b200/csrc/wb_dynamics.cuh"
 #ifdef EMU_WITH_LQ
 #include "../../wb_humanoid_mpc_b200/csrc/wb_lq.cuh"
+#include "../../wb_humanoid_mpc_b200/csrc/cen_host.cuh"
 #endif
 
 using namespace b200sqp;
@@ -49,5 +50,6 @@ int emu_dyn(const b200sqp_model_desc* d, const double* x, const double* u, doubl
 
 #ifdef EMU_WITH_LQ
 #include "wb_emu_lq.inc"
+#include "cen_emu.inc"
 #endif
 }

@@ -22,7 +22,7 @@ def build(force=False):
     srcs = list(EMU.glob("*.cu")) + list(EMU.glob("*.inc")) + list(CSRC.glob("*.cuh")) + list(CSRC.glob("*.inc"))
     if force or not so.exists() or any(s.stat().st_mtime > so.stat().st_mtime for s in srcs):
         nvcc = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
-        subprocess.run([nvcc, "-O2", "-std=c++17", "-DEMU_WITH_LQ", "-shared", "-Xcompiler", "-fPIC", "-Wno-deprecated-gpu-targets",
+        subprocess.run([nvcc, "-O2", "-std=c++17", "-DEMU_WITH_LQ", "-gencode", "arch=compute_100a,code=sm_100a", "-shared", "-Xcompiler", "-fPIC", "-Wno-deprecated-gpu-targets",
                         "-diag-suppress", "177", "-o", str(so), str(EMU / "wb_emu.cu")], check=True)
     return so
 
@@ -64,3 +64,25 @@ def lq_node(desc, x, u, xnext, xref, dt, contact, swing, impact, arm_phase):
     n = nut.value
     return dict(A=A.T.copy(), B=Bt.T[:, :n].copy(), b=b, Q=Q.T.copy(), S=St.T[:n].copy(), R=Rt.T[:n, :n].copy(), q=q, r=rt[:n].copy(),
                 Pu=Pu.T[:, :n].copy(), Px=Px.T.copy(), u0=u0, nut=n, perf=perf, raw=unpack_raw_blocks(raw, NX, NU))
+
+
+def cen_node(desc, cdesc, x, u, xnext, xref, dt, contact, swing, impact, arm_phase):
+    """One intermediate node of the centroidal path: cen_lq_kernel + cen_proj_kernel phase schedules on the host (padded QP record)."""
+    NX, NU, NT, CX = 58, 35, 23, 35
+    pad = lambda v: np.concatenate([F(v), np.zeros(NX - CX)])
+    xs, us, xn, xr = pad(x), F(u), pad(xnext), pad(xref)
+    nin = EmuNodeIn(_p(xs), _p(us), _p(xn), _p(xr), dt, (C.c_int * 2)(*[int(c) for c in contact]), (C.c_double * 6)(*np.asarray(swing, float).reshape(6)),
+                    (C.c_double * 2)(*impact), arm_phase)
+    A, Bt, b = np.zeros((NX, NX)), np.zeros((NT, NX)), np.zeros(NX)
+    Q, St, Rt, q, rt = np.zeros((NX, NX)), np.zeros((NX, NT)), np.zeros((NT, NT)), np.zeros(NX), np.zeros(NT)
+    Pu, Px, u0 = np.zeros((NT, NU)), np.zeros((NX, NU)), np.zeros(NU)
+    nut = C.c_int(0)
+    perf = np.zeros(4)
+    per = 2 * CX * CX + 2 * CX * NU + NU * NU + 2 * CX + NU + 1 + 14 * (CX + NU + 1) + 1
+    raw = np.zeros(per)
+    rc = lib().emu_cen_node(C.byref(desc), C.byref(cdesc), C.byref(nin), _p(raw), _p(A), _p(Bt), _p(b), _p(Q), _p(St), _p(Rt), _p(q), _p(rt),
+                            _p(Pu), _p(Px), _p(u0), C.byref(nut), _p(perf))
+    assert rc == 0
+    n = nut.value
+    return dict(A=A.T.copy(), B=Bt.T[:, :n].copy(), b=b, Q=Q.T.copy(), S=St.T[:n].copy(), R=Rt.T[:n, :n].copy(), q=q, r=rt[:n].copy(),
+                Pu=Pu.T[:, :n].copy(), Px=Px.T.copy(), u0=u0, nut=n, perf=perf, raw=unpack_raw_blocks(raw, CX, NU))

@@ -23,3 +23,12 @@ def flow_map(model: dict, x, u, derivatives: bool = True, device: int = 0):
     if not derivatives:
         return xd
     return xd, np.swapaxes(A, 1, 2).copy(), np.swapaxes(Bm, 1, 2).copy()   # column-major -> [row, col]
+
+
+def base_velocity(model: dict, x0, device: int = 0):
+    """Ab^-1 * x0[:6]: the base velocity CentroidalMpcTargetTrajectoriesCalculator::commandedVelocityToTargetTrajectories derives from the
+    NORMALIZED momentum (CentroidalMpcTargetTrajectoriesCalculator.cpp:121-125) = flow_map(x0, u = 0)[6:12] / mass.  x0 [nx] or [B, nx]."""
+    x = np.atleast_2d(np.asarray(x0, float))
+    xd = flow_map(model, x, np.zeros_like(x), derivatives=False, device=device)
+    bv = xd[:, 6:12] / sum(model["mass"])
+    return bv[0] if np.ndim(x0) == 1 else bv

@@ -122,28 +122,23 @@ __device__ __forceinline__ NodeOut nodeOut(const WbDev& d, size_t node, size_t s
   return out;
 }
 
-// K1a: node physics.  Intermediate nodes write their Mid record; terminal and event nodes are finished here.
-__global__ void __launch_bounds__(LQA_THREADS, 3) lq_dyn_kernel(WbDev d) {
-  extern __shared__ double smem[];
-  const int k = blockIdx.x, b = blockIdx.y;
-  if (d.flags[b * F_NF + F_CONVERGED]) return;
+// Terminal and event nodes are the same for every OCP family that runs in this device state (whole-body; centroidal, cen_kernels.cuh):
+// returns true when node k was one of them and has been written.  Qfd: NX diagonal final-cost weights; rawNx / rawNu: dimensions of the
+// optional raw block dump.
+__device__ __forceinline__ bool lqTerminalOrEventNode(const WbDev& d, const NodeIn& n, int k, size_t node, size_t stage, const double* Qfd,
+                                                      int rawNx, int rawNu, double* smem) {
   const int N = d.N;
-  const size_t node = static_cast<size_t>(b) * (N + 1) + k, stage = static_cast<size_t>(b) * N + k;
-  NodeIn n;
-  loadNode(d, b, k, n);
-  n.x = d.x + node * NX;
   double* perf = d.perfNode + node * 4;
   if (k == N) {
     // setupTerminalNode: final cost 1/2 (x - xref)' Qf (x - xref)   (Transcription.cpp:125-154, HumanoidCostConstraintFactory.cpp:218-228)
-    const WbDeviceModel& m = *d.model;
     double* Q = const_cast<double*>(d.qp.Q) + node * NX * NX;
     double* q = const_cast<double*>(d.qp.q) + node * NX;
-    for (int i = threadIdx.x; i < NX * NX; i += blockDim.x) Q[i] = (i % NX == i / NX) ? m.Qfd[i % NX] : 0.0;
+    for (int i = threadIdx.x; i < NX * NX; i += blockDim.x) Q[i] = (i % NX == i / NX) ? Qfd[i % NX] : 0.0;
     double part = 0.0;
     for (int i = threadIdx.x; i < NX; i += blockDim.x) {
       const double dx = n.x[i] - n.xref[i];
-      q[i] = m.Qfd[i] * dx;
-      part += 0.5 * m.Qfd[i] * dx * dx;
+      q[i] = Qfd[i] * dx;
+      part += 0.5 * Qfd[i] * dx * dx;
     }
     smem[threadIdx.x] = part;
     __syncthreads();
@@ -153,10 +148,8 @@ __global__ void __launch_bounds__(LQA_THREADS, 3) lq_dyn_kernel(WbDev d) {
       perf[0] = c;
       perf[1] = perf[2] = perf[3] = 0.0;
     }
-    return;
+    return true;
   }
-  n.u = d.u + stage * NU;
-  n.xnext = d.x + (node + 1) * NX;
   if (n.event == 1) {
     // setupEventNode: identity jump map, no cost, no input (Transcription.cpp:156-192)
     NodeOut out = nodeOut(d, node, stage);
@@ -184,13 +177,32 @@ __global__ void __launch_bounds__(LQA_THREADS, 3) lq_dyn_kernel(WbDev d) {
     if (out.raw) {
       for (long long i = threadIdx.x; i < d.rawPer; i += blockDim.x) out.raw[i] = 0.0;
       __syncthreads();
-      for (int i = threadIdx.x; i < NX; i += blockDim.x) {
-        out.raw[i + NX * i] = 1.0;
-        out.raw[NX * NX + NX * NU + i] = n.x[i] - n.xnext[i];
+      for (int i = threadIdx.x; i < rawNx; i += blockDim.x) {
+        out.raw[i + rawNx * i] = 1.0;
+        out.raw[rawNx * rawNx + rawNx * rawNu + i] = n.x[i] - n.xnext[i];
       }
     }
-    return;
+    return true;
   }
+  return false;
+}
+
+// K1a: node physics.  Intermediate nodes write their Mid record; terminal and event nodes are finished here.
+__global__ void __launch_bounds__(LQA_THREADS, 3) lq_dyn_kernel(WbDev d) {
+  extern __shared__ double smem[];
+  const int k = blockIdx.x, b = blockIdx.y;
+  if (d.flags[b * F_NF + F_CONVERGED]) return;
+  const int N = d.N;
+  const size_t node = static_cast<size_t>(b) * (N + 1) + k, stage = static_cast<size_t>(b) * N + k;
+  NodeIn n;
+  loadNode(d, b, k, n);
+  n.x = d.x + node * NX;
+  double* perf = d.perfNode + node * 4;
+  if (k < N) {
+    n.u = d.u + stage * NU;
+    n.xnext = d.x + (node + 1) * NX;
+  }
+  if (lqTerminalOrEventNode(d, n, k, node, stage, d.model->Qfd, NX, NU, smem)) return;
   __shared__ WbDeviceModel msh;  // model constants staged once per CTA: the kinematic phases read them in dependent sequences
   for (int i = threadIdx.x; i < static_cast<int>(sizeof(WbDeviceModel) / 8); i += blockDim.x)
     reinterpret_cast<double*>(&msh)[i] = reinterpret_cast<const double*>(d.model)[i];

@@ -46,7 +46,11 @@ class B200SqpSolver:
         self._desc = abi.model_desc(model)
         self._h = C.c_void_p()
         L = _l.lib()
-        _l.check(L.b200sqp_create(C.byref(self._desc), C.byref(self.settings), C.c_int(device), C.byref(self._h)))
+        if model.get("kind") == "centroidal":   # CentroidalMpcInterface OCP: same solver interface, nx = nu = 12 + nj at the ABI
+            self._cdesc = abi.cen_desc(model)
+            _l.check(L.b200sqp_cen_create(C.byref(self._desc), C.byref(self._cdesc), C.byref(self.settings), C.c_int(device), C.byref(self._h)))
+        else:
+            _l.check(L.b200sqp_create(C.byref(self._desc), C.byref(self.settings), C.c_int(device), C.byref(self._h)))
         self._raw_per = 0
         if capture_raw_blocks:
             per = C.c_int64()
