@@ -105,3 +105,57 @@ def test_receding_horizon_converges(spread):
         assert steps[-1] >= steps[0] and steps[-1] > 0.7, steps
     host.close()
     hm.close()
+
+
+def test_host_solver_centroidal_matches_python_harness():
+    """the C++ host layer on the centroidal model file: b200sqp_cen_create behind b200sqp::host::SqpSolver, cold and warm-started solve"""
+    from wb_humanoid_mpc_b200 import centroidal
+    from wb_humanoid_mpc_b200.solver import B200SqpSolver
+
+    model = model_loader.load_packaged_model("g1_centroidal")
+    hm = host_lib.HostModel(host_lib.CEN_MODEL_TXT)
+    rng = np.random.default_rng(5)
+    B, horizon = 3, 0.6
+    gaits = ["walk", "stance", "walk"]
+    cmds = [[rng.uniform(-0.3, 0.8), rng.uniform(-0.2, 0.2), model["reference"]["defaultBaseHeight"], rng.uniform(-0.3, 0.3)] for _ in range(B)]
+    x0s = []
+    for _ in range(B):
+        x0 = np.array(model["x_init"], float)
+        x0[:6] = rng.uniform(-0.05, 0.05, 6)
+        x0[9:12] += rng.uniform(-0.05, 0.05, 3)
+        x0[12:] += rng.uniform(-0.05, 0.05, 23)
+        x0s.append(x0)
+    st = abi.default_settings(model, sqp_iteration=2)
+    host = host_lib.HostSqpSolver(hm, st, B)
+    bvs = [hm.base_velocity(x0) for x0 in x0s]
+    for b in range(B):
+        assert np.allclose(bvs[b], centroidal.base_velocity(model, x0s[b]), atol=1e-14)
+        host.set_gait(b, gaits[b], 0.0, 3 * horizon)
+        host.set_command(b, 0.0, x0s[b], cmds[b], horizon, base_vel=bvs[b])
+    host.run(0.0, np.array(x0s), horizon)
+    prev = []
+    for b in range(B):
+        inst = references.build_instance(model, x0s[b], t0=0.0, horizon=horizon, gait=gaits[b], cmd=cmds[b], base_vel=bvs[b])
+        py = B200SqpSolver(model, st)
+        r = py.run([inst])
+        p = host.primal_solution(b)
+        assert p["x"].shape[1] == 35 and np.array_equal(p["t"], inst["t_nodes"])
+        dx = float(np.abs(p["x"] - r["x"][0]).max())
+        print("centroidal instance", b, gaits[b], "max |dx| host vs python", dx)
+        assert dx < 1e-6, (b, dx)
+        prev.append((py, references.to_primal_solution(inst["t_nodes"], inst["node_event"], r["x"][0], r["u"][0], inst["mode_schedule"])))
+    t1 = 3 * model["sqp"]["dt"]
+    x1s = [prev[b][1]["x"][3] for b in range(B)]
+    bv1 = [hm.base_velocity(x) for x in x1s]
+    for b in range(B):
+        host.set_command(b, t1, x1s[b], cmds[b], horizon, base_vel=bv1[b])
+    host.run(t1, np.array(x1s), t1 + horizon)
+    for b in range(B):
+        inst = references.build_instance(model, x1s[b], t0=t1, horizon=horizon, gait=gaits[b], gait_start=0.0, cmd=cmds[b], previous=prev[b][1],
+                                         base_vel=bv1[b])
+        r = prev[b][0].run([inst])
+        dx = float(np.abs(host.primal_solution(b)["x"] - r["x"][0]).max())
+        print("centroidal warm instance", b, "max |dx|", dx)
+        assert dx < 1e-6, (b, dx)
+    host.close()
+    hm.close()

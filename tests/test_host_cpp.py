@@ -134,3 +134,48 @@ def test_trajectory_spread_identical_schedules_sqp_time_convention(model):
     for i in post:
         if i + 1 < n - 1:
             assert abs(ct[i + 1] - (inst["t_nodes"][i] + 1e-9)) < 1e-15
+
+
+# ---- centroidal model file and instance builder ---------------------------------------------------------------------------------------------
+@pytest.fixture(scope="module")
+def cmodel():
+    return model_loader.load_packaged_model("g1_centroidal")
+
+
+@pytest.fixture(scope="module")
+def chmodel():
+    m = host_lib.HostModel(host_lib.CEN_MODEL_TXT)
+    yield m
+    m.close()
+
+
+def test_centroidal_flat_model_file_matches_json(cmodel, chmodel, hmodel):
+    from wb_humanoid_mpc_b200 import abi
+
+    d_cc, st = chmodel.desc_and_settings()
+    assert bytes(abi.model_desc(cmodel)) == bytes(d_cc)
+    assert bytes(abi.cen_desc(cmodel)) == bytes(chmodel.cen_desc())
+    assert bytes(abi.default_settings(cmodel)) == bytes(st)
+    assert (chmodel.nx, chmodel.nu, chmodel.dt, chmodel.horizon) == (35, 35, 0.02, 1.2)
+    assert hmodel.cen_desc() is None
+
+
+@pytest.mark.parametrize("gait,t0,horizon,start", [("stance", 0.0, 0.4, None), ("walk", 0.0, 2.0, None), ("walk", 0.37, 1.2, 0.1), ("trot", 0.0, 0.6, None)])
+def test_centroidal_instance_matches_python(cmodel, chmodel, gait, t0, horizon, start):
+    rng = np.random.default_rng(11)
+    x0 = np.array(cmodel["x_init"], float)
+    x0[:6] = rng.uniform(-0.1, 0.1, 6)
+    x0[6:12] += rng.uniform(-0.05, 0.05, 6)
+    bv = rng.uniform(-0.2, 0.2, 6)   # stands for Ab^-1 x0[:6] (a device quantity; any vector exercises the rule)
+    cmd = [0.6, -0.1, cmodel["reference"]["defaultBaseHeight"], 0.3]
+    py = references.build_instance(cmodel, x0, t0=t0, horizon=horizon, gait=gait, gait_start=start, cmd=cmd, base_vel=bv)
+    cc = chmodel.build_instance(x0, t0=t0, horizon=horizon, gait=gait, gait_start=start, cmd=cmd, base_vel=bv)
+    for k in KEYS:
+        a, b = np.asarray(py[k]), np.asarray(cc[k])
+        assert a.shape == b.shape, (k, a.shape, b.shape)
+        assert np.allclose(a, b, rtol=0, atol=1e-13), (k, np.abs(a.astype(float) - b.astype(float)).max())
+    # the target momentum rides in the first six reference states, the pose in the next six
+    assert np.allclose(py["x_ref"][0, 2:5], 0) and py["x_ref"].shape[1] == 35
+    # a non-zero momentum without base_vel is refused by the Python restatement
+    with pytest.raises(ValueError):
+        references.build_instance(cmodel, x0, t0=t0, horizon=horizon, gait=gait, cmd=cmd)

@@ -18,4 +18,5 @@ if __name__ == "__main__":
     c = build_g1_centroidal_from_reference(root)
     out = DATA_DIR / "g1_centroidal_model.json"
     out.write_text(json.dumps(c, indent=1))
+    write_flat(c, DATA_DIR / "g1_centroidal_model.txt")
     print("wrote", out, "nx", c["nx"], "nu", c["nu"], "torso link on body", c["task_space_cost"]["body"])

@@ -200,7 +200,9 @@ class SqpSolver {
   void solveGroup(int nNodes, const std::vector<int>& members, const std::vector<Instance>& inst) {
     Group& G = groups_[nNodes];
     const int Bg = static_cast<int>(members.size()), nx = model_.nx, nu = model_.nu, n = nNodes;
-    if (!G.h) check(b200sqp_create(&model_.desc, &settings_, device_, &G.h));
+    if (!G.h)
+      check(model_.centroidal ? b200sqp_cen_create(&model_.desc, &model_.cen, &settings_, device_, &G.h)
+                              : b200sqp_create(&model_.desc, &settings_, device_, &G.h));
     const size_t B_ = static_cast<size_t>(Bg), n_ = static_cast<size_t>(n);
     if (G.capacity != Bg || G.nNodes != n) {
       check(b200sqp_set_batch(G.h, Bg, n));

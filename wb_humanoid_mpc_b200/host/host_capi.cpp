@@ -48,12 +48,29 @@ int b200host_model_desc(void* m, b200sqp_model_desc* desc, b200sqp_settings* st)
   return 0;
 }
 
+// 1 and *cen filled for a centroidal model file, 0 for a whole-body one
+int b200host_model_cen_desc(void* m, b200sqp_cen_desc* cen) {
+  const HostModel& M = *static_cast<HostModel*>(m);
+  if (M.centroidal && cen) *cen = M.cen;
+  return M.centroidal ? 1 : 0;
+}
+
 // One instance, host only (no GPU): the arrays of b200sqp_upload_instances.  prev_* = the previous PrimalSolution (equal-length time, state
 // and input trajectories) or prev_n = 0 for a cold start.  Returns the node count, or -1 (b200host_last_error).
+namespace {
+// target trajectories of either MPC; base_vel (6, may be null = zeros) is only read for a centroidal model
+TargetTrajectories targetsFor(const HostModel& M, double t0, const vector_t& x0, const std::array<double, 4>& c, double horizon, const double* base_vel) {
+  if (!M.centroidal) return commandedVelocityToTargetTrajectories(M, t0, x0, c, horizon);
+  std::array<double, 6> bv{0, 0, 0, 0, 0, 0};
+  if (base_vel) std::copy(base_vel, base_vel + 6, bv.begin());
+  return commandedVelocityToTargetTrajectoriesCentroidal(M, t0, x0, c, horizon, bv);
+}
+}  // namespace
+
 int b200host_build_instance(void* model, double t0, const double* x0, double horizon, const char* gait, double gait_start, const double* cmd,
                             int prev_n, const double* prev_t, const double* prev_x, const double* prev_u, int max_nodes, double* t_nodes,
                             uint8_t* node_event, uint8_t* contact, double* swing, double* impact, double* arm, double* xref, double* x_init,
-                            double* u_init) {
+                            double* u_init, const double* base_vel) {
   return guarded([&] {
     const HostModel& M = *static_cast<HostModel*>(model);
     SwitchedModelReferenceManager rm(M);
@@ -62,7 +79,7 @@ int b200host_build_instance(void* model, double t0, const double* x0, double hor
     const vector_t x0v(x0, x0 + M.nx);
     std::array<double, 4> c{0.0, 0.0, M.defaultBaseHeight, 0.0};
     if (cmd) c = {cmd[0], cmd[1], cmd[2], cmd[3]};
-    rm.setTargetTrajectories(commandedVelocityToTargetTrajectories(M, t0, x0v, c, horizon));
+    rm.setTargetTrajectories(targetsFor(M, t0, x0v, c, horizon, base_vel));
     rm.preSolverRun(t0, tf);
     PrimalSolution prev;
     if (prev_n > 0) {
@@ -131,11 +148,20 @@ int b200host_solver_set_gait(void* s, int b, const char* gait, double start, dou
     return 0;
   });
 }
-int b200host_solver_set_command(void* s, void* model, int b, double t0, const double* x0, const double* cmd, double horizon) {
+int b200host_solver_set_command(void* s, void* model, int b, double t0, const double* x0, const double* cmd, double horizon, const double* base_vel) {
   return guarded([&] {
     const HostModel& M = *static_cast<HostModel*>(model);
     static_cast<SqpSolver*>(s)->getReferenceManager(b).setTargetTrajectories(
-        commandedVelocityToTargetTrajectories(M, t0, vector_t(x0, x0 + M.nx), {cmd[0], cmd[1], cmd[2], cmd[3]}, horizon));
+        targetsFor(M, t0, vector_t(x0, x0 + M.nx), {cmd[0], cmd[1], cmd[2], cmd[3]}, horizon, base_vel));
+    return 0;
+  });
+}
+// Ab^-1 * x0[0..6) of a centroidal state (device call; zeros without touching the device when the momentum is zero)
+int b200host_centroidal_base_velocity(void* model, const double* x0, double* out6) {
+  return guarded([&] {
+    const HostModel& M = *static_cast<HostModel*>(model);
+    const auto bv = centroidalBaseVelocity(M, vector_t(x0, x0 + M.nx));
+    std::copy(bv.begin(), bv.end(), out6);
     return 0;
   });
 }

@@ -40,6 +40,8 @@ struct HostModel {
   std::string name;
   int nj = 0, nx = 0, nu = 0;
   b200sqp_model_desc desc{};
+  bool centroidal = false;    // kind 1: the centroidal MPC (nx = nu = 12 + nj); `cen` is then the second argument of b200sqp_cen_create
+  b200sqp_cen_desc cen{};
   double totalMass = 0.0;
   std::vector<double> initialState, defaultJointState;
   double defaultBaseHeight = 0.0;
@@ -162,6 +164,20 @@ inline HostModel loadModelFile(const std::string& path) {
   d.coll_r_foot = c[2];
   d.coll_r_knee = c[3];
   for (int i = 0; i < 4; ++i) d.arm_swing_joint[i] = static_cast<int32_t>(get("arm_swing_joints", 4)[i]);
+  m.centroidal = rec.count("kind") && rec["kind"].size() == 1 && rec["kind"][0] == 1.0;
+  if (m.centroidal) {
+    b200sqp_cen_desc& c2 = m.cen;
+    std::memset(&c2, 0, sizeof(c2));
+    c2.torso_frame = static_cast<int32_t>(get("cen_torso_frame", 1)[0]);
+    for (int k = 0; k < 9; ++k) c2.torso_R[k] = get("cen_torso_R", 9)[k];
+    for (int k = 0; k < 12; ++k) c2.torso_w[k] = get("cen_torso_w", 12)[k];
+    c2.icp_weight = get("cen_icp_weight", 1)[0];
+    for (int s2 = 0; s2 < 2; ++s2)
+      for (int k = 0; k < 6; ++k) {
+        c2.torque_joint[s2][k] = static_cast<int32_t>(get("cen_torque_joint", 12)[6 * s2 + k]);
+        c2.torque_w[s2][k] = get("cen_torque_w", 12)[6 * s2 + k];
+      }
+  }
   m.initialState = get("x_init", m.nx);
   m.defaultJointState = get("default_joint_state", m.nj);
   m.defaultBaseHeight = get("default_base_height", 1)[0];

@@ -306,6 +306,57 @@ inline TargetTrajectories commandedVelocityToTargetTrajectories(const HostModel&
   return tt;
 }
 
+// CentroidalMpcTargetTrajectoriesCalculator::commandedVelocityToTargetTrajectories (humanoid_centroidal_mpc/src/command/
+// CentroidalMpcTargetTrajectoriesCalculator.cpp:82-160).  baseVel = Ab^-1 * x0[0..6) -- the inverse base block of the centroidal momentum
+// matrix times the NORMALIZED momentum, as the reference computes it (centroidalBaseVelocity() below obtains it from the device); the yaw
+// average uses baseVel[5], the roll rate in the ZYX ordering, as the reference does.
+inline TargetTrajectories commandedVelocityToTargetTrajectoriesCentroidal(const HostModel& m, double initTime, const vector_t& x0,
+                                                                          const std::array<double, 4>& cmd, double horizon,
+                                                                          const std::array<double, 6>& baseVel) {
+  const int nj = m.nj;
+  std::array<double, 6> pose{x0[6], x0[7], x0[8], x0[9], 0.0, 0.0};
+  const double yaw = pose[3];
+  const double vgx = std::cos(yaw) * cmd[0] - std::sin(yaw) * cmd[1], vgy = std::sin(yaw) * cmd[0] + std::cos(yaw) * cmd[1];
+  const std::array<double, 6> momentum{vgx, vgy, 0.0, 0.0, 0.0, cmd[3] / m.totalMass};
+  const double tMid = 0.7 * horizon;
+  const std::array<double, 3> avg{(baseVel[0] + vgx) / 2, (baseVel[1] + vgy) / 2, (baseVel[5] + cmd[3]) / 2};
+  pose[2] = cmd[2];
+  auto integrate = [](std::array<double, 6> p, const std::array<double, 3>& av, double h, double dT) {
+    p[0] += av[0] * dT;
+    p[1] += av[1] * dT;
+    p[2] = h;
+    p[3] += av[2] * dT;
+    p[4] = p[5] = 0.0;
+    return p;
+  };
+  const auto mid = integrate(pose, avg, cmd[2], tMid);
+  const auto fin = integrate(mid, {vgx, vgy, cmd[3]}, cmd[2], horizon - tMid);
+  TargetTrajectories tt;
+  tt.timeTrajectory = {initTime, initTime + tMid, initTime + horizon};
+  for (const auto& p : {pose, mid, fin}) {
+    vector_t x(m.nx, 0.0);
+    for (int k = 0; k < 6; ++k) {
+      x[k] = momentum[k];
+      x[6 + k] = p[k];
+    }
+    for (int j = 0; j < nj; ++j) x[12 + j] = m.defaultJointState[j];
+    tt.stateTrajectory.push_back(x);
+  }
+  return tt;
+}
+// Ab^-1 * x0[0..6) for a centroidal state, from the device flow map at zero input: flow(x0, 0)[6..12) = Ab^-1 (m hbar)
+inline std::array<double, 6> centroidalBaseVelocity(const HostModel& m, const vector_t& x0, int device = 0) {
+  std::array<double, 6> bv{0, 0, 0, 0, 0, 0};
+  bool zero = true;
+  for (int k = 0; k < 6; ++k) zero = zero && x0[k] == 0.0;
+  if (zero) return bv;
+  vector_t u(m.nu, 0.0), xd(m.nx, 0.0);
+  if (b200sqp_centroidal_flow_map(&m.desc, 1, x0.data(), u.data(), xd.data(), nullptr, nullptr, device) != 0)
+    throw std::runtime_error(std::string("[b200sqp::host] centroidalBaseVelocity: ") + b200sqp_last_error());
+  for (int k = 0; k < 6; ++k) bv[k] = xd[6 + k] / m.totalMass;
+  return bv;
+}
+
 // WeightCompInitializer: weight-compensating normal forces on the stance feet
 inline vector_t weightCompensatingInput(const HostModel& m, bool left, bool right) {
   vector_t u(m.nu, 0.0);

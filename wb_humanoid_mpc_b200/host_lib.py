@@ -19,6 +19,7 @@ PKG = Path(__file__).resolve().parent
 HOST = PKG / "host"
 SO = PKG / "libb200sqp_host.so"
 MODEL_TXT = PKG / "data" / "g1_wb_model.txt"
+CEN_MODEL_TXT = PKG / "data" / "g1_centroidal_model.txt"
 _lib = None
 dp = C.POINTER(C.c_double)
 u8p = C.POINTER(C.c_uint8)
@@ -54,9 +55,10 @@ def lib():
         L.b200host_solver_create.argtypes = [C.c_void_p, C.POINTER(abi.Settings), C.c_int, C.c_int, C.c_int]
         L.b200host_solver_destroy.argtypes = [C.c_void_p]
         L.b200host_build_instance.argtypes = [C.c_void_p, C.c_double, dp, C.c_double, C.c_char_p, C.c_double, dp, C.c_int, dp, dp, dp, C.c_int, dp, u8p, u8p,
-                                              dp, dp, dp, dp, dp, dp]
+                                              dp, dp, dp, dp, dp, dp, dp]
         L.b200host_solver_set_gait.argtypes = [C.c_void_p, C.c_int, C.c_char_p, C.c_double, C.c_double]
-        L.b200host_solver_set_command.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_double, dp, dp, C.c_double]
+        L.b200host_solver_set_command.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_double, dp, dp, C.c_double, dp]
+        L.b200host_centroidal_base_velocity.argtypes = [C.c_void_p, dp, dp]
         L.b200host_solver_reset.argtypes = [C.c_void_p]
         L.b200host_solver_run.argtypes = [C.c_void_p, C.c_void_p, C.c_double, dp, C.c_double]
         L.b200host_solver_n_nodes.argtypes = [C.c_void_p, C.c_int]
@@ -94,7 +96,20 @@ class HostModel:
         lib().b200host_model_desc(self.h, C.byref(d), C.byref(s))
         return d, s
 
-    def build_instance(self, x0, t0=0.0, horizon=None, gait="stance", gait_start=None, cmd=None, previous=None, max_nodes=512):
+    def cen_desc(self):
+        """b200sqp_cen_desc of a centroidal model file, None for a whole-body one"""
+        c = abi.CenDesc()
+        L = lib()
+        L.b200host_model_cen_desc.argtypes = [C.c_void_p, C.POINTER(abi.CenDesc)]
+        return c if L.b200host_model_cen_desc(self.h, C.byref(c)) == 1 else None
+
+    def base_velocity(self, x0):
+        """Ab^-1 * x0[:6] of a centroidal state (device call unless the momentum is zero)"""
+        x0, out = np.ascontiguousarray(x0, dtype=np.float64), np.zeros(6)
+        _check(lib().b200host_centroidal_base_velocity(self.h, _p(x0), _p(out)))
+        return out
+
+    def build_instance(self, x0, t0=0.0, horizon=None, gait="stance", gait_start=None, cmd=None, previous=None, max_nodes=512, base_vel=None):
         horizon = self.horizon if horizon is None else horizon
         x0 = np.ascontiguousarray(x0, dtype=np.float64)
         n, nx, nu = max_nodes, self.nx, self.nu
@@ -110,7 +125,8 @@ class HostModel:
             pn = 0
         k = _check(lib().b200host_build_instance(self.h, t0, _p(x0), horizon, gait.encode(), t0 if gait_start is None else gait_start,
                                                  None if cm is None else _p(cm), pn, _p(pt), _p(px), _p(pu), n, _p(t), ev.ctypes.data_as(u8p),
-                                                 cf.ctypes.data_as(u8p), _p(sw), _p(imp), _p(arm), _p(xr), _p(xi), _p(ui)))
+                                                 cf.ctypes.data_as(u8p), _p(sw), _p(imp), _p(arm), _p(xr), _p(xi), _p(ui),
+                                                 None if base_vel is None else _p(np.ascontiguousarray(base_vel, dtype=np.float64))))
         return dict(x0=x0, x_init=xi[:k], u_init=ui[:k - 1], t_nodes=t[:k], node_event=ev[:k], contact_flags=cf[:k], swing_ref=sw[:k],
                     impact_factor=imp[:k], arm_phase=arm[:k], x_ref=xr[:k])
 
@@ -146,9 +162,10 @@ class HostSqpSolver:
     def set_gait(self, b, gait, start, final):
         _check(lib().b200host_solver_set_gait(self.h, b, gait.encode(), start, final))
 
-    def set_command(self, b, t0, x0, cmd, horizon):
+    def set_command(self, b, t0, x0, cmd, horizon, base_vel=None):
         x0, cmd = np.ascontiguousarray(x0, dtype=np.float64), np.ascontiguousarray(cmd, dtype=np.float64)
-        _check(lib().b200host_solver_set_command(self.h, self.model.h, b, t0, _p(x0), _p(cmd), horizon))
+        bv = None if base_vel is None else _p(np.ascontiguousarray(base_vel, dtype=np.float64))
+        _check(lib().b200host_solver_set_command(self.h, self.model.h, b, t0, _p(x0), _p(cmd), horizon, bv))
 
     def set_trajectory_spread(self, on: bool):
         L = lib()

@@ -500,7 +500,22 @@ def write_flat(model: dict, path) -> None:
     L = [f"name 1 {model['name']}"]
     for k in ("nj", "nx", "nu", "gravity"):
         L.append(rec(k, [model[k]]))
-    for k in ("parent", "joint_R", "joint_p", "joint_axis", "mass", "com", "inertia", "q_lower", "q_upper", "frame_body", "frame_p", "contact_rect",
+    cen = model.get("kind") == "centroidal"
+    L.append(rec("kind", [1 if cen else 0]))
+    frame_body, frame_p = list(model["frame_body"]), [list(p) for p in model["frame_p"]]
+    if cen:  # the task-space link rides as the last frame of the table (b200sqp_cen_desc.torso_frame), as in abi.model_desc
+        ts = model["task_space_cost"]
+        L.append(rec("cen_torso_frame", [len(frame_body)]))
+        frame_body.append(ts["body"])
+        frame_p.append(ts["p"])
+        L.append(rec("cen_torso_R", ts["R"]))
+        L.append(rec("cen_torso_w", ts["weights"]))
+        L.append(rec("cen_icp_weight", [model["icp_weight"]]))
+        L.append(rec("cen_torque_joint", [j for side in model["leg_torque_cost"] for j in side["joints"]]))
+        L.append(rec("cen_torque_w", [w for side in model["leg_torque_cost"] for w in side["weights"]]))
+    L.append(rec("frame_body", frame_body))
+    L.append(rec("frame_p", frame_p))
+    for k in ("parent", "joint_R", "joint_p", "joint_axis", "mass", "com", "inertia", "q_lower", "q_upper", "contact_rect",
               "Q_diag", "R_diag", "Qf_diag", "x_init", "foot_cost_weights", "arm_swing_joints"):
         L.append(rec(k, model[k]))
     g = model["foot_gains"]
