@@ -140,9 +140,14 @@ class B200SqpSolver:
         return self.primal_solution()
 
     # -- results -------------------------------------------------------------------------------------------------------------
-    def primal_solution(self, with_gains: bool | None = None):
+    def primal_solution(self, with_gains: bool | None = None, out: dict | None = None):
+        """out = {"x": [B, n, nx], "u": [B, n-1, nu]} lets the caller supply (page-locked) destination arrays for the download"""
         B, n, nx, nu = self.batch, self.n_nodes, self.nx, self.nu
-        x, u = np.zeros((B, n, nx)), np.zeros((B, n - 1, nu))
+        if out is not None:
+            x, u = out["x"], out["u"]
+            assert x.shape == (B, n, nx) and u.shape == (B, n - 1, nu) and x.flags.c_contiguous and u.flags.c_contiguous
+        else:
+            x, u = np.zeros((B, n, nx)), np.zeros((B, n - 1, nu))
         with_gains = bool(self.settings.use_feedback_policy) if with_gains is None else with_gains
         K = np.zeros((B, n - 1, nx, nu)) if with_gains else None
         log = (abi.IterLog * (B * self.settings.sqp_iteration))()
