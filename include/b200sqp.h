@@ -149,6 +149,12 @@ int b200sqp_reset(b200sqp_handle h);
 /* SqpSolver::runImpl for every instance; asynchronous on `stream`. */
 int b200sqp_solve(b200sqp_handle h, void* stream);
 
+/* A non-blocking CUDA stream owned by the handle, for callers without CUDA headers: b200sqp_solve(h, stream) on it lets several handles
+ * (e.g. two b200sqp::host::SqpSolver objects double-buffering a workload) overlap on the device instead of serialising on the legacy
+ * default stream.  The handle's host<->device copies (upload / reset / download) run on a second internal stream and are complete when
+ * those calls return. */
+int b200sqp_own_stream(b200sqp_handle h, void** stream);
+
 /* Global-step mode (settings.global_step = 1; SURVEY.md section 8e, not a reference semantic): one line-search step size per SQP iteration
  * for the whole, possibly multi-GPU, batch.  Per iteration b200sqp_solve evaluates the fixed ladder alpha_j = alpha_decay^j >= alpha_min
  * for every active instance with the reference's filter test (FilterLinesearch.cpp:34-57) and leaves

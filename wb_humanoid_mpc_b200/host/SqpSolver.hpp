@@ -19,6 +19,7 @@
 #pragma once
 #include <chrono>
 #include <map>
+#include <mutex>
 #include <memory>
 #include <thread>
 
@@ -57,7 +58,7 @@ class SqpSolver {
     groupOf_.assign(batch, -1);
     slotOf_.assign(batch, -1);
     const unsigned hw = std::thread::hardware_concurrency();
-    threads_ = hostThreads > 0 ? hostThreads : static_cast<int>(std::max(1u, std::min(hw ? hw : 1u, 64u)));
+    threads_ = hostThreads > 0 ? hostThreads : static_cast<int>(std::max(1u, std::min(hw ? hw : 1u, 16u)));   // per-instance host work is light: more threads only add spawn cost
   }
   ~SqpSolver() {
     for (auto& g : groups_) {
@@ -98,6 +99,9 @@ class SqpSolver {
     bench_.hostPreRun = since(tPre);
     for (auto& kv : members) solveGroup(kv.first, kv.second, inst);
   }
+
+  // see solveGroup: serialise the device phase of this object with every other SqpSolver of the process that also opted in
+  void setExclusiveSolve(bool on) { exclusiveSolve_ = on; }
 
   const PrimalSolution& primalSolution(int b) const { return primal_.at(b); }
   const std::vector<StepInfo>& getIterationsLog(int b) const {
@@ -244,7 +248,17 @@ class SqpSolver {
     check(b200sqp_upload_instances(G.h, x0, xi, ui, tn, ev, cf, sw, imp, arm, xr));
     bench_.upload += since(tm);
     tm = now();
-    check(b200sqp_solve(G.h, nullptr));
+    void* stream = nullptr;   // the handle's own non-blocking stream: several SqpSolver objects overlap on the device
+    check(b200sqp_own_stream(G.h, &stream));
+    if (exclusiveSolve_) {
+      // double buffering with several SqpSolver objects: one solve on the GPU at a time, the others build / unpack their batches meanwhile.
+      // Without the token concurrent solves share the GPU evenly, finish together and keep the objects in lock-step (host phases aligned,
+      // GPU idle during them).
+      std::lock_guard<std::mutex> token(deviceToken(device_));
+      check(b200sqp_solve(G.h, stream));
+    } else {
+      check(b200sqp_solve(G.h, stream));
+    }
     bench_.solve += since(tm);
     tm = now();
     double *x = G.st.x, *u = G.st.u;
@@ -291,6 +305,11 @@ class SqpSolver {
     bench_.hostUnpack += since(tm);
   }
 
+  static std::mutex& deviceToken(int device) {
+    static std::mutex tokens[16];
+    return tokens[(device % 16 + 16) % 16];
+  }
+  bool exclusiveSolve_ = false;
   HostModel model_;
   b200sqp_settings settings_;
   int device_, batch_, threads_ = 1;

@@ -169,6 +169,10 @@ int b200host_solver_set_trajectory_spread(void* s, int on) {
   static_cast<SqpSolver*>(s)->setTrajectorySpread(on != 0);
   return 0;
 }
+int b200host_solver_set_exclusive_solve(void* s, int on) {
+  static_cast<SqpSolver*>(s)->setExclusiveSolve(on != 0);
+  return 0;
+}
 int b200host_solver_reset(void* s) {
   return guarded([&] {
     static_cast<SqpSolver*>(s)->reset();

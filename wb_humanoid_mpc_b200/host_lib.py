@@ -172,6 +172,12 @@ class HostSqpSolver:
         L.b200host_solver_set_trajectory_spread.argtypes = [C.c_void_p, C.c_int]
         L.b200host_solver_set_trajectory_spread(self.h, int(on))
 
+    def set_exclusive_solve(self, on: bool):
+        """double buffering with several solver objects: one solve on the GPU at a time (SqpSolver::setExclusiveSolve)"""
+        L = lib()
+        L.b200host_solver_set_exclusive_solve.argtypes = [C.c_void_p, C.c_int]
+        L.b200host_solver_set_exclusive_solve(self.h, int(on))
+
     def reset(self):
         _check(lib().b200host_solver_reset(self.h))
 
