@@ -209,6 +209,9 @@ typedef struct b200sqp_cen_desc {
   double icp_weight;            /* icp_cost_weights.icpErrorWeight */
   int32_t torque_joint[2][6];   /* ExternalTorqueQuadraticCostAD: active joints (0-based joint indices) per contact ... */
   double torque_w[2][6];        /* ... and their weights (left_leg_torque_cost / right_leg_torque_cost) */
+  int32_t model_type;           /* centroidalModelType: 0 FullCentroidalDynamics, 1 SingleRigidBodyDynamics (CentroidalModelInfo.h:47) */
+  double inertia_nominal[9];    /* SRBD only: CentroidalModelInfo::centroidalInertiaNominal (row-major) and comToBasePositionNominal, i.e. */
+  double com_to_base_nominal[3];/* ccrba at q = (0_6, defaultJointState) (ocs2_centroidal_model/src/FactoryFunctions.cpp:113-121)          */
 } b200sqp_cen_desc;
 int b200sqp_cen_create(const b200sqp_model_desc* model, const b200sqp_cen_desc* cen, const b200sqp_settings* settings, int device,
                        b200sqp_handle* out);

@@ -47,6 +47,27 @@ void computeCentroidalMap(const RobotModel& m, const S* q, CentroidalData<S>& c)
   const int nv = m.nv();
   c.Ag.assign(6 * nv, S(0.0));
   std::vector<S> qd(nv, S(0.0));
+  if (m.centroidalModelType == 1) {
+    // updateCentroidalDynamics, SingleRigidBodyDynamics branch (ModelHelperFunctions.cpp:61-79): Ag = [Ab 0] from the nominal inertia and
+    // com offset rotated with the base; com = base position - R r_nominal; the frame placements still follow the full kinematics
+    forwardKinematics<S>(m, q, qd.data(), static_cast<const S*>(nullptr), V3<S>(), c.kin);
+    const M3<S>& R = c.kin.oMi[0].R;
+    const M3<S> T = R * c.kin.Szyx;   // Euler-rate -> global angular velocity
+    const V3<S> rw = R * V3<S>(S(m.comToBaseNominal[0]), S(m.comToBaseNominal[1]), S(m.comToBaseNominal[2]));
+    M3<S> In;
+    for (int k = 0; k < 9; ++k) In.m[k] = S(m.inertiaNominal[k]);
+    const M3<S> A12 = skew(rw) * T, A22 = (R * In) * (transpose(R) * T);
+    const S mass(m.totalMass());
+    for (int r = 0; r < 3; ++r) {
+      c.Ag[r * nv + r] = mass;
+      for (int k = 0; k < 3; ++k) {
+        c.Ag[r * nv + 3 + k] = mass * A12(r, k);
+        c.Ag[(3 + r) * nv + 3 + k] = A22(r, k);
+      }
+    }
+    c.com = V3<S>(q[0] - rw[0], q[1] - rw[1], q[2] - rw[2]);
+    return;
+  }
   for (int k = 0; k < nv; ++k) {
     qd[k] = S(1.0);
     forwardKinematics<S>(m, q, qd.data(), static_cast<const S*>(nullptr), V3<S>(), c.kin);

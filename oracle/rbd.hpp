@@ -143,6 +143,11 @@ struct RobotModel {
   std::vector<int> frameBody;
   std::vector<std::array<double, 3>> frameP;
   double gravity = 9.81;
+  // CentroidalModelInfo of the centroidal MPC (ocs2_centroidal_model/include/ocs2_centroidal_model/CentroidalModelInfo.h:47-70): model type
+  // (0 FullCentroidalDynamics, 1 SingleRigidBodyDynamics) and the nominal inertia / com offset the latter uses; ignored by the whole-body OCP
+  int centroidalModelType = 0;
+  double inertiaNominal[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
+  double comToBaseNominal[3] = {0, 0, 0};
   double totalMass() const {
     double m = 0;
     for (const auto& b : inertia) m += b.m;

@@ -10,10 +10,11 @@ from test_oracle_cen_ocp import perturbed_state, random_input
 from wb_humanoid_mpc_b200 import abi, model_loader
 
 
-@pytest.fixture(scope="module")
-def model():
+@pytest.fixture(scope="module", params=[0, 1], ids=["full", "srbd"])
+def model(request):
     m = dict(model_loader.load_packaged_model("g1_centroidal"))
     m["icp_weight"] = 2.0   # exercise the ICP rows too (0 in the shipped task.info)
+    m["centroidalModelType"] = request.param   # 0 FullCentroidalDynamics (shipped), 1 SingleRigidBodyDynamics
     return m
 
 

@@ -151,3 +151,33 @@ def test_batch_of_instances_is_independent(model):
     for b, inst in enumerate(insts):
         one = B200SqpSolver(model, st).run([inst])
         assert np.array_equal(one["x"][0], sol["x"][b]) and np.array_equal(one["u"][0], sol["u"][b])
+
+
+def test_srbd_model_type_matches_oracle(model):
+    """centroidalModelType 1 (SingleRigidBodyDynamics): LQ blocks and two SQP iterations against the oracle"""
+    from wb_humanoid_mpc_b200.solver import B200SqpSolver
+
+    m1 = dict(model)
+    m1["centroidalModelType"] = 1
+    rng = np.random.default_rng(6)
+    inst = make_instance(m1, rng, "walk", 0.4, [0.3, 0.1, 0.7925, 0.2], momentum=True)
+    st = abi.default_settings(m1, sqp_iteration=2)
+    solver = B200SqpSolver(m1, st, capture_raw_blocks=True)
+    sol = solver.run([inst])
+    ref = oracle_solve(m1, inst, st, keep_raw=True)
+    assert sol["n_iter"][0] == len(ref["log"])
+    for it in range(len(ref["log"])):
+        g, o = sol["log"][0, it], ref["log"][it]
+        assert g[8] == o[8]
+        for j in (0, 1, 2, 3, 4, 5, 6, 7, 10, 11):
+            assert abs(g[j] - o[j]) <= 1e-6 * max(1.0, abs(o[j])), (it, j, g[j], o[j])
+    assert rel(sol["x"][0], ref["x"]) < 1e-6 and rel(sol["u"][0], ref["u"]) < 1e-6
+    raw = solver.raw_stage_blocks()   # blocks of the LAST iteration on both sides
+    for k in range(len(inst["t_nodes"]) - 1):
+        g, o = orc.unpack_raw_blocks(raw[0, k], 35, 35), ref["raw"][k]
+        for key in ["A", "B", "b", "C", "D", "e", "Q", "R"]:
+            assert rel(g[key], o[key]) < 1e-6, (k, key)
+    # and the model type matters: the full model gives different dynamics blocks
+    full = B200SqpSolver(model, st, capture_raw_blocks=True)
+    full.run([inst])
+    assert rel(orc.unpack_raw_blocks(full.raw_stage_blocks()[0, 0], 35, 35)["B"], ref["raw"][0]["B"]) > 1e-4

@@ -179,3 +179,21 @@ def test_centroidal_instance_matches_python(cmodel, chmodel, gait, t0, horizon, 
     # a non-zero momentum without base_vel is refused by the Python restatement
     with pytest.raises(ValueError):
         references.build_instance(cmodel, x0, t0=t0, horizon=horizon, gait=gait, cmd=cmd)
+
+
+def test_srbd_model_file_and_base_velocity(cmodel, tmp_path):
+    """centroidalModelType 1: the flat file carries the nominal inertia / com offset; the host's closed-form Ab^-1 hbar equals the Python one"""
+    from wb_humanoid_mpc_b200 import abi, centroidal
+
+    m1 = dict(cmodel)
+    m1["centroidalModelType"] = 1
+    path = tmp_path / "g1_srbd.txt"
+    model_loader.write_flat(m1, path)
+    hm = host_lib.HostModel(path)
+    assert bytes(abi.cen_desc(m1)) == bytes(hm.cen_desc()) and hm.cen_desc().model_type == 1
+    rng = np.random.default_rng(12)
+    x0 = np.array(cmodel["x_init"], float)
+    x0[:6] = rng.uniform(-0.2, 0.2, 6)
+    x0[9:12] = rng.uniform(-0.4, 0.4, 3)
+    assert np.allclose(hm.base_velocity(x0), centroidal.base_velocity(m1, x0), rtol=0, atol=1e-14)
+    hm.close()

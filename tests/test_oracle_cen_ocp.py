@@ -205,3 +205,43 @@ def test_sqp_config0_converges(model, orc):
         if I["node_event"][k] == 1:
             continue
         assert np.abs(orc.eq_constraint(k, out["x"][k], out["u"][k])).max() < 5e-2
+
+
+# ---- SingleRigidBodyDynamics model type (centroidalModelType 1) ----------------------------------------------------------------------------
+def srbd_model(model):
+    m = dict(model)
+    m["centroidalModelType"] = 1
+    return m
+
+
+def test_srbd_equals_full_model_at_nominal_joints(model, orc):
+    """The SRBD model freezes the centroidal inertia and the com offset at the nominal joint angles: there (any base pose, zero joint
+    velocities) both model types give the same flow map.  Pins model_loader.srbd_nominal against the oracle's centroidal momentum matrix."""
+    o1 = ol.CenOracle(srbd_model(model))
+    rng = np.random.default_rng(30)
+    x = np.array(model["x_init"], float)
+    x[12:] = model["reference"]["defaultJointState"]
+    x[:6] = rng.uniform(-0.3, 0.3, 6)
+    x[6:12] += rng.uniform(-0.3, 0.3, 6)
+    u = random_input(model, rng, [1, 1])
+    u[12:] = 0.0
+    assert np.allclose(o1.flow_map(x, u), orc.flow_map(x, u), atol=1e-12)
+    u[12:] = rng.uniform(-0.5, 0.5, model["nj"])   # joint velocities move the full model's base (Aj qdot_j), not the SRBD one
+    f1, f0 = o1.flow_map(x, u), orc.flow_map(x, u)
+    assert np.allclose(f1[:6], f0[:6], atol=1e-12) and np.abs(f1[6:12] - f0[6:12]).max() > 1e-3
+
+
+def test_srbd_flow_map_jacobians_and_base_velocity(model):
+    from wb_humanoid_mpc_b200 import centroidal
+
+    m1 = srbd_model(model)
+    o1 = ol.CenOracle(m1)
+    rng = np.random.default_rng(31)
+    x, u = perturbed_state(model, rng), random_input(model, rng, [1, 0])
+    f, A, B = o1.flow_map_lin(x, u)
+    nx = model["nx"]
+    J = fd(lambda z: o1.flow_map(z[:nx], z[nx:]), np.concatenate([x, u]))
+    assert np.allclose(A, J[:, :nx], atol=2e-6) and np.allclose(B, J[:, nx:], atol=2e-6)
+    # closed-form Ab^-1 hbar of the target-trajectory rule == flow(x, 0)[6:12] / m
+    bv = centroidal.base_velocity(m1, x)
+    assert np.allclose(bv, o1.flow_map(x, np.zeros(model["nu"]))[6:12] / sum(model["mass"]), atol=1e-12)

@@ -63,6 +63,9 @@ class CenDesc(C.Structure):
         ("icp_weight", C.c_double),
         ("torque_joint", (C.c_int32 * 6) * 2),
         ("torque_w", (C.c_double * 6) * 2),
+        ("model_type", C.c_int32),
+        ("inertia_nominal", C.c_double * 9),
+        ("com_to_base_nominal", C.c_double * 3),
     ]
 
 
@@ -177,4 +180,10 @@ def cen_desc(model: dict) -> CenDesc:
         for k in range(6):
             c.torque_joint[s][k] = model["leg_torque_cost"][s]["joints"][k]
             c.torque_w[s][k] = model["leg_torque_cost"][s]["weights"][k]
+    c.model_type = int(model.get("centroidalModelType", 0))
+    I = np.asarray(model["srbd_nominal"]["inertia"]).reshape(9)
+    for k in range(9):
+        c.inertia_nominal[k] = I[k]
+    for k in range(3):
+        c.com_to_base_nominal[k] = model["srbd_nominal"]["com_to_base"][k]
     return c

@@ -29,6 +29,25 @@ def base_velocity(model: dict, x0, device: int = 0):
     """Ab^-1 * x0[:6]: the base velocity CentroidalMpcTargetTrajectoriesCalculator::commandedVelocityToTargetTrajectories derives from the
     NORMALIZED momentum (CentroidalMpcTargetTrajectoriesCalculator.cpp:121-125) = flow_map(x0, u = 0)[6:12] / mass.  x0 [nx] or [B, nx]."""
     x = np.atleast_2d(np.asarray(x0, float))
+    if int(model.get("centroidalModelType", 0)) == 1:
+        bv = np.array([srbd_base_velocity(model, xi) for xi in x])
+        return bv[0] if np.ndim(x0) == 1 else bv
     xd = flow_map(model, x, np.zeros_like(x), derivatives=False, device=device)
     bv = xd[:, 6:12] / sum(model["mass"])
     return bv[0] if np.ndim(x0) == 1 else bv
+
+
+def srbd_base_velocity(model: dict, x0):
+    """Ab^-1 * x0[:6] for the SingleRigidBodyDynamics model, closed form (updateCentroidalDynamics, ModelHelperFunctions.cpp:61-79, and the block
+    inverse of ModelHelperFunctionsImpl.h:40-47): Ab = [[m 1, m [R r]x T], [0, R I R' T]] with the nominal inertia I and com offset r."""
+    z, y, xr = x0[9:12]
+    cz, sz, cy, sy, cx, sx = np.cos(z), np.sin(z), np.cos(y), np.sin(y), np.cos(xr), np.sin(xr)
+    R = np.array([[cz * cy, cz * sy * sx - sz * cx, cz * sy * cx + sz * sx], [sz * cy, sz * sy * sx + cz * cx, sz * sy * cx - cz * sx], [-sy, cy * sx, cy * cx]])
+    T = R @ np.array([[-sy, 0, 1], [cy * sx, cx, 0], [cy * cx, -sx, 0.0]])   # Euler-rate (z, y, x) -> global angular velocity
+    m = sum(model["mass"])
+    rw = R @ np.asarray(model["srbd_nominal"]["com_to_base"])
+    S = np.array([[0, -rw[2], rw[1]], [rw[2], 0, -rw[0]], [-rw[1], rw[0], 0]])
+    A22 = R @ np.asarray(model["srbd_nominal"]["inertia"]) @ R.T @ T
+    w = np.linalg.solve(A22, x0[3:6])
+    v = (x0[0:3] - m * S @ T @ w) / m
+    return np.concatenate([v, w])

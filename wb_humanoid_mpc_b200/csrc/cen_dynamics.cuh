@@ -28,6 +28,10 @@ struct CenModel {  // subset of b200sqp_model_desc the flow map reads
   double mtot;
   int contactBody[2];
   double contactP[2][3];
+  // CentroidalModelInfo::centroidalModelType (0 full centroidal dynamics, 1 single rigid body) with the nominal inertia / com offset of the
+  // latter; read by cenKinematics (cen_ocp.cuh).  cen_flow_kernel below always evaluates the full model.
+  int modelType;
+  double inertiaNominal[9], comToBaseNominal[3];
 };
 
 HD D1 dsin(D1 a) { return D1{sin(a.v), cos(a.v) * a.d}; }

@@ -20,6 +20,9 @@ inline void cenModelFromWb(const WbDeviceModel& wm, CenModel& cm) {
     }
   }
   cm.mtot = wm.mtot;
+  cm.modelType = 0;
+  for (int k = 0; k < 9; ++k) cm.inertiaNominal[k] = 0.0;
+  for (int k = 0; k < 3; ++k) cm.comToBaseNominal[k] = 0.0;
   for (int c = 0; c < 2; ++c) {
     cm.contactBody[c] = wm.frameBody[3 * c];
     for (int k = 0; k < 3; ++k) cm.contactP[c][k] = wm.frameP[3 * c][k];
@@ -42,6 +45,10 @@ inline const char* makeCenDeviceModel(const b200sqp_model_desc& d, const b200sqp
     if (d.frame_body[f] < 0 || d.frame_body[f] >= NB) return "frame body out of range";
     for (int k = 0; k < 3; ++k) m.frameP[f][k] = d.frame_p[f][k];
   }
+  if (c.model_type != 0 && c.model_type != 1) return "model_type must be 0 (FullCentroidalDynamics) or 1 (SingleRigidBodyDynamics)";
+  m.kin.modelType = c.model_type;
+  for (int k = 0; k < 9; ++k) m.kin.inertiaNominal[k] = c.inertia_nominal[k];
+  for (int k = 0; k < 3; ++k) m.kin.comToBaseNominal[k] = c.com_to_base_nominal[k];
   m.torsoFrame = c.torso_frame;
   for (int k = 0; k < 9; ++k) m.torsoR[k] = c.torso_R[k];
   for (int k = 0; k < 12; ++k) {

@@ -57,7 +57,8 @@ struct CenKin {
   D1 M[NB];
   DV3 mu[NB];
   D1 J[NB][6];
-  DV3 G, Sw[3];      // centre of mass; world axes of the three Euler-rate columns
+  DV3 G, Sw[3];      // centre of mass as the dynamics see it (data.com[0]); world axes of the three Euler-rate columns
+  DV3 Gcom;          // pinocchio::centerOfMass(q) (= G for the full model; the SRBD model carries a nominal offset in G instead)
   D1 mass;
   D1 Ag[6][NV - 3];  // columns 3..28 (translation columns are [m 1; 0])
 };
@@ -87,6 +88,33 @@ HD void cenKinematics(const CenModel& m, const D1* q, CenKin& k) {
     k.R[i] = k.R[pa] * (Rj * Rq);
     k.p[i] = k.p[pa] + k.R[pa] * dconst(m.jp[i][0], m.jp[i][1], m.jp[i][2]);
     k.ax[i] = k.R[i] * dconst(a[0], a[1], a[2]);
+  }
+  if (m.modelType == 1) {
+    // updateCentroidalDynamics, SingleRigidBodyDynamics branch (ocs2_centroidal_model/src/ModelHelperFunctions.cpp:61-79): Ag = [Ab 0] from the
+    // nominal centroidal inertia and com offset carried with the base; the frame placements above still follow the full kinematics
+    const DV3 rw = k.R[0] * dconst(m.comToBaseNominal[0], m.comToBaseNominal[1], m.comToBaseNominal[2]);
+    DM3 In, Rt;
+#pragma unroll
+    for (int e = 0; e < 9; ++e) In.m[e] = dmk(m.inertiaNominal[e]);
+#pragma unroll
+    for (int r = 0; r < 3; ++r)
+#pragma unroll
+      for (int e = 0; e < 3; ++e) Rt.m[3 * r + e] = k.R[0].m[3 * e + r];
+    const DM3 Iw = (k.R[0] * In) * Rt;
+    k.mass = dmk(m.mtot);
+    k.G = k.p[0] - rw;
+    DV3 mu = dconst(0, 0, 0);
+    for (int i = 0; i < NB; ++i) mu = mu + m.mass[i] * (k.p[i] + k.R[i] * dconst(m.com[i][0], m.com[i][1], m.com[i][2]));
+    k.Gcom = (1.0 / m.mtot) * mu;
+    for (int c = 3; c < NV; ++c)
+      for (int r = 0; r < 6; ++r) k.Ag[r][c - 3] = dmk(0.0);
+    for (int e = 0; e < 3; ++e) {
+      const DV3 hl = m.mtot * dcross(rw, k.Sw[e]);
+      const DV3 LG = Iw * k.Sw[e];
+      k.Ag[0][e] = hl.x; k.Ag[1][e] = hl.y; k.Ag[2][e] = hl.z;
+      k.Ag[3][e] = LG.x; k.Ag[4][e] = LG.y; k.Ag[5][e] = LG.z;
+    }
+    return;
   }
 #pragma unroll 1
   for (int i = 0; i < NB; ++i) {
@@ -120,6 +148,7 @@ HD void cenKinematics(const CenModel& m, const D1* q, CenKin& k) {
   }
   k.mass = k.M[0];
   k.G = (dmk(1.0) / k.mass) * k.mu[0];
+  k.Gcom = k.G;
 #pragma unroll 1
   for (int c = 3; c < NV; ++c) {
     const int b = (c < 6) ? 0 : c - 5;
@@ -325,8 +354,8 @@ HD void cenNodeDual(const CenOcpModel& m, const NodeIn& n, const double* torsoRe
       o.res[r++] = w[10] * (t.torsoVang.y - dmk(torsoRef[11]));
       o.res[r++] = w[11] * (t.torsoVang.z - dmk(torsoRef[12]));
     }
-    o.res[r++] = m.icpSqrtW * (0.5 * (t.footPos[0].x + t.footPos[1].x) - k.G.x);
-    o.res[r++] = m.icpSqrtW * (0.5 * (t.footPos[0].y + t.footPos[1].y) - k.G.y);
+    o.res[r++] = m.icpSqrtW * (0.5 * (t.footPos[0].x + t.footPos[1].x) - k.Gcom.x);
+    o.res[r++] = m.icpSqrtW * (0.5 * (t.footPos[0].y + t.footPos[1].y) - k.Gcom.y);
     for (int c = 0; c < 2; ++c) {
       const double* w = m.footSqrtW;
       o.res[r++] = w[0] * t.footPos[c].x;

@@ -177,6 +177,9 @@ inline HostModel loadModelFile(const std::string& path) {
         c2.torque_joint[s2][k] = static_cast<int32_t>(get("cen_torque_joint", 12)[6 * s2 + k]);
         c2.torque_w[s2][k] = get("cen_torque_w", 12)[6 * s2 + k];
       }
+    c2.model_type = static_cast<int32_t>(get("cen_model_type", 1)[0]);
+    for (int k = 0; k < 9; ++k) c2.inertia_nominal[k] = get("cen_inertia_nominal", 9)[k];
+    for (int k = 0; k < 3; ++k) c2.com_to_base_nominal[k] = get("cen_com_to_base_nominal", 3)[k];
   }
   m.initialState = get("x_init", m.nx);
   m.defaultJointState = get("default_joint_state", m.nj);

@@ -350,6 +350,42 @@ inline std::array<double, 6> centroidalBaseVelocity(const HostModel& m, const ve
   bool zero = true;
   for (int k = 0; k < 6; ++k) zero = zero && x0[k] == 0.0;
   if (zero) return bv;
+  if (m.cen.model_type == 1) {
+    // SingleRigidBodyDynamics: Ab = [[m 1, m [R r]x T], [0, R I R' T]] in closed form (ModelHelperFunctions.cpp:61-79)
+    const double z = x0[9], y = x0[10], xr = x0[11];
+    const double cz = std::cos(z), sz = std::sin(z), cy = std::cos(y), sy = std::sin(y), cx = std::cos(xr), sx = std::sin(xr);
+    const double R[9] = {cz * cy, cz * sy * sx - sz * cx, cz * sy * cx + sz * sx, sz * cy, sz * sy * sx + cz * cx, sz * sy * cx - cz * sx, -sy, cy * sx, cy * cx};
+    const double Sb[9] = {-sy, 0, 1, cy * sx, cx, 0, cy * cx, -sx, 0};
+    auto mul = [](const double* A, const double* B, double* C) {
+      for (int i = 0; i < 3; ++i)
+        for (int j = 0; j < 3; ++j) C[3 * i + j] = A[3 * i] * B[j] + A[3 * i + 1] * B[3 + j] + A[3 * i + 2] * B[6 + j];
+    };
+    double T[9], RI[9], Rt[9], RIRt[9], A22[9];
+    mul(R, Sb, T);
+    mul(R, m.cen.inertia_nominal, RI);
+    for (int i = 0; i < 3; ++i)
+      for (int j = 0; j < 3; ++j) Rt[3 * i + j] = R[3 * j + i];
+    mul(RI, Rt, RIRt);
+    mul(RIRt, T, A22);
+    const double* r0 = m.cen.com_to_base_nominal;
+    const double rw[3] = {R[0] * r0[0] + R[1] * r0[1] + R[2] * r0[2], R[3] * r0[0] + R[4] * r0[1] + R[5] * r0[2], R[6] * r0[0] + R[7] * r0[1] + R[8] * r0[2]};
+    // w = A22^-1 h_ang (cofactor inverse)
+    const double* A = A22;
+    const double c00 = A[4] * A[8] - A[5] * A[7], c01 = A[5] * A[6] - A[3] * A[8], c02 = A[3] * A[7] - A[4] * A[6];
+    const double det = A[0] * c00 + A[1] * c01 + A[2] * c02;
+    const double inv[9] = {c00 / det, (A[2] * A[7] - A[1] * A[8]) / det, (A[1] * A[5] - A[2] * A[4]) / det,
+                           c01 / det, (A[0] * A[8] - A[2] * A[6]) / det, (A[2] * A[3] - A[0] * A[5]) / det,
+                           c02 / det, (A[1] * A[6] - A[0] * A[7]) / det, (A[0] * A[4] - A[1] * A[3]) / det};
+    double w[3], Tw[3];
+    for (int i = 0; i < 3; ++i) w[i] = inv[3 * i] * x0[3] + inv[3 * i + 1] * x0[4] + inv[3 * i + 2] * x0[5];
+    for (int i = 0; i < 3; ++i) Tw[i] = T[3 * i] * w[0] + T[3 * i + 1] * w[1] + T[3 * i + 2] * w[2];
+    const double cr[3] = {rw[1] * Tw[2] - rw[2] * Tw[1], rw[2] * Tw[0] - rw[0] * Tw[2], rw[0] * Tw[1] - rw[1] * Tw[0]};
+    for (int i = 0; i < 3; ++i) {
+      bv[i] = (x0[i] - m.totalMass * cr[i]) / m.totalMass;
+      bv[3 + i] = w[i];
+    }
+    return bv;
+  }
   vector_t u(m.nu, 0.0), xd(m.nx, 0.0);
   if (b200sqp_centroidal_flow_map(&m.desc, 1, x0.data(), u.data(), xd.data(), nullptr, nullptr, device) != 0)
     throw std::runtime_error(std::string("[b200sqp::host] centroidalBaseVelocity: ") + b200sqp_last_error());

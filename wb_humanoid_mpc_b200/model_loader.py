@@ -424,6 +424,8 @@ def build_wb_model(urdf_path, task_path, reference_path=None, gait_path=None, ki
             targetDisplacementVelocity=info_float(ref, "targetDisplacementVelocity"),
             targetRotationVelocity=info_float(ref, "targetRotationVelocity"),
         )
+    if kind == "centroidal" and "reference" in model:
+        model["srbd_nominal"] = srbd_nominal(model, model["reference"]["defaultJointState"])
     if gait_path is not None:
         g = parse_info(gait_path)
         gaits = {}
@@ -435,6 +437,29 @@ def build_wb_model(urdf_path, task_path, reference_path=None, gait_path=None, ki
                 )
         model["gaits"] = gaits
     return model
+
+
+def srbd_nominal(model: dict, joint_angles) -> dict:
+    """createCentroidalModelInfo for the SingleRigidBodyDynamics type (ocs2_centroidal_model/src/FactoryFunctions.cpp:113-121): pinocchio::ccrba at
+    q = (0_6, nominalJointAngles) -> centroidal rotational inertia (about the centre of mass; world axes = base axes there) and base - com."""
+    nb = model["nj"] + 1
+    R, p = [np.eye(3)], [np.zeros(3)]
+    for i in range(1, nb):
+        pa = model["parent"][i]
+        a = np.asarray(model["joint_axis"][i], float)
+        th = joint_angles[i - 1]
+        K = np.array([[0, -a[2], a[1]], [a[2], 0, -a[0]], [-a[1], a[0], 0]])
+        Rq = np.eye(3) + math.sin(th) * K + (1 - math.cos(th)) * (K @ K)
+        R.append(R[pa] @ np.asarray(model["joint_R"][i]) @ Rq)
+        p.append(p[pa] + R[pa] @ np.asarray(model["joint_p"][i]))
+    ms = np.asarray(model["mass"])
+    c = np.array([p[i] + R[i] @ np.asarray(model["com"][i]) for i in range(nb)])
+    G = (ms[:, None] * c).sum(0) / ms.sum()
+    Ig = np.zeros((3, 3))
+    for i in range(nb):
+        d = c[i] - G
+        Ig += R[i] @ np.asarray(model["inertia"][i]) @ R[i].T + ms[i] * (d @ d * np.eye(3) - np.outer(d, d))
+    return dict(inertia=Ig.tolist(), com_to_base=(-G).tolist())
 
 
 def _ee_kinematics_weights(task, prefix) -> np.ndarray:
@@ -513,6 +538,9 @@ def write_flat(model: dict, path) -> None:
         L.append(rec("cen_icp_weight", [model["icp_weight"]]))
         L.append(rec("cen_torque_joint", [j for side in model["leg_torque_cost"] for j in side["joints"]]))
         L.append(rec("cen_torque_w", [w for side in model["leg_torque_cost"] for w in side["weights"]]))
+        L.append(rec("cen_model_type", [model.get("centroidalModelType", 0)]))
+        L.append(rec("cen_inertia_nominal", model["srbd_nominal"]["inertia"]))
+        L.append(rec("cen_com_to_base_nominal", model["srbd_nominal"]["com_to_base"]))
     L.append(rec("frame_body", frame_body))
     L.append(rec("frame_p", frame_p))
     for k in ("parent", "joint_R", "joint_p", "joint_axis", "mass", "com", "inertia", "q_lower", "q_upper", "contact_rect",
