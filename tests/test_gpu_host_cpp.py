@@ -50,6 +50,13 @@ def test_host_solver_matches_python_harness_cold_and_warm():
         assert np.allclose(lg[:, 3], r["log"][0, : lg.shape[0], LOG_FIELDS.index("merit")], rtol=1e-7)
         prev.append((py, references.to_primal_solution(inst["t_nodes"], inst["node_event"], r["x"][0], r["u"][0], inst["mode_schedule"])))
     assert host.benchmarks()[0] > 0.0
+    # sqp::Logger CSV (host/SqpLogging.hpp): the reference's 19 columns, one line per instance and iteration
+    csv = host.write_log(0.0).strip().split("\n")
+    assert csv[0].split(", ")[:3] == ["problemNumber", "time", "iteration"] and len(csv[0].split(", ")) == 19
+    assert len(csv) - 1 == sum(host.iterations_log(b).shape[0] for b in range(B))
+    row = csv[1].split(", ")
+    assert len(row) == 19 and int(row[0]) == 0 and float(row[10]) == host.iterations_log(0)[0, 6] and row[11] in ("Constraint", "Dual", "Cost", "Zero")
+    assert row[18] in ("Not Converged", "Maximum number of iterations reached")
 
     # receding horizon: second solve 3 nodes later, warm-started from the previous primal solution on both sides
     t1 = 3 * model["sqp"]["dt"]

@@ -3,6 +3,7 @@
 #include <cstring>
 #include <string>
 
+#include "SqpLogging.hpp"
 #include "SqpSolver.hpp"
 
 using namespace b200sqp::host;
@@ -225,6 +226,21 @@ int b200host_solver_get_log(void* s, int b, double* out /* [iters][12] */, int m
       o[11] = si.convergence;
     }
     return k;
+  });
+}
+// sqp::Logger CSV (header + one line per instance and iteration of the last run) into buf; returns the length needed (without the NUL)
+int b200host_solver_write_log(void* s, double time, char* buf, int cap) {
+  return guarded([&] {
+    std::ostringstream os;
+    os << logHeader();
+    writeLog(os, *static_cast<SqpSolver*>(s), time);
+    const std::string str = os.str();
+    if (buf && cap > 0) {
+      const size_t n = std::min(str.size(), static_cast<size_t>(cap - 1));
+      std::memcpy(buf, str.data(), n);
+      buf[n] = 0;
+    }
+    return static_cast<int>(str.size());
   });
 }
 int b200host_solver_benchmarks(void* s, double* ms) {

@@ -197,6 +197,15 @@ class HostSqpSolver:
         k = _check(lib().b200host_solver_get_log(self.h, b, _p(out), self.settings.sqp_iteration))
         return out[:k]
 
+    def write_log(self, time=0.0) -> str:
+        """sqp::Logger CSV of the last run (host/SqpLogging.hpp)"""
+        L = lib()
+        L.b200host_solver_write_log.argtypes = [C.c_void_p, C.c_double, C.c_char_p, C.c_int]
+        n = _check(L.b200host_solver_write_log(self.h, time, None, 0))
+        buf = C.create_string_buffer(n + 1)
+        _check(L.b200host_solver_write_log(self.h, time, buf, n + 1))
+        return buf.value.decode()
+
     def benchmarks(self):
         """ms: [LQ, QP, line search, projection share | host preRun, pack, upload, solve, download, unpack]"""
         ms = np.zeros(10)
