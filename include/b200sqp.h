@@ -216,6 +216,12 @@ typedef struct b200sqp_cen_desc {
 int b200sqp_cen_create(const b200sqp_model_desc* model, const b200sqp_cen_desc* cen, const b200sqp_settings* settings, int device,
                        b200sqp_handle* out);
 
+/* Joint-torque map of the MRT controllers (computeJointTorques, humanoid_common_mpc/src/pinocchio_model/DynamicsHelperFunctions.cpp:232-270;
+ * WBMpcMrtJointController.cpp:141): feed-forward torques of whole-body (x, u) samples, e.g. every node of a batch of primal solutions.
+ *   x [count][2*(6+nj)], u [count][12+nj] -> tau [count][nj]; qddb [count][6] = the base acceleration of computeBaseAcceleration, may be NULL.
+ * Host pointers; stateless. */
+int b200sqp_joint_torques(const b200sqp_model_desc* model, int count, const double* x, const double* u, double* tau, double* qddb, int device);
+
 /* Stage blocks of the last LQ approximation, for block-level parity tests:
  *   which = 0 raw (before projection): A [nx*nx] B [nx*nu] b [nx] Q S(nu x nx) R q r C(nc_max x nx) D(nc_max x nu) e nc
  *   see b200sqp_stage_layout for offsets. */

@@ -174,6 +174,30 @@ void wbFlowMap(const WbParams& P, const S* x, const S* u, S* xdot) {
   for (int j = 0; j < P.model.nj; ++j) xdot[nv + 6 + j] = u[12 + j];
 }
 
+// computeJointTorques (humanoid_common_mpc/src/pinocchio_model/DynamicsHelperFunctions.cpp:232-270): tau_j = M_j [qdd_b; qdd_j] + nle_j - (J' W)_j
+// with qdd_b from computeBaseAcceleration; M a + nle is one RNEA, the joint rows of J' W are axis . (M + (p_f - p_joint) x F) along each leg.
+inline void wbJointTorques(const WbParams& P, const double* x, const double* u, double* tau, double* qddbOut = nullptr) {
+  const RobotModel& m = P.model;
+  const int nv = m.nv();
+  double qddb[6];
+  KinData<double> kd;
+  wbBaseAcceleration<double>(P, x, u, qddb, &kd);   // kd: placements (zero-velocity pass)
+  std::vector<double> a(nv, 0.0), full(nv);
+  for (int k = 0; k < 6; ++k) a[k] = qddb[k];
+  for (int j = 0; j < m.nj; ++j) a[6 + j] = u[12 + j];
+  rnea<double>(m, x, x + nv, a.data(), full.data());
+  for (int c = 0; c < 2; ++c) {
+    const FrameKin<double> fk = frameKinematics(m, kd, P.contactFrame[c]);
+    const V3<double> F(u[6 * c], u[6 * c + 1], u[6 * c + 2]), Mo(u[6 * c + 3], u[6 * c + 4], u[6 * c + 5]);
+    for (int b = m.frameBody[P.contactFrame[c]]; b > 0; b = m.parent[b]) {
+      const V3<double> ax = kd.oMi[b].R * V3<double>(m.axis[b][0], m.axis[b][1], m.axis[b][2]);
+      full[5 + b] -= dot(ax, Mo + cross(fk.pos - kd.oMi[b].p, F));
+    }
+  }
+  for (int j = 0; j < m.nj; ++j) tau[j] = full[6 + j];
+  if (qddbOut) std::copy(qddb, qddb + 6, qddbOut);
+}
+
 // ---- end-effector quantities at (x,u) -------------------------------------------------------------------------------------------
 template <class S>
 struct FootState {

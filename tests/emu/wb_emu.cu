@@ -7,6 +7,7 @@
 
 #include "../../wb_humanoid_mpc_b200/csrc/wb_host.cuh"
 #include "../../wb_humanoid_mpc_b200/csrc/wb_dynamics.cuh"
+#include "../../wb_humanoid_mpc_b200/csrc/wb_torque.cuh"
 #ifdef EMU_WITH_LQ
 #include "../../wb_humanoid_mpc_b200/csrc/wb_lq.cuh"
 #include "../../wb_humanoid_mpc_b200/csrc/cen_host.cuh"
@@ -45,6 +46,16 @@ int emu_dyn(const b200sqp_model_desc* d, const double* x, const double* u, doubl
     RUN_PHASE(NT, dynPhaseFinal(P, m, u, w));
     RUN_PHASE(NT, dynWriteFlow(P, x, u, w, xdot));
   }
+  return 0;
+}
+
+int emu_joint_torques(const b200sqp_model_desc* d, const double* x, const double* u, double* tau, double* qddb) {
+  static WbDeviceModel m;
+  if (const char* e = makeDeviceModel(*d, m)) {
+    std::fprintf(stderr, "emu: %s\n", e);
+    return -1;
+  }
+  wbJointTorques(m, x, u, tau, qddb);
   return 0;
 }
 

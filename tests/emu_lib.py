@@ -86,3 +86,10 @@ def cen_node(desc, cdesc, x, u, xnext, xref, dt, contact, swing, impact, arm_pha
     n = nut.value
     return dict(A=A.T.copy(), B=Bt.T[:, :n].copy(), b=b, Q=Q.T.copy(), S=St.T[:n].copy(), R=Rt.T[:n, :n].copy(), q=q, r=rt[:n].copy(),
                 Pu=Pu.T[:, :n].copy(), Px=Px.T.copy(), u0=u0, nut=n, perf=perf, raw=unpack_raw_blocks(raw, CX, NU))
+
+
+def joint_torques(desc, x, u):
+    tau, qddb = np.zeros(23), np.zeros(6)
+    rc = lib().emu_joint_torques(C.byref(desc), _p(F(x)), _p(F(u)), _p(tau), _p(qddb))
+    assert rc == 0
+    return tau, qddb

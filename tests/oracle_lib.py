@@ -200,6 +200,11 @@ class WbOracle:
         self.L.orc_wb_base_accel_literal(self.h, _p(F(x)), _p(F(u)), _p(out))
         return out
 
+    def joint_torques(self, x, u):
+        tau, qddb = np.zeros(self.nj), np.zeros(6)
+        self.L.orc_wb_joint_torques(self.h, _p(F(x)), _p(F(u)), _p(tau), _p(qddb))
+        return tau, qddb
+
     def crba_nle(self, x):
         nv = 6 + self.nj
         M, nle = np.zeros((nv, nv)), np.zeros(nv)

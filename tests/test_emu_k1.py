@@ -62,3 +62,24 @@ def test_lq_node_blocks_and_projection(model, wb, contact):
     pr = orc.change_of_input_variables(r["A"], r["B"], r["b"], r["Q"], r["S"], r["R"], r["q"], r["r"], r["c"], e["Pu"], e["Px"], e["u0"])
     for k in ["A", "B", "b", "Q", "S", "R", "q", "r"]:
         assert rel(e[k], pr[k]) < 1e-10, k
+
+
+def test_joint_torque_map(model, wb):
+    """computeJointTorques: the thread-per-node world-frame recursion (csrc/wb_torque.cuh) against the oracle (RNEA - J'W) and, for the
+    oracle itself, the identity that the base rows of the same inverse dynamics vanish up to the dropped lin/ang coupling of M_bb"""
+    rng = np.random.default_rng(5)
+    for _ in range(4):
+        x, u = rand_state(model, rng), rand_input(model, rng)
+        tau, qddb = emu.joint_torques(wb.desc, x, u)
+        to, qo = wb.joint_torques(x, u)
+        assert np.max(np.abs(qddb - qo)) < 1e-10 * max(1.0, np.abs(qo).max())
+        assert np.max(np.abs(tau - to)) < 1e-10 * max(1.0, np.abs(to).max())
+        assert np.allclose(qo, wb.flow_map(x, u)[29:35], atol=1e-12)
+    # at rest under weight-compensating wrenches the knees carry load and the base does not accelerate
+    from wb_humanoid_mpc_b200 import references
+
+    x = np.array(model["x_init"], float)
+    x[29:] = 0.0
+    u = references.weight_compensating_input(model, [1, 1])
+    tau, qddb = emu.joint_torques(wb.desc, x, u)
+    assert np.abs(qddb[:3]).max() < 1e-9 and abs(tau[3]) > 1.0 and abs(tau[9]) > 1.0

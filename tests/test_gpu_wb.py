@@ -216,3 +216,21 @@ def test_flight_and_single_support_gaits_match_oracle(model, gait):
     # a different (equally valid) pivot order changes the conditioning of the projected QP: inputs and gains agree to 1e-6 / 1e-5 here
     assert rel(sol["u"][0], ref["u"]) < 1e-6
     assert rel(sol["K"][0], ref["K"]) < 1e-5
+
+
+def test_joint_torque_map_matches_oracle(model):
+    """b200sqp_joint_torques (MRT feed-forward torques) on every node of a solved batch against the oracle"""
+    from wb_humanoid_mpc_b200.solver import B200SqpSolver, joint_torques
+
+    rng = np.random.default_rng(8)
+    insts = make_instances(model, rng, [("walk", 1.1, [0.4, 0.0, 0.7925, 0.1]), ("stance", 1.1, None)])
+    sol = B200SqpSolver(model, abi.default_settings(model, sqp_iteration=2)).run(insts)
+    x, u = sol["x"][:, :-1], sol["u"]
+    tau, qddb = joint_torques(model, x, u)
+    assert tau.shape == (2, x.shape[1], 23) and qddb.shape == (2, x.shape[1], 6)
+    wb = orc.WbOracle(model)
+    for b in range(2):
+        for k in range(0, x.shape[1], 3):
+            to, qo = wb.joint_torques(x[b, k], u[b, k])
+            assert np.max(np.abs(tau[b, k] - to)) < 1e-9 * max(1.0, np.abs(to).max()), (b, k)
+            assert np.max(np.abs(qddb[b, k] - qo)) < 1e-9 * max(1.0, np.abs(qo).max()), (b, k)

@@ -16,6 +16,7 @@
 #ifdef B200SQP_WITH_WB
 #include "wb_solver.cuh"
 #include "cen_dynamics.cuh"
+#include "wb_torque.cuh"
 #include "cen_kernels.cuh"
 #include "cen_host.cuh"
 #endif

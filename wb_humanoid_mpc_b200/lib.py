@@ -130,6 +130,7 @@ EXPORTED_SYMBOLS = [
     "b200sqp_download_value_function",
     "b200sqp_centroidal_flow_map",
     "b200sqp_cen_create",
+    "b200sqp_joint_torques",
     "b200sqp_download_stage_blocks",
     "b200sqp_stage_doubles",
     "b200sqp_get_stage_times",

@@ -187,3 +187,15 @@ class B200SqpSolver:
         n = C.c_int64()
         _l.check(_l.lib().b200sqp_get_launch_count(self._h, C.byref(n)))
         return n.value
+
+
+def joint_torques(model: dict, x, u, device: int = 0):
+    """computeJointTorques for whole-body samples through the C ABI (b200sqp_joint_torques): x [..., nx], u [..., nu] -> (tau [..., nj],
+    qddb [..., 6]); e.g. x = sol["x"][:, :-1], u = sol["u"] of a batch of primal solutions."""
+    x, u = _f(x), _f(u)
+    lead = x.shape[:-1]
+    n = int(np.prod(lead)) if lead else 1
+    desc = abi.model_desc(model)
+    tau, qddb = np.zeros((n, model["nj"])), np.zeros((n, 6))
+    _l.check(_l.lib().b200sqp_joint_torques(C.byref(desc), C.c_int(n), _p(x.reshape(n, -1)), _p(u.reshape(n, -1)), _p(tau), _p(qddb), C.c_int(device)))
+    return tau.reshape(*lead, -1), qddb.reshape(*lead, 6)
