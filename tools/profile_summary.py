@@ -7,7 +7,11 @@ import subprocess
 import sys
 from pathlib import Path
 
+import os
+
 ROOT = Path(__file__).resolve().parents[1]
+LAUNCH_NOTE = os.environ.get("PROFILE_LAUNCH_NOTE", "bench.py --steps 2 --warmup 1, B=256, 115 nodes")
+FULL_NOTE = os.environ.get("PROFILE_FULL_NOTE", "bench.py --batch 64, one launch")
 GO, PR = ROOT / "gpurun_out", ROOT / "profiles"
 tag = sys.argv[1]
 kernels = [a.split(":") for a in sys.argv[2:]]
@@ -28,7 +32,7 @@ if ll.exists():
         except ValueError:
             pass
     tot = sum(sum(v) for v in agg.values())
-    out += [f"## launch list (`profiles/{ll.name}`; bench.py --steps 2 --warmup 1, B=256, 115 nodes)", "",
+    out += [f"## launch list (`profiles/{ll.name}`; {LAUNCH_NOTE})", "",
             "| kernel | launches | total ms | avg ms | share |", "|---|---|---|---|---|"]
     for k, v in sorted(agg.items(), key=lambda kv: -sum(kv[1])):
         out.append(f"| {k} | {len(v)} | {sum(v)/1e6:.3f} | {sum(v)/len(v)/1e6:.3f} | {sum(v)/tot:.3f} |")
@@ -51,7 +55,7 @@ for short, name in kernels:
     raw = subprocess.run(["ncu", "-i", str(rep), "--page", "raw", "--csv"], capture_output=True, text=True).stdout
     rows = list(csv.reader(raw.splitlines()))
     h, units, v = rows[0], rows[1], rows[-1]
-    out += [f"## {name}  (`ncu --set full`, bench.py --batch 64, one launch)", "", "| metric | unit | value |", "|---|---|---|"]
+    out += [f"## {name}  (`ncu --set full`, {FULL_NOTE})", "", "| metric | unit | value |", "|---|---|---|"]
     vals = {}
     for n in WANT:
         if n in h:
