@@ -97,7 +97,29 @@ class SqpSolver {
     std::map<int, std::vector<int>> members;
     for (int b = 0; b < batch_; ++b) members[inst[b].n_nodes()].push_back(b);
     bench_.hostPreRun = since(tPre);
-    for (auto& kv : members) solveGroup(kv.first, kv.second, inst);
+    if (members.size() == 1 || exclusiveSolve_) {
+      for (auto& kv : members) solveGroup(kv.first, kv.second, inst);
+      return;
+    }
+    // several node-count groups (mixed contact schedules): every group has its own handle and CUDA stream, so the groups are driven by one
+    // host thread each and their kernels overlap on the device -- small groups alone would leave most SMs idle
+    for (auto& kv : members) groups_[kv.first];   // create the map nodes up front: the threads only look them up
+    std::vector<std::thread> pool;
+    std::vector<std::exception_ptr> err(members.size());
+    size_t gi = 0;
+    for (auto& kv : members) {
+      pool.emplace_back([this, &kv, &inst, &err, gi] {
+        try {
+          solveGroup(kv.first, kv.second, inst);
+        } catch (...) {
+          err[gi] = std::current_exception();
+        }
+      });
+      ++gi;
+    }
+    for (auto& th : pool) th.join();
+    for (auto& e : err)
+      if (e) std::rethrow_exception(e);
   }
 
   // see solveGroup: serialise the device phase of this object with every other SqpSolver of the process that also opted in
@@ -243,10 +265,11 @@ class SqpSolver {
       std::copy(I.arm_phase.begin(), I.arm_phase.end(), arm + static_cast<size_t>(s) * n);
       std::copy(I.x_ref.begin(), I.x_ref.end(), xr + static_cast<size_t>(s) * n * nx);
     });
-    bench_.hostPack += since(tm);
+    Benchmarks local;
+    local.hostPack = since(tm);
     tm = now();
     check(b200sqp_upload_instances(G.h, x0, xi, ui, tn, ev, cf, sw, imp, arm, xr));
-    bench_.upload += since(tm);
+    local.upload = since(tm);
     tm = now();
     void* stream = nullptr;   // the handle's own non-blocking stream: several SqpSolver objects overlap on the device
     check(b200sqp_own_stream(G.h, &stream));
@@ -259,7 +282,7 @@ class SqpSolver {
     } else {
       check(b200sqp_solve(G.h, stream));
     }
-    bench_.solve += since(tm);
+    local.solve = since(tm);
     tm = now();
     double *x = G.st.x, *u = G.st.u;
     const int iters = settings_.sqp_iteration;
@@ -271,14 +294,14 @@ class SqpSolver {
       G.p.resize(static_cast<size_t>(Bg) * n * nx);
       check(b200sqp_download_value_function(G.h, G.P.data(), G.p.data()));
     }
-    bench_.download += since(tm);
+    local.download = since(tm);
     tm = now();
     float ms[4];
     check(b200sqp_get_stage_times(G.h, ms));
-    bench_.linearQuadraticApproximation += ms[0];
-    bench_.solveQp += ms[1];
-    bench_.linesearch += ms[2];
-    bench_.projectionShareOfLq += ms[3];
+    local.linearQuadraticApproximation = ms[0];
+    local.solveQp = ms[1];
+    local.linesearch = ms[2];
+    local.projectionShareOfLq = ms[3];
     for (int s = 0; s < Bg; ++s)
       if (status[s] != 0) throw std::runtime_error("[SqpSolver] Failed to solve QP");  // SqpSolver.cpp:306-308
     const int gid = nNodes;
@@ -302,7 +325,17 @@ class SqpSolver {
         log_[b].push_back(si);
       }
     });
-    bench_.hostUnpack += since(tm);
+    local.hostUnpack = since(tm);
+    std::lock_guard<std::mutex> lk(benchMutex_);   // groups may run on concurrent host threads
+    bench_.hostPack += local.hostPack;
+    bench_.upload += local.upload;
+    bench_.solve += local.solve;
+    bench_.download += local.download;
+    bench_.hostUnpack += local.hostUnpack;
+    bench_.linearQuadraticApproximation += local.linearQuadraticApproximation;
+    bench_.solveQp += local.solveQp;
+    bench_.linesearch += local.linesearch;
+    bench_.projectionShareOfLq += local.projectionShareOfLq;
   }
 
   static std::mutex& deviceToken(int device) {
@@ -310,6 +343,7 @@ class SqpSolver {
     return tokens[(device % 16 + 16) % 16];
   }
   bool exclusiveSolve_ = false;
+  std::mutex benchMutex_;
   HostModel model_;
   b200sqp_settings settings_;
   int device_, batch_, threads_ = 1;
