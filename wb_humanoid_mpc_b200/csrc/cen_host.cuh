@@ -1,5 +1,7 @@
 // Host-side conversion of (b200sqp_model_desc, b200sqp_cen_desc) into the centroidal device constant block.
 #pragma once
+#include <memory>
+
 #include "cen_solver.cuh"
 #include "wb_host.cuh"
 
@@ -35,7 +37,8 @@ inline const char* makeCenDeviceModel(const b200sqp_model_desc& d, const b200sqp
   if (c.torso_frame != NFRAMES) return "torso_frame must be the last entry (index 10) of the frame table";
   b200sqp_model_desc base = d;
   base.n_frames = NFRAMES;
-  static WbDeviceModel wm;
+  const std::unique_ptr<WbDeviceModel> wmp(new WbDeviceModel);
+  WbDeviceModel& wm = *wmp;
   if (const char* e = makeDeviceModel(base, wm)) return e;
   std::memset(&out, 0, sizeof(out));
   CenOcpModel& m = out.ocp;
