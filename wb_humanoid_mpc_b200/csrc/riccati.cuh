@@ -64,7 +64,24 @@ __host__ __device__ inline RicLayout riccati_layout(int nx, int nm) {
   L.total = 2 * L.pq + 2 * L.ab + L.w + 2 * L.y + 2 * L.rs + L.linv + L.vec;
   return L;
 }
-__host__ __device__ inline size_t riccati_smem_doubles(int nx, int numax) { return static_cast<size_t>(riccati_layout(nx, numax).total); }
+// Leading dimensions of the shared-memory operands of the one-CTA kernel: ld = 4 (mod 8) makes every DMMA fragment load conflict free.  A
+// fragment load reads, per half-warp, the doubles {r + ld*c : r, c in 0..3} (or {c + ld*r}); with 16 eight-byte banks these are 16 distinct
+// banks iff 4*ld = +-8... i.e. ld = 4 or 12 (mod 16); nx = 58 (ld 58 = 10 mod 16) paid a two-way conflict on every operand fetch.
+__host__ __device__ inline int ric_pad(int n) { return ((n + 3) & ~7) + 4; }
+__host__ __device__ inline RicLayout riccati_layout_padded(int nx, int nm) {
+  const int lx = ric_pad(nx), lm = ric_pad(nm);
+  RicLayout L;
+  L.pq = even_up(lx * (nx + 1));
+  L.ab = even_up(lx * (nx + 1 + nm));
+  L.w = L.ab;
+  L.y = even_up(lm * (nx + 1));
+  L.rs = even_up(lm * nm);
+  L.linv = even_up(lm * nm);
+  L.vec = even_up(nx) * 2 + even_up(nm) * 3 + 8;
+  L.total = 2 * L.pq + 2 * L.ab + L.w + 2 * L.y + 2 * L.rs + L.linv + L.vec;
+  return L;
+}
+__host__ __device__ inline size_t riccati_smem_doubles(int nx, int numax) { return static_cast<size_t>(riccati_layout_padded(nx, numax).total); }
 
 // asynchronous global -> shared copy of n doubles by the whole block (16-byte chunks when both sides allow it)
 __device__ __forceinline__ void async_copy(double* dst, const double* src, int n) {
@@ -76,6 +93,23 @@ __device__ __forceinline__ void async_copy(double* dst, const double* src, int n
   }
 }
 
+// the same for a (rows x cols) column-major block with source / destination leading dimensions lds / ldd
+__device__ __forceinline__ void async_copy_cols(double* dst, int ldd, const double* src, int lds, int rows, int cols) {
+  const bool wide = ((reinterpret_cast<uintptr_t>(src) | reinterpret_cast<uintptr_t>(dst)) & 15) == 0 && ((rows | lds | ldd) & 1) == 0;
+  if (wide) {
+    const int h = rows >> 1;
+    for (int i = threadIdx.x; i < h * cols; i += blockDim.x) {
+      const int c = i / h, r = 2 * (i - c * h);
+      __pipeline_memcpy_async(dst + r + c * ldd, src + r + c * lds, 16);
+    }
+  } else {
+    for (int i = threadIdx.x; i < rows * cols; i += blockDim.x) {
+      const int c = i / rows, r = i - c * rows;
+      __pipeline_memcpy_async(dst + r + c * ldd, src + r + c * lds, 8);
+    }
+  }
+}
+
 // NXT / NMT > 0: sizes fixed at compile time (the whole-body instantiation <58, 23>: index arithmetic folds to shifts and multiplies);
 // 0: read from the view (generic QP interface)
 template <int NXT, int NMT>
@@ -83,7 +117,8 @@ __global__ void __launch_bounds__(256, 1) riccati_kernel(QpDeviceView v) {
   extern __shared__ double sm[];
   const int inst = blockIdx.x;
   const int nx = NXT ? NXT : v.nx, nm = NMT ? NMT : v.numax, N = v.N, nx1 = nx + 1;
-  const RicLayout L = riccati_layout(nx, nm);
+  const RicLayout L = riccati_layout_padded(nx, nm);
+  const int lx = ric_pad(nx), lm = ric_pad(nm);   // leading dimensions of the nx-row / nm-row operands in the backward sweep
   double* PQ[2] = {sm, sm + L.pq};
   double* AB[2] = {sm + 2 * L.pq, sm + 2 * L.pq + L.ab};
   double* W = AB[1] + L.ab;
@@ -105,27 +140,30 @@ __global__ void __launch_bounds__(256, 1) riccati_kernel(QpDeviceView v) {
   // terminal stage: [P_N | p_N] = [Q_N + reg I | q_N]
   {
     const double* QN = v.Q + (iN1 + N) * nx * nx;
-    for (int i = threadIdx.x; i < nx * nx; i += blockDim.x) PQ[cur][i] = QN[i] + ((i % nx) == (i / nx) ? v.reg : 0.0);
-    block_copy(nx, v.q + (iN1 + N) * nx, PQ[cur] + nx * nx);
+    for (int i = threadIdx.x; i < nx * nx; i += blockDim.x) {
+      const int r = i % nx, c = i / nx;
+      PQ[cur][r + c * lx] = QN[i] + (r == c ? v.reg : 0.0);
+    }
+    block_copy(nx, v.q + (iN1 + N) * nx, PQ[cur] + lx * nx);
     __syncthreads();
     if (v.keepP) {
-      block_copy(nx * nx, PQ[cur], v.P + (iN1 + N) * nx * nx);
-      block_copy(nx, PQ[cur] + nx * nx, v.p + (iN1 + N) * nx);
+      for (int i = threadIdx.x; i < nx * nx; i += blockDim.x) v.P[(iN1 + N) * nx * nx + i] = PQ[cur][(i % nx) + (i / nx) * lx];
+      block_copy(nx, PQ[cur] + lx * nx, v.p + (iN1 + N) * nx);
     }
   }
   auto prefetch = [&](int k, int set, double* qdst) {
     const size_t sk = iN + k;
     const int nu = v.nu ? v.nu[sk] : nm;
-    async_copy(AB[set], v.A + sk * nx * nx, nx * nx);
-    async_copy(AB[set] + nx * nx, v.b + sk * nx, nx);
+    async_copy_cols(AB[set], lx, v.A + sk * nx * nx, nx, nx, nx);
+    async_copy(AB[set] + lx * nx, v.b + sk * nx, nx);
     if (nu > 0) {
-      async_copy(AB[set] + nx * nx1, v.Bm + sk * nx * nm, nx * nu);
-      async_copy(Y[set], v.S + sk * nm * nx, nm * nx);
-      async_copy(Y[set] + nm * nx, v.r + sk * nm, nu);
-      async_copy(Rs[set], v.R + sk * nm * nm, nm * nm);
+      async_copy_cols(AB[set] + lx * nx1, lx, v.Bm + sk * nx * nm, nx, nx, nu);
+      async_copy_cols(Y[set], lm, v.S + sk * nm * nx, nm, nm, nx);
+      async_copy(Y[set] + lm * nx, v.r + sk * nm, nu);
+      async_copy_cols(Rs[set], lm, v.R + sk * nm * nm, nm, nm, nm);
     }
-    async_copy(qdst, v.Q + (iN1 + k) * nx * nx, nx * nx);
-    async_copy(qdst + nx * nx, v.q + (iN1 + k) * nx, nx);
+    async_copy_cols(qdst, lx, v.Q + (iN1 + k) * nx * nx, nx, nx, nx);
+    async_copy(qdst + lx * nx, v.q + (iN1 + k) * nx, nx);
     __pipeline_commit();
   };
   prefetch(N - 1, 0, PQ[1 - cur]);
@@ -144,45 +182,45 @@ __global__ void __launch_bounds__(256, 1) riccati_kernel(QpDeviceView v) {
     __syncthreads();
     RIC_TICK(1)
     // ---- W = P [A | b | B] ; then W_b += p  (v = P b + p) ----------------------------------------------------------
-    par_mma_gemm<false, false, 4>(P, nx, nx1 + nu, nx, 1.0, Pc, nx, ABk, nx, W, nx);
+    par_mma_gemm<false, false, 4>(P, nx, nx1 + nu, nx, 1.0, Pc, lx, ABk, lx, W, lx);
     __syncthreads();
     RIC_TICK(2)
-    for (int i = threadIdx.x; i < nx; i += blockDim.x) W[nx * nx + i] += Pc[nx * nx + i];
+    for (int i = threadIdx.x; i < nx; i += blockDim.x) W[lx * nx + i] += Pc[lx * nx + i];
     __syncthreads();
     RIC_TICK(3)
     // [P | p] is dead: start streaming stage k-1 (its [Q | q] goes into that buffer)
     if (k > 0) prefetch(k - 1, 1 - set, Pc);
     // ---- [Q~ | q~] = [Q | q] + A'[W_A | v] (+reg), [S~ | r~] = [S | r] + B'[W_A | v], R~ = R + B'W_B (+reg) ----------------
-    par_mma_gemm<true, true, 4>(P, nx, nx1, nx, 1.0, ABk, nx, W, nx, Pn, nx);
+    par_mma_gemm<true, true, 4>(P, nx, nx1, nx, 1.0, ABk, lx, W, lx, Pn, lx);
     if (nu > 0) {
-      par_mma_gemm<true, true, 4>(P, nu, nx1, nx, 1.0, ABk + nx * nx1, nx, W, nx, Yk, nm);
-      par_mma_gemm<true, true, 3>(P, nu, nu, nx, 1.0, ABk + nx * nx1, nx, W + nx * nx1, nx, Rk, nm);
+      par_mma_gemm<true, true, 4>(P, nu, nx1, nx, 1.0, ABk + lx * nx1, lx, W, lx, Yk, lm);
+      par_mma_gemm<true, true, 3>(P, nu, nu, nx, 1.0, ABk + lx * nx1, lx, W + lx * nx1, lx, Rk, lm);
     }
     __syncthreads();
     RIC_TICK(4)
-    for (int i = threadIdx.x; i < nx; i += blockDim.x) Pn[i + i * nx] += v.reg;
-    for (int i = threadIdx.x; i < nu; i += blockDim.x) Rk[i + i * nm] += v.reg;
+    for (int i = threadIdx.x; i < nx; i += blockDim.x) Pn[i + i * lx] += v.reg;
+    for (int i = threadIdx.x; i < nu; i += blockDim.x) Rk[i + i * lm] += v.reg;
     __syncthreads();
     RIC_TICK(5)
     if (nu > 0) {
       // ---- R~ = L L', Linv = L^-1: fused, register resident, warp 0 ---------------------------------------------------------------
       if (threadIdx.x < 32) {
-        if (nm <= 8) warp_chol_inverse<8>(nu, Rk, nm, Linv, nm, &ok);
-        else if (nm <= 16) warp_chol_inverse<16>(nu, Rk, nm, Linv, nm, &ok);
-        else if (nm <= 24) warp_chol_inverse<24>(nu, Rk, nm, Linv, nm, &ok);
-        else warp_chol_inverse<32>(nu, Rk, nm, Linv, nm, &ok);
+        if (nm <= 8) warp_chol_inverse<8>(nu, Rk, lm, Linv, lm, &ok);
+        else if (nm <= 16) warp_chol_inverse<16>(nu, Rk, lm, Linv, lm, &ok);
+        else if (nm <= 24) warp_chol_inverse<24>(nu, Rk, lm, Linv, lm, &ok);
+        else warp_chol_inverse<32>(nu, Rk, lm, Linv, lm, &ok);
       }
       __syncthreads();
       RIC_TICK(6)
       // ---- [Yl | yl] = L^-1 [S~ | r~] (into W) ---------------------------------------------------------------------------------
       double* Yl = W;
-      double* Kout = W + even_up(nm * nx1);
-      par_mma_gemm<false, false, 4>(P, nu, nx1, nu, 1.0, Linv, nm, Yk, nm, Yl, nm);
+      double* Kout = W + even_up(lm * nx1);   // [K | k] keeps the dense leading dimension nm of its destination in HBM
+      par_mma_gemm<false, false, 4>(P, nu, nx1, nu, 1.0, Linv, lm, Yk, lm, Yl, lm);
       __syncthreads();
     RIC_TICK(8)
       // ---- [P | p] = [Q~ | q~] - Yl'[Yl | yl] ; [K | k] = -L^-T [Yl | yl] ---------------------------------------------------
-      par_mma_gemm<true, true, 4>(P, nx, nx1, nu, -1.0, Yl, nm, Yl, nm, Pn, nx);
-      par_mma_gemm<true, false, 4>(P, nu, nx1, nu, -1.0, Linv, nm, Yl, nm, Kout, nm);
+      par_mma_gemm<true, true, 4>(P, nx, nx1, nu, -1.0, Yl, lm, Yl, lm, Pn, lx);
+      par_mma_gemm<true, false, 4>(P, nu, nx1, nu, -1.0, Linv, lm, Yl, lm, Kout, nm);
       __syncthreads();
     RIC_TICK(9)
       for (int t = threadIdx.x; t < nm * nx; t += blockDim.x) v.K[sk * nm * nx + t] = (t % nm < nu) ? Kout[t] : 0.0;
@@ -192,17 +230,17 @@ __global__ void __launch_bounds__(256, 1) riccati_kernel(QpDeviceView v) {
     for (int t = threadIdx.x; t < nx * nx; t += blockDim.x) {
       const int i = t % nx, j = t / nx;
       if (i > j) {
-        const double m = 0.5 * (Pn[i + j * nx] + Pn[j + i * nx]);
-        Pn[i + j * nx] = m;
-        Pn[j + i * nx] = m;
+        const double m = 0.5 * (Pn[i + j * lx] + Pn[j + i * lx]);
+        Pn[i + j * lx] = m;
+        Pn[j + i * lx] = m;
       }
     }
     cur = 1 - cur;
     __syncthreads();
     RIC_TICK(10)
     if (v.keepP) {
-      block_copy(nx * nx, PQ[cur], v.P + (iN1 + k) * nx * nx);
-      block_copy(nx, PQ[cur] + nx * nx, v.p + (iN1 + k) * nx);
+      for (int i = threadIdx.x; i < nx * nx; i += blockDim.x) v.P[(iN1 + k) * nx * nx + i] = PQ[cur][(i % nx) + (i / nx) * lx];
+      block_copy(nx, PQ[cur] + lx * nx, v.p + (iN1 + k) * nx);
     }
   }
   __syncthreads();
