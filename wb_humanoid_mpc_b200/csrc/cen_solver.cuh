@@ -241,7 +241,7 @@ struct CenPjWs {
   int* iw;
 };
 HD size_t cenPjWsDoubles() {
-  return 2 * CNX * CNX + CNX + CNX * CNX + 2 * CNU * CNX + CNX + CNU + NC_MAX * NX + NC_MAX + NC_MAX * NU + NC_MAX * (NX + 1) + NC_MAX * NUT_MAX +
+  return 2 * CNX * CNX + CNX + CNX * CNX + 2 * CNU * CNX + CNX + CNU + NC_MAX * NX + NC_MAX + LU_LD * NU + NC_MAX * (NX + 1) + NC_MAX * NUT_MAX +
          CNU * CNX + CNU * NUT_MAX + CNU + 2 * CNU * CNX + CNU + 64;
 }
 HD void cenPjWsMap(double* b, CenPjWs& s) {
@@ -256,7 +256,7 @@ HD void cenPjWsMap(double* b, CenPjWs& s) {
   s.CD = s.r + CNU;
   s.ev = s.CD + NC_MAX * NX;
   s.LU = s.ev + NC_MAX;
-  s.Xt = s.LU + NC_MAX * NU;
+  s.Xt = s.LU + LU_LD * NU;
   s.Kt = s.Xt + NC_MAX * (NX + 1);
   s.Px = s.Kt + NC_MAX * NUT_MAX;
   s.Pu = s.Px + CNU * CNX;

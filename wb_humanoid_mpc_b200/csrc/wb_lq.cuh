@@ -129,7 +129,7 @@ struct PjWs {
   // cost change-of-variables views
   double *T11, *T12, *R11, *R21, *W, *V, *rr;   // nc x 58 (ld 14), nut x 58 (ld 23), nc x nc (ld 14), nut x nc (ld 23), nc x nut (ld 14), nut x nut (ld 23), 35 + 35
 };
-constexpr int PJ_SCRATCH = 3600;   // max over the phases: 1806 (projection), 1152 (dynamics), 2790 (swing rows), 3585 (cost change of variables)
+constexpr int PJ_SCRATCH = 3600;   // max over the phases: 1841 (projection), 1152 (dynamics), 2790 (swing rows), 3585 (cost change of variables)
 HD size_t pjWsDoubles() {
   return NX * NX + NU * NX + NU * NU + 1 + NZ + 1 + NX + NC_MAX * (NX + 1) + NC_MAX * NUT_MAX + 12 * NZ + JU_MAX * NUC + PJ_SCRATCH + 48;
 }
@@ -148,7 +148,7 @@ HD void pjWsMap(double* base, PjWs& s) {
   // phase 1 (projection): CD | e | LU | triangular-solve workspace
   s.CD = s.scratch;                          // 14 x 93 = 1302
   s.ev = s.CD + NC_MAX * NZ;                 // 14
-  s.LU = s.ev + NC_MAX;                      // 14 x 35 = 490
+  s.LU = s.ev + NC_MAX;                      // 14 x 35 with ld LU_LD = 525
   // dynamics change of variables
   s.B1 = s.scratch;                          // 12 x 14 = 168
   s.D12 = s.B1 + 12 * NC_MAX;                // 12 x 82 = 984
@@ -577,6 +577,10 @@ HD void costPhaseGradient(Par P, const NodeIn& n, const double* JU, const double
   for (int it = P.tid; it < JU_MAX * NUC; it += P.nt) midJU[it] = (it % JU_MAX < nr) ? JU[it] : 0.0;
 }
 
+// Leading dimension of the LU work matrix (nc <= 14 rows x 35 columns, lane = column): odd, so that the 32 lanes walking a row hit distinct
+// shared-memory banks (ld 14 put lanes j and j + 8 on the same bank).
+constexpr int LU_LD = 15;
+
 // ---- projection: Eigen::FullPivLU semantics (complete pivoting; particular solution with free variables = 0; kernel basis) ----------------
 // Whole factorisation by ONE warp: lane l owns columns l and l+32; pivot search = per-lane scan + shuffle arg-max with ties resolved
 // towards the smaller column-major index (the first maximum of Eigen's / the oracle's scan).  Host harness: sequential.
@@ -590,7 +594,7 @@ HD void luPhaseFactor(Par P, int nc, double* LU, int* rowOf, int* colOf) {
     for (int j = lane; j < NU; j += 32)
       if (j >= k)
         for (int i = k; i < nc; ++i) {
-          const double a = fabs(LU[i + NC_MAX * j]);
+          const double a = fabs(LU[i + LU_LD * j]);
           if (a > best) {
             best = a;
             bidx = j * NC_MAX + i;
@@ -608,16 +612,16 @@ HD void luPhaseFactor(Par P, int nc, double* LU, int* rowOf, int* colOf) {
     const int pj = bidx / NC_MAX, pi = bidx % NC_MAX;
     if (pi != k)
       for (int j = lane; j < NU; j += 32) {
-        const double t = LU[k + NC_MAX * j];
-        LU[k + NC_MAX * j] = LU[pi + NC_MAX * j];
-        LU[pi + NC_MAX * j] = t;
+        const double t = LU[k + LU_LD * j];
+        LU[k + LU_LD * j] = LU[pi + LU_LD * j];
+        LU[pi + LU_LD * j] = t;
       }
     __syncwarp();
     if (pj != k)
       for (int i = lane; i < nc; i += 32) {
-        const double t = LU[i + NC_MAX * k];
-        LU[i + NC_MAX * k] = LU[i + NC_MAX * pj];
-        LU[i + NC_MAX * pj] = t;
+        const double t = LU[i + LU_LD * k];
+        LU[i + LU_LD * k] = LU[i + LU_LD * pj];
+        LU[i + LU_LD * pj] = t;
       }
     if (lane == 0) {
       int t = rowOf[k];
@@ -628,12 +632,12 @@ HD void luPhaseFactor(Par P, int nc, double* LU, int* rowOf, int* colOf) {
       colOf[pj] = t;
     }
     __syncwarp();
-    const double piv = LU[k + NC_MAX * k];
-    for (int i = k + 1 + lane; i < nc; i += 32) LU[i + NC_MAX * k] /= piv;
+    const double piv = LU[k + LU_LD * k];
+    for (int i = k + 1 + lane; i < nc; i += 32) LU[i + LU_LD * k] /= piv;
     __syncwarp();
     for (int j = k + 1 + lane; j < NU; j += 32) {
-      const double ukj = LU[k + NC_MAX * j];
-      for (int i = k + 1; i < nc; ++i) LU[i + NC_MAX * j] = fma(-LU[i + NC_MAX * k], ukj, LU[i + NC_MAX * j]);
+      const double ukj = LU[k + LU_LD * j];
+      for (int i = k + 1; i < nc; ++i) LU[i + LU_LD * j] = fma(-LU[i + LU_LD * k], ukj, LU[i + LU_LD * j]);
     }
     __syncwarp();
   }
@@ -644,7 +648,7 @@ HD void luPhaseFactor(Par P, int nc, double* LU, int* rowOf, int* colOf) {
     double best = -1.0;
     for (int j = k; j < NU; ++j)
       for (int i = k; i < nc; ++i) {
-        const double a = fabs(LU[i + NC_MAX * j]);
+        const double a = fabs(LU[i + LU_LD * j]);
         if (a > best) {
           best = a;
           pi = i;
@@ -653,9 +657,9 @@ HD void luPhaseFactor(Par P, int nc, double* LU, int* rowOf, int* colOf) {
       }
     if (pi != k) {
       for (int j = 0; j < NU; ++j) {
-        const double t = LU[k + NC_MAX * j];
-        LU[k + NC_MAX * j] = LU[pi + NC_MAX * j];
-        LU[pi + NC_MAX * j] = t;
+        const double t = LU[k + LU_LD * j];
+        LU[k + LU_LD * j] = LU[pi + LU_LD * j];
+        LU[pi + LU_LD * j] = t;
       }
       const int t = rowOf[k];
       rowOf[k] = rowOf[pi];
@@ -663,19 +667,19 @@ HD void luPhaseFactor(Par P, int nc, double* LU, int* rowOf, int* colOf) {
     }
     if (pj != k) {
       for (int i = 0; i < nc; ++i) {
-        const double t = LU[i + NC_MAX * k];
-        LU[i + NC_MAX * k] = LU[i + NC_MAX * pj];
-        LU[i + NC_MAX * pj] = t;
+        const double t = LU[i + LU_LD * k];
+        LU[i + LU_LD * k] = LU[i + LU_LD * pj];
+        LU[i + LU_LD * pj] = t;
       }
       const int t = colOf[k];
       colOf[k] = colOf[pj];
       colOf[pj] = t;
     }
-    const double piv = LU[k + NC_MAX * k];
-    for (int i = k + 1; i < nc; ++i) LU[i + NC_MAX * k] /= piv;
+    const double piv = LU[k + LU_LD * k];
+    for (int i = k + 1; i < nc; ++i) LU[i + LU_LD * k] /= piv;
     for (int j = k + 1; j < NU; ++j) {
-      const double ukj = LU[k + NC_MAX * j];
-      for (int i = k + 1; i < nc; ++i) LU[i + NC_MAX * j] = fma(-LU[i + NC_MAX * k], ukj, LU[i + NC_MAX * j]);
+      const double ukj = LU[k + LU_LD * j];
+      for (int i = k + 1; i < nc; ++i) LU[i + LU_LD * j] = fma(-LU[i + LU_LD * k], ukj, LU[i + LU_LD * j]);
     }
   }
 #endif
@@ -696,14 +700,14 @@ HD void luPhaseSolveDirect(Par P, int nc, const double* LU, const int* rowOf, co
         if (i < nc) {
           double s = z[i];
 #pragma unroll
-          for (int j = 0; j < i; ++j) s = fma(-LU[i + NC_MAX * j], z[j], s);
+          for (int j = 0; j < i; ++j) s = fma(-LU[i + LU_LD * j], z[j], s);
           z[i] = s;
         }
       }
     } else {
       const int kk = it - NX - 1;
 #pragma unroll
-      for (int i = 0; i < NC_MAX; ++i) z[i] = (i < nc) ? LU[i + NC_MAX * (nc + kk)] : 0.0;
+      for (int i = 0; i < NC_MAX; ++i) z[i] = (i < nc) ? LU[i + LU_LD * (nc + kk)] : 0.0;
     }
 #pragma unroll
     for (int i = NC_MAX - 1; i >= 0; --i) {
@@ -711,8 +715,8 @@ HD void luPhaseSolveDirect(Par P, int nc, const double* LU, const int* rowOf, co
         double s = z[i];
 #pragma unroll
         for (int j = i + 1; j < NC_MAX; ++j)
-          if (j < nc) s = fma(-LU[i + NC_MAX * j], z[j], s);
-        z[i] = s / LU[i + NC_MAX * i];
+          if (j < nc) s = fma(-LU[i + LU_LD * j], z[j], s);
+        z[i] = s / LU[i + LU_LD * i];
       }
     }
     double* dst = (it <= NX) ? Xt + NC_MAX * it : Kt + NC_MAX * (it - NX - 1);
