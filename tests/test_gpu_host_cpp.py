@@ -166,3 +166,63 @@ def test_host_solver_centroidal_matches_python_harness():
         assert dx < 1e-6, (b, dx)
     host.close()
     hm.close()
+
+
+def test_double_buffered_solvers_and_concurrent_groups_reproduce_the_serial_result():
+    """two SqpSolver objects on two host threads with setExclusiveSolve (the double-buffering pattern of bench.py) and a mixed batch whose
+    node-count groups are solved concurrently: every instance must come out exactly as from a single solver run on its own"""
+    import threading
+
+    model = model_loader.load_packaged_model()
+    hm = host_lib.HostModel()
+    rng = np.random.default_rng(21)
+    B, horizon = 6, 1.1
+    gaits = ["walk", "stance", "slow_walk", "walk", "trot", "stance"]   # several node counts -> several groups per solver
+    x0s = []
+    for _ in range(B):
+        x0 = np.array(model["x_init"], float)
+        x0[2] = model["reference"]["defaultBaseHeight"]
+        x0[6:29] += rng.uniform(-0.05, 0.05, 23)
+        x0s.append(x0)
+    x0s = np.array(x0s)
+    st = abi.default_settings(model, sqp_iteration=2)
+
+    def make():
+        s = host_lib.HostSqpSolver(hm, st, B)
+        for b in range(B):
+            s.set_gait(b, gaits[b], 0.0, 3 * horizon)
+            s.set_command(b, 0.0, x0s[b], [0.3, 0.0, model["reference"]["defaultBaseHeight"], 0.1], horizon)
+        return s
+
+    ref = make()
+    ref.set_exclusive_solve(True)   # exclusive mode solves the groups one after the other: the serial reference
+    ref.run(0.0, x0s, horizon)
+    want = [ref.primal_solution(b)["x"].copy() for b in range(B)]
+    assert len({w.shape[0] for w in want}) > 1   # the batch really has several node counts
+
+    conc = make()                   # default mode: groups concurrently, one host thread and CUDA stream per group
+    conc.run(0.0, x0s, horizon)
+    for b in range(B):
+        assert np.array_equal(conc.primal_solution(b)["x"], want[b]), b
+
+    pair = [make(), make()]
+    for s in pair:
+        s.set_exclusive_solve(True)
+
+    def work(s):
+        for _ in range(3):
+            s.reset()
+            s.run(0.0, x0s, horizon)
+
+    th = [threading.Thread(target=work, args=(s,)) for s in pair]
+    for t in th:
+        t.start()
+    for t in th:
+        t.join()
+    for s in pair:
+        for b in range(B):
+            assert np.array_equal(s.primal_solution(b)["x"], want[b]), b
+        s.close()
+    ref.close()
+    conc.close()
+    hm.close()
