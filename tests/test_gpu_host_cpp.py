@@ -176,8 +176,8 @@ def test_double_buffered_solvers_and_concurrent_groups_reproduce_the_serial_resu
     model = model_loader.load_packaged_model()
     hm = host_lib.HostModel()
     rng = np.random.default_rng(21)
-    B, horizon = 6, 1.1
-    gaits = ["walk", "stance", "slow_walk", "walk", "trot", "stance"]   # several node counts -> several groups per solver
+    B, horizon = 6, 1.5
+    gaits = ["walk", "stance", "slow_walk", "walk", "trot", "stance"]   # node counts 50 / 48 / 47 at this horizon -> three groups per solver
     x0s = []
     for _ in range(B):
         x0 = np.array(model["x_init"], float)
