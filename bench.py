@@ -260,10 +260,22 @@ def main():
     # overlap the LQ approximation of the other.  Every step still moves its own inputs and results; this is the serving pattern.
     e2e = e2e_serial
     e2e_pipe = None
+    solvers = None
     if not args.global_step and args.steps >= 2:
         import threading
 
-        solvers = [solver, B200SqpSolver(model, settings, device=local_rank)]
+        try:   # the second handle doubles the device footprint (4.1 GB per 256 instances): very large per-GPU batches fall back to serial
+            solvers = [solver, B200SqpSolver(model, settings, device=local_rank)]
+            solvers[1].upload(pinned)
+        except Exception as e:
+            print(f"bench.py: double-buffered e2e unavailable ({e!r}); reporting the serial number", file=sys.stderr)
+            solvers = None
+        if dist is not None:   # the double-buffered leg contains barriers: every rank runs it or none does
+            okt = torch.tensor([1 if solvers is not None else 0], dtype=torch.int32, device="cuda")
+            dist.all_reduce(okt, op=dist.ReduceOp.MIN)
+            if int(okt.item()) == 0:
+                solvers = None
+    if solvers is not None:
         streams = [torch.cuda.Stream(), torch.cuda.Stream()]
         outs = [{"x": pin(np.zeros((B, n_nodes, nx))), "u": pin(np.zeros((B, n_nodes - 1, nu)))} for _ in range(2)]
         results = [None, None]
