@@ -1,3 +1,5 @@
+"""Experiment (GPU box): host-thread count of b200sqp::host::SqpSolver and the double-buffering pattern -- one solver object vs. two objects on
+two host threads with setExclusiveSolve; prints ms per run() and the host-side stage split.  Result recorded in DESIGN.md section 5/6."""
 import sys, threading, time
 from pathlib import Path
 import numpy as np

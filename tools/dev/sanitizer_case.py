@@ -1,3 +1,5 @@
+"""compute-sanitizer case: one small whole-body solve with feedback gains and value function (memcheck / racecheck run on a GPU box:
+compute-sanitizer --tool memcheck python tools/dev/sanitizer_case.py)."""
 import numpy as np, sys
 sys.path.insert(0,'/root/repo'); sys.path.insert(0,'/root/repo/tests')
 from wb_humanoid_mpc_b200 import abi, model_loader

@@ -1,3 +1,5 @@
+"""Experiment (GPU box): bandwidth of b200sqp_upload_instances / b200sqp_download against a plain pinned torch copy of the same bytes
+(found the row-granular cudaMemcpy2D slowdown that the contiguous-copy path for unpadded states fixes)."""
 import sys, time
 from pathlib import Path
 import numpy as np, torch
