@@ -146,7 +146,9 @@ void b200sqp_host_free(void* p);
  * (device-to-device restore, no host traffic). */
 int b200sqp_reset(b200sqp_handle h);
 
-/* SqpSolver::runImpl for every instance; asynchronous on `stream`. */
+/* SqpSolver::runImpl for every instance.  All kernels are enqueued on `stream` (NULL = the legacy default stream); the call returns when the
+ * last of them has finished: the filter line search reads the number of pending instances after every trial, like the reference's
+ * synchronous runImpl.  Several handles driven from several host threads overlap on the device (b200sqp_own_stream). */
 int b200sqp_solve(b200sqp_handle h, void* stream);
 
 /* A non-blocking CUDA stream owned by the handle, for callers without CUDA headers: b200sqp_solve(h, stream) on it lets several handles
