@@ -197,3 +197,25 @@ def test_srbd_model_file_and_base_velocity(cmodel, tmp_path):
     x0[9:12] = rng.uniform(-0.4, 0.4, 3)
     assert np.allclose(hm.base_velocity(x0), centroidal.base_velocity(m1, x0), rtol=0, atol=1e-14)
     hm.close()
+
+
+def test_example_application_compiles_links_and_fails_loudly_without_a_gpu(tmp_path):
+    """examples/host_batch.cpp: the header-only host layer + SqpLogging build warning-free against the C ABI alone; without a CUDA device
+    the application must stop with the library's error (no CPU fallback)"""
+    import subprocess
+    from pathlib import Path
+
+    from wb_humanoid_mpc_b200 import lib
+
+    root = Path(__file__).resolve().parents[1]
+    lib.lib()   # make sure libb200sqp.so exists
+    exe = tmp_path / "host_batch"
+    pkg = root / "wb_humanoid_mpc_b200"
+    res = subprocess.run(["g++", "-std=c++17", "-O1", "-Wall", "-Wextra", "-Werror", f"-I{root}", str(root / "examples" / "host_batch.cpp"), f"-L{pkg}", "-lb200sqp",
+                          "-pthread", f"-Wl,-rpath,{pkg}", "-o", str(exe)], capture_output=True, text=True)
+    assert res.returncode == 0, res.stderr
+    import torch
+
+    if not torch.cuda.is_available():
+        run = subprocess.run([str(exe), str(pkg / "data" / "g1_wb_model.txt"), "2"], capture_output=True, text=True, cwd=tmp_path)
+        assert run.returncode == 1 and "no CPU fallback" in run.stderr
