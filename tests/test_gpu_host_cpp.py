@@ -1,6 +1,7 @@
 """b200sqp::host::SqpSolver (C++ mirror of ocs2::SqpSolver over the C ABI) against the Python harness: same instances -> same primal
 (the two instance builders agree to 1e-13, not bitwise, so the solutions agree to solver conditioning: 1e-9 on x)
-solution, iteration log and warm-started second solve; mixed gaits exercise the grouping by node count."""
+solution, iteration log and warm-started second solve (grouping by node count: the last test of this file, where the gaits really differ in
+their node counts)."""
 import numpy as np
 import pytest
 
