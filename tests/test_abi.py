@@ -66,3 +66,26 @@ def test_product_does_not_import_the_oracle():
         if p.suffix in (".py", ".cu", ".cuh", ".inc", ".h"):
             t = p.read_text()
             assert "oracle_lib" not in t and "liboracle" not in t and "libwbemu" not in t and "orc_" not in t, p
+
+
+def test_product_never_touches_the_oracle():
+    """oracle/ is test infrastructure: no source of the product package may import, include, link or dlopen it (only tests/, smoke() and
+    bench.py's CPU legs do)"""
+    import re
+    from pathlib import Path
+
+    root = Path(__file__).resolve().parents[1]
+    pat = re.compile(r"(import\s+oracle_lib|from\s+oracle_lib|liboracle|#include\s+[\"<][^\"<>]*oracle/|\borc_[a-z_]+\s*\()")
+    bad = []
+    for f in (root / "wb_humanoid_mpc_b200").rglob("*"):
+        if f.suffix in {".py", ".cpp", ".hpp", ".cu", ".cuh", ".inc", ".h"}:
+            for n, line in enumerate(f.read_text(errors="ignore").splitlines(), 1):
+                if pat.search(line):
+                    bad.append(f"{f.relative_to(root)}:{n}: {line.strip()}")
+    for f in (root / "include").glob("*.h"):
+        if pat.search(f.read_text()):
+            bad.append(str(f))
+    assert not bad, "\n".join(bad)
+    # bench.py: the oracle only inside the CPU-baseline / reference legs
+    src = (root / "bench.py").read_text()
+    assert src.count("import oracle_lib") <= 2 and "def oracle_batch_solve" in src
