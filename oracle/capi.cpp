@@ -6,6 +6,7 @@
 
 #include "sqp.hpp"
 #include "test_problems.hpp"
+#include "trajectory_spreading.hpp"
 #ifdef ORC_WITH_WB
 #include "wb_problem.hpp"
 #include "cen_dynamics.hpp"
@@ -55,6 +56,32 @@ void storeLog(const std::vector<IterationLog>& log, double* out, int cap, int* n
 }  // namespace
 
 extern "C" {
+
+// trajectorySpread on flat arrays, in place: t [n], x [n][nx], tags [n] (an integer tag per sample, e.g. its mode), events [n_events_in] (one value per
+// event of the old trajectory, filtered with extractEventsArray).  Returns the new length; flags = {willTruncate, willSpread};
+// post [<= n] receives the updated post-event indices (n_post), events_out the kept event data (n_events_out).
+int orc_trajectory_spread(int n_old_ev, const double* old_ev, const int* old_modes, int n_new_ev, const double* new_ev, const int* new_modes, int n, int nx,
+                          double* t, double* x, int* tags, int* flags, int* post, int* n_post, int n_events_in, const double* events_in,
+                          double* events_out, int* n_events_out) {
+  oracle::SpreadSchedule o{std::vector<double>(old_ev, old_ev + n_old_ev), std::vector<int>(old_modes, old_modes + n_old_ev + 1)};
+  oracle::SpreadSchedule w{std::vector<double>(new_ev, new_ev + n_new_ev), std::vector<int>(new_modes, new_modes + n_new_ev + 1)};
+  std::vector<double> tv(t, t + n), xv(x, x + static_cast<size_t>(n) * nx), gv(tags, tags + n);
+  const oracle::SpreadPlan plan = oracle::spreadPlan(o, w, tv);
+  const size_t m = oracle::spreadApply(plan, xv, nx);
+  oracle::spreadApply(plan, gv, 1);
+  oracle::spreadApplyTime(plan, tv);
+  std::copy(tv.begin(), tv.end(), t);
+  std::copy(xv.begin(), xv.end(), x);
+  for (size_t i = 0; i < m; ++i) tags[i] = static_cast<int>(gv[i]);
+  flags[0] = plan.willTruncate;
+  flags[1] = plan.willSpread;
+  *n_post = static_cast<int>(plan.postEventIndices.size());
+  for (size_t i = 0; i < plan.postEventIndices.size(); ++i) post[i] = static_cast<int>(plan.postEventIndices[i]);
+  int ne = 0;
+  for (size_t i = plan.keepEventsFirst; i < plan.keepEventsLast && static_cast<int>(i) < n_events_in; ++i) events_out[ne++] = events_in[i];
+  *n_events_out = ne;
+  return static_cast<int>(m);
+}
 
 int orc_time_discretization(double t0, double tf, double dt, const double* ev, int nev, double* t_out, int* ev_out, int cap) {
   auto td = timeDiscretizationWithEvents(t0, tf, dt, std::vector<double>(ev, ev + nev));

@@ -57,6 +57,23 @@ def time_discretization(t0, tf, dt, events):
     return t[:n].copy(), e[:n].copy()
 
 
+def trajectory_spread(old_events, old_modes, new_events, new_modes, t, x, tags, event_data=()):
+    """oracle/trajectory_spreading.hpp on flat arrays -> dict(t, x, tags, will_truncate, will_spread, post_event_indices, event_data)"""
+    oe, ne = F(old_events), F(new_events)
+    om, nm = np.ascontiguousarray(old_modes, dtype=np.int32), np.ascontiguousarray(new_modes, dtype=np.int32)
+    t, x = np.array(t, dtype=np.float64, order="C"), np.array(x, dtype=np.float64, order="C")
+    tags = np.array(tags, dtype=np.int32, order="C")
+    fl, post, npost = np.zeros(2, dtype=np.int32), np.zeros(len(t) + 1, dtype=np.int32), C.c_int(0)
+    ev_in = F(event_data)
+    ev_out, nev = np.zeros(len(ev_in) + 1), C.c_int(0)
+    L = lib()
+    L.orc_trajectory_spread.restype = C.c_int
+    m = L.orc_trajectory_spread(C.c_int(len(oe)), _p(oe), _pi(om), C.c_int(len(ne)), _p(ne), _pi(nm), C.c_int(len(t)), C.c_int(x.shape[1]), _p(t), _p(x),
+                                _pi(tags), _pi(fl), _pi(post), C.byref(npost), C.c_int(len(ev_in)), _p(ev_in), _p(ev_out), C.byref(nev))
+    return dict(t=t[:m], x=x[:m], tags=tags[:m], will_truncate=bool(fl[0]), will_spread=bool(fl[1]), post_event_indices=post[: npost.value].tolist(),
+                event_data=ev_out[: nev.value])
+
+
 def riccati(A, B, b, Q, S, R, q, r, dx0, nu=None, reg=1e-12):
     """Padded stage arrays: A (N,nx,nx) etc. given as numpy arrays in math layout [k, row, col]."""
     N, nx = A.shape[0], A.shape[1]

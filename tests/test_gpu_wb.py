@@ -131,6 +131,49 @@ def test_full_size_properties(model):
         assert ms[0] > 0 and ms[1] > 0 and ms[2] > 0
 
 
+@pytest.mark.parametrize("gait,cmd", [("walk", [0.5, 0.0, 0.7925, 0.0]), ("stance", None)])
+def test_benchmark_size_matches_oracle(model, gait, cmd):
+    """BASELINE configs[2] at its REAL size -- horizon 3.5 s, dt 0.035 (100 intervals; `walk` adds 14 event nodes => 115 nodes), cold start,
+    sqpIteration 1 -- GPU (C ABI) against the oracle on the same instance: LQ blocks of every stage, the QP step (dx, remapped du), the
+    remapped gains K, all ten PerformanceIndex log fields, accepted step size / step type / convergence code and the primal trajectory.
+
+    Tolerances: blocks 1e-9 relative (as at the short horizons).  The QP outputs go through 114 sequential Riccati stages; the backward
+    recursion is contractive in exact arithmetic but each stage re-amplifies the 1e-15 block differences by cond(R~) (~1e6 with the
+    friction-cone barrier Hessians next to 1e-3 input weights), so the relative difference of dx/du/K grows from ~1e-9 at N = 30 to ~1e-8 at
+    N = 114; the test allows 1e-7 for the trajectory and the step and 1e-6 for the gains, like the short-horizon tests."""
+    from wb_humanoid_mpc_b200.solver import B200SqpSolver
+
+    rng = np.random.default_rng(31)
+    inst = make_instances(model, rng, [(gait, 3.5, cmd)])[0]
+    n = len(inst["t_nodes"])
+    assert n == (115 if gait == "walk" else 101)
+    st = abi.default_settings(model, sqp_iteration=1, use_feedback_policy=1)
+    solver = B200SqpSolver(model, st, capture_raw_blocks=True)
+    sol = solver.run([inst])
+    raw = solver.raw_stage_blocks()
+    ref = oracle_solve(model, inst, st, keep_raw=True)
+    assert not sol["status"].any()
+    for k in range(n - 1):
+        g = orc.unpack_raw_blocks(raw[0, k], 58, 35)
+        o = ref["raw"][k]
+        assert g["nc"] == o["nc"], k
+        for key in ["A", "B", "b", "Q", "S", "R", "q", "r", "C", "D", "e"]:
+            assert rel(g[key], o[key]) < 1e-9, (k, key, rel(g[key], o[key]))
+    g, o = sol["log"][0, 0], ref["log"][0]
+    assert g[8] == o[8] and int(g[9]) == int(o[9]) and int(g[13]) == int(o[13])
+    alpha = g[8]
+    assert alpha > 0
+    for j in (0, 1, 2, 3, 4, 5, 6, 7, 10, 11, 12):
+        assert abs(g[j] - o[j]) <= 1e-7 * max(1.0, abs(o[j])), (j, g[j], o[j])
+    dx = (sol["x"][0] - inst["x_init"]) / alpha
+    du = (sol["u"][0] - inst["u_init"]) / alpha
+    assert rel(dx, ref["dx"]) < 1e-7, rel(dx, ref["dx"])
+    assert rel(du, ref["du"]) < 1e-7, rel(du, ref["du"])
+    assert rel(sol["x"][0], ref["x"]) < 1e-7
+    assert rel(sol["u"][0], ref["u"]) < 1e-7
+    assert rel(sol["K"][0], ref["K"]) < 1e-6, rel(sol["K"][0], ref["K"])
+
+
 def test_upload_validation(model):
     from wb_humanoid_mpc_b200.lib import B200SqpError
     from wb_humanoid_mpc_b200.solver import B200SqpSolver, stack_instances
@@ -188,6 +231,34 @@ def test_value_function_matches_oracle(model):
     wb.sqp(inst["t_nodes"], inst["node_event"], inst["x0"], inst["x_init"], inst["u_init"], st)
     Po, po = wb.last_value_function(inst["x_init"])
     assert rel(P[0], Po) < 1e-7 and rel(p[0], po) < 1e-6
+
+
+def test_value_function_of_instances_converging_at_different_iterations(model):
+    """sqpIteration > 1 with createValueFunction: an instance that converges before the last iteration keeps the re-centred cost-to-go of
+    the iteration it converged in (SqpSolver.cpp:321-329 runs inside that instance's own last iteration); the QP and the re-centring of the
+    later iterations of the batch must not touch it."""
+    from wb_humanoid_mpc_b200.solver import B200SqpSolver
+
+    rng = np.random.default_rng(16)
+    insts = make_instances(model, rng, [("stance", 0.5, None), ("walk", 0.5, [0.4, 0.0, 0.7925, 0.1])])
+    # an instance that starts on its reference converges after one tiny step (PRIMAL); the perturbed ones need more iterations
+    x_nom = np.array(model["x_init"], float)
+    x_nom[2] = model["reference"]["defaultBaseHeight"]
+    insts.insert(1, references.build_instance(model, x_nom, t0=0.0, horizon=0.5, gait="stance", cmd=None))
+    st = abi.default_settings(model, sqp_iteration=6, create_value_function=1)
+    solver = B200SqpSolver(model, st)
+    sol = solver.run(insts)
+    P, p = solver.value_function()
+    assert len(set(int(v) for v in sol["n_iter"])) > 1, sol["n_iter"]   # the case this test is about
+    for b, inst in enumerate(insts):
+        wb = orc.WbOracle(model)
+        wb.set_nodes(inst["contact_flags"], inst["swing_ref"], inst["impact_factor"], inst["arm_phase"], inst["x_ref"])
+        ref = wb.sqp(inst["t_nodes"], inst["node_event"], inst["x0"], inst["x_init"], inst["u_init"], st)
+        assert sol["n_iter"][b] == len(ref["log"])
+        x_lin = ref["x"] - ref["log"][-1][8] * ref["dx"]   # linearisation trajectory of the instance's last iteration
+        Po, po = wb.last_value_function(x_lin)
+        assert rel(P[b], Po) < 1e-6, (b, rel(P[b], Po))
+        assert rel(p[b], po) < 1e-5, (b, rel(p[b], po))
 
 
 @pytest.mark.parametrize("gait", ["run", "jump", "trot", "left_leg"])

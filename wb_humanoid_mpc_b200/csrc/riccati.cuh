@@ -43,6 +43,10 @@ struct QpDeviceView {
   int* status;  // [B]
   int keepP;
   double reg;
+  // optional per-instance skip flags (the SQP solver's F_CONVERGED word, stride skipStride ints): a converged instance keeps the QP outputs
+  // of the iteration it converged in -- in particular its re-centred cost-to-go (SqpSolver::extractValueFunction)
+  const int* skip;
+  int skipStride;
 };
 
 __host__ __device__ inline int even_up(int n) { return (n + 1) & ~1; }
@@ -116,6 +120,7 @@ template <int NXT, int NMT>
 __global__ void __launch_bounds__(256, 1) riccati_kernel(QpDeviceView v) {
   extern __shared__ double sm[];
   const int inst = blockIdx.x;
+  if (v.skip && v.skip[inst * v.skipStride]) return;
   const int nx = NXT ? NXT : v.nx, nm = NMT ? NMT : v.numax, N = v.N, nx1 = nx + 1;
   const RicLayout L = riccati_layout_padded(nx, nm);
   const int lx = ric_pad(nx), lm = ric_pad(nm);   // leading dimensions of the nx-row / nm-row operands in the backward sweep

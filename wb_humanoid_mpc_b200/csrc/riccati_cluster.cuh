@@ -46,6 +46,7 @@ __global__ void __cluster_dims__(RC, 1, 1) __launch_bounds__(256, 1) riccati_clu
   cg::cluster_group cluster = cg::this_cluster();
   const int rank = static_cast<int>(cluster.block_rank());
   const int inst = blockIdx.x / RC;
+  if (v.skip && v.skip[inst * v.skipStride]) return;   // uniform over the cluster (same instance), before any cluster barrier
   const int nx = NXT ? NXT : v.nx, nm = NMT ? NMT : v.numax, N = v.N, nx1 = nx + 1;
   const RicLayout L = riccati_layout(nx, nm);
   double* PQ[2] = {sm, sm + L.pq};

@@ -467,7 +467,8 @@ class TrajectorySpreading {
       newM.insert(newM.begin(), t0 - 1e-4);
     }
     const bool oldLastMatched = (oldStart + w - 1 == oldLast), newLastMatched = (newStart + w - 1 == newLast);
-    if (!oldLastMatched && (newLastMatched || oldMs.eventTimes[oldStart + w - 1] < newMs.eventTimes[newStart + w - 1])) {
+    // (w == 0 erases the whole trajectory; the reference indexes eventTimes out of range there, so that case is skipped)
+    if (w > 0 && !oldLastMatched && (newLastMatched || oldMs.eventTimes[oldStart + w - 1] < newMs.eventTimes[newStart + w - 1])) {
       oldM.push_back(oldMs.eventTimes[oldStart + w - 1]);
       newM.push_back(newLastMatched ? tf + 1e-4 : newMs.eventTimes[newStart + w - 1]);
     }

@@ -393,7 +393,7 @@ class TrajectorySpreading:
             new_m.insert(0, t0 - 1e-4)
         old_last_matched = (old_start + w - 1 == old_last)
         new_last_matched = (new_start + w - 1 == new_last)
-        if (not old_last_matched) and (new_last_matched or old.event_times[old_start + w - 1] < new.event_times[new_start + w - 1]):
+        if w > 0 and (not old_last_matched) and (new_last_matched or old.event_times[old_start + w - 1] < new.event_times[new_start + w - 1]):
             old_m.append(old.event_times[old_start + w - 1])
             new_m.append(tf + 1e-4 if new_last_matched else new.event_times[new_start + w - 1])
         self.erase_from = len(old_time)
