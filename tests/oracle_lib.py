@@ -3,6 +3,7 @@ from __future__ import annotations
 
 import ctypes as C
 import subprocess
+import sys
 from pathlib import Path
 
 import numpy as np
@@ -32,8 +33,59 @@ def build_oracle(force=False):
     so = ORACLE_DIR / "liboracle.so"
     srcs = list(ORACLE_DIR.glob("*.hpp")) + list(ORACLE_DIR.glob("*.cpp")) + list(ORACLE_DIR.glob("*.inc"))
     if force or not so.exists() or any(s.stat().st_mtime > so.stat().st_mtime for s in srcs):
-        subprocess.run(["make", "-C", str(ORACLE_DIR), "-s"], check=True)
+        subprocess.run(["make", "-C", str(ORACLE_DIR), "-s", "liboracle.so"], check=True, stdout=sys.stderr)
     return so
+
+
+_fast = None
+
+
+def build_fast(force=False):
+    """oracle/fast/liboracle_fast.so: the fast CPU baseline (timed arm of bench.py); see oracle/fast/wb_fast.cu"""
+    so = ORACLE_DIR / "fast" / "liboracle_fast.so"
+    csrc = ROOT / "wb_humanoid_mpc_b200" / "csrc"
+    srcs = [ORACLE_DIR / "fast" / "wb_fast.cu"] + list(csrc.glob("*.cuh")) + list(csrc.glob("*.inc"))
+    stale = not so.exists() or any(s.stat().st_mtime > so.stat().st_mtime for s in srcs)
+    import shutil
+    if (force or stale) and (shutil.which("nvcc") or (Path("/usr/local/cuda/bin/nvcc").exists())):
+        subprocess.run(["make", "-C", str(ORACLE_DIR), "-s", "fast"] + (["-B"] if force else []), check=True, stdout=sys.stderr)
+    return so
+
+
+def fast_lib():
+    global _fast
+    if _fast is None:
+        _fast = C.CDLL(str(build_fast()))
+        _fast.orc_fast_wb_sqp_batch.restype = C.c_int
+    return _fast
+
+
+def fast_wb_sqp_batch(model, batch, settings, threads=1, node_threads=1, want_gains=False):
+    """the fast CPU baseline on a stacked batch (solver.stack_instances layout) -> dict(x, u, log, n_iter, K, stage_s, seconds)"""
+    import time
+
+    from wb_humanoid_mpc_b200 import abi
+
+    desc = abi.model_desc(model)
+    u8 = lambda a: np.ascontiguousarray(a, dtype=np.uint8)
+    B, n = batch["t_nodes"].shape
+    nx, nu = model["nx"], model["nu"]
+    x, u = F(batch["x_init"]).copy(), F(batch["u_init"]).copy()
+    arrs = [F(batch["t_nodes"]), u8(batch["node_event"]), F(batch["x0"]), u8(batch["contact_flags"]), F(batch["swing_ref"]), F(batch["impact_factor"]),
+            F(batch["arm_phase"]), F(batch["x_ref"])]
+    log = np.zeros((B, settings.sqp_iteration, 16))
+    n_iter = np.zeros(B, dtype=np.int32)
+    K = np.zeros((B, n - 1, nx, nu)) if want_gains else None
+    stage = np.zeros(3)
+    u8p = C.POINTER(C.c_uint8)
+    t0 = time.perf_counter()
+    rc = fast_lib().orc_fast_wb_sqp_batch(C.byref(desc), C.c_int(B), C.c_int(threads), C.c_int(node_threads), C.c_int(n), _p(arrs[0]),
+                                          arrs[1].ctypes.data_as(u8p), _p(arrs[2]), _p(x), _p(u), arrs[3].ctypes.data_as(u8p), _p(arrs[4]), _p(arrs[5]),
+                                          _p(arrs[6]), _p(arrs[7]), C.byref(settings), _p(log), n_iter.ctypes.data_as(C.POINTER(C.c_int32)), _p(K), _p(stage))
+    dt = time.perf_counter() - t0
+    if rc != 0:
+        raise RuntimeError(f"fast CPU baseline failed ({rc})")
+    return dict(x=x, u=u, log=log, n_iter=n_iter, K=None if K is None else np.swapaxes(K, -1, -2).copy(), stage_s=stage, seconds=dt)
 
 
 def lib():

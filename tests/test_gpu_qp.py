@@ -8,6 +8,15 @@ from test_oracle_qp import _known_solution_problem, rand_cost, rand_dyn, stack
 pytestmark = pytest.mark.gpu
 
 
+@pytest.fixture(params=["cluster", "two_kernel", "generic"])
+def k2_mode(request, monkeypatch):
+    """the three K2 variants for the whole-body sizes (b200sqp.cu launch_riccati): 4-CTA cluster kernel (small batches), riccati_wb.cuh's backward
+    + forward kernels (the large-batch default), the generic one-CTA kernel"""
+    monkeypatch.setenv("B200SQP_NO_CLUSTER", "0" if request.param == "cluster" else "1")
+    monkeypatch.setenv("B200SQP_K2_LEGACY", "1" if request.param == "generic" else "0")
+    return request.param
+
+
 def _random_batch(rng, Bn, N, nx, numax, nu_pattern=None):
     A = rng.uniform(-1, 1, (Bn, N, nx, nx)) * (0.6 / np.sqrt(nx))
     A += np.eye(nx)
@@ -68,7 +77,47 @@ def test_riccati_vs_oracle(nx, numax, N, Bn):
     _compare(sol, Bn, data, nu, dx0)
 
 
-def test_riccati_varying_nu_and_event_stages():
+def test_riccati_whole_body_sizes_all_variants(k2_mode):
+    from wb_humanoid_mpc_b200.qp import BatchedQp
+
+    rng = np.random.default_rng(58023)
+    nx, numax, N, Bn = 58, 23, 100, 4
+    data, nu, dx0 = _random_batch(rng, Bn, N, nx, numax)
+    qp = BatchedQp(Bn, N, nx, numax)
+    qp.upload(*data, dx0, nu)
+    qp.solve()
+    sol = qp.download()
+    assert not sol["status"].any()
+    _compare(sol, Bn, data, nu, dx0)
+
+
+def test_riccati_large_batch_default_dispatch():
+    """a batch beyond the cluster threshold takes the two-kernel path by default; two waves of CTAs (batch > number of SMs); every instance
+    against the oracle would take minutes, so instances 0, 17, 149, 299 are compared and all are checked for dynamic feasibility"""
+    from wb_humanoid_mpc_b200.qp import BatchedQp
+
+    rng = np.random.default_rng(300)
+    nx, numax, N, Bn = 58, 23, 12, 300
+    pattern = rng.choice([21, 22, 23, 23, 0], size=(Bn, N)).astype(np.int32)
+    data, nu, dx0 = _random_batch(rng, Bn, N, nx, numax, pattern)
+    qp = BatchedQp(Bn, N, nx, numax)
+    qp.upload(*data, dx0, nu)
+    qp.solve()
+    sol = qp.download()
+    assert not sol["status"].any()
+    A, Bm, b, Q, S, R, q, r = data
+    for i in (0, 17, 149, 299):
+        ref = orc.riccati(A[i], Bm[i], b[i], Q[i], S[i], R[i], q[i], r[i], dx0[i], nu[i])
+        for key in ("dx", "du", "K", "k", "P", "p"):
+            assert _rel(sol[key][i], ref[key]) < 1e-9, (i, key)
+    for i in range(Bn):
+        for k in range(N):
+            m = nu[i, k]
+            xn = A[i, k] @ sol["dx"][i, k] + Bm[i, k][:, :m] @ sol["du"][i, k, :m] + b[i, k]
+            assert np.max(np.abs(xn - sol["dx"][i, k + 1])) < 1e-10, (i, k)
+
+
+def test_riccati_varying_nu_and_event_stages(k2_mode):
     """per-stage projected input dimension 21/22/23 and nu=0 event stages (G1 whole-body shapes)"""
     from wb_humanoid_mpc_b200.qp import BatchedQp
 
@@ -117,7 +166,7 @@ def test_riccati_failure_is_reported():
     assert ei.value.code == -4
 
 
-def test_kkt_residual_full_size():
+def test_kkt_residual_full_size(k2_mode):
     """north_star parity list: the KKT residual of the GPU QP solution, assembled stage-wise as in OcpToKkt (no oracle involved):
     with costates lambda_k = P_k dx_k + p_k,
         stationarity in dx_k : Q dx + S' du + q + A' lambda_{k+1} - lambda_k = 0,   in du_k : S dx + R du + r + B' lambda_{k+1} = 0,
@@ -167,8 +216,10 @@ def test_cluster_variant_is_bitwise_identical_and_deterministic():
     qp = BatchedQp(Bn, N, nx, numax)
     qp.upload(*data, dx0, nu)
     old = os.environ.get("B200SQP_NO_CLUSTER")
+    old_legacy = os.environ.get("B200SQP_K2_LEGACY")
     try:
         os.environ["B200SQP_NO_CLUSTER"] = "1"
+        os.environ["B200SQP_K2_LEGACY"] = "1"   # the generic one-CTA kernel is the bit-exact reference of the cluster variant
         qp.solve()
         ref = qp.download()
         os.environ["B200SQP_NO_CLUSTER"] = "0"
@@ -178,6 +229,10 @@ def test_cluster_variant_is_bitwise_identical_and_deterministic():
             for key in ("dx", "du", "K", "k", "P", "p"):
                 assert np.array_equal(sol[key], ref[key]), (rep, key, np.abs(sol[key] - ref[key]).max())
     finally:
+        if old_legacy is None:
+            os.environ.pop("B200SQP_K2_LEGACY", None)
+        else:
+            os.environ["B200SQP_K2_LEGACY"] = old_legacy
         if old is None:
             os.environ.pop("B200SQP_NO_CLUSTER", None)
         else:

@@ -137,16 +137,15 @@ def test_benchmark_size_matches_oracle(model, gait, cmd):
     sqpIteration 1 -- GPU (C ABI) against the oracle on the same instance: LQ blocks of every stage, the QP step (dx, remapped du), the
     remapped gains K, all ten PerformanceIndex log fields, accepted step size / step type / convergence code and the primal trajectory.
 
-    Tolerances: blocks 1e-9 relative (as at the short horizons).  The QP outputs go through 114 sequential Riccati stages; the backward
-    recursion is contractive in exact arithmetic but each stage re-amplifies the 1e-15 block differences by cond(R~) (~1e6 with the
-    friction-cone barrier Hessians next to 1e-3 input weights), so the relative difference of dx/du/K grows from ~1e-9 at N = 30 to ~1e-8 at
-    N = 114; the test allows 1e-7 for the trajectory and the step and 1e-6 for the gains, like the short-horizon tests."""
+    Tolerances: blocks 1e-9 relative as at the short horizons (measured 1e-14 .. 1e-16); QP step, trajectory, gains and log fields 1e-9
+    relative -- measured on B200: dx 4e-13, du 7e-13, K 5e-13, log fields <= 1e-13 (tools/dev/parity_n100.py): the 114 sequential Riccati
+    stages do NOT amplify the block differences beyond the short-horizon level (N = 32: dx 4e-13)."""
     from wb_humanoid_mpc_b200.solver import B200SqpSolver
 
     rng = np.random.default_rng(31)
     inst = make_instances(model, rng, [(gait, 3.5, cmd)])[0]
     n = len(inst["t_nodes"])
-    assert n == (115 if gait == "walk" else 101)
+    assert n == (115 if gait == "walk" else 112)   # 100 intervals of dt 0.035 + the gait's event nodes
     st = abi.default_settings(model, sqp_iteration=1, use_feedback_policy=1)
     solver = B200SqpSolver(model, st, capture_raw_blocks=True)
     sol = solver.run([inst])
@@ -164,14 +163,14 @@ def test_benchmark_size_matches_oracle(model, gait, cmd):
     alpha = g[8]
     assert alpha > 0
     for j in (0, 1, 2, 3, 4, 5, 6, 7, 10, 11, 12):
-        assert abs(g[j] - o[j]) <= 1e-7 * max(1.0, abs(o[j])), (j, g[j], o[j])
+        assert abs(g[j] - o[j]) <= 1e-9 * max(1.0, abs(o[j])), (j, g[j], o[j])
     dx = (sol["x"][0] - inst["x_init"]) / alpha
     du = (sol["u"][0] - inst["u_init"]) / alpha
-    assert rel(dx, ref["dx"]) < 1e-7, rel(dx, ref["dx"])
-    assert rel(du, ref["du"]) < 1e-7, rel(du, ref["du"])
-    assert rel(sol["x"][0], ref["x"]) < 1e-7
-    assert rel(sol["u"][0], ref["u"]) < 1e-7
-    assert rel(sol["K"][0], ref["K"]) < 1e-6, rel(sol["K"][0], ref["K"])
+    assert rel(dx, ref["dx"]) < 1e-9, rel(dx, ref["dx"])
+    assert rel(du, ref["du"]) < 1e-9, rel(du, ref["du"])
+    assert rel(sol["x"][0], ref["x"]) < 1e-9
+    assert rel(sol["u"][0], ref["u"]) < 1e-9
+    assert rel(sol["K"][0], ref["K"]) < 1e-9, rel(sol["K"][0], ref["K"])
 
 
 def test_upload_validation(model):
@@ -240,12 +239,12 @@ def test_value_function_of_instances_converging_at_different_iterations(model):
     from wb_humanoid_mpc_b200.solver import B200SqpSolver
 
     rng = np.random.default_rng(16)
-    insts = make_instances(model, rng, [("stance", 0.5, None), ("walk", 0.5, [0.4, 0.0, 0.7925, 0.1])])
-    # an instance that starts on its reference converges after one tiny step (PRIMAL); the perturbed ones need more iterations
+    insts = make_instances(model, rng, [("walk", 0.3, [0.4, 0.0, 0.7925, 0.1])])
+    # an instance that starts on its reference converges after 7 iterations (METRICS), the perturbed walking one uses all 10
     x_nom = np.array(model["x_init"], float)
     x_nom[2] = model["reference"]["defaultBaseHeight"]
-    insts.insert(1, references.build_instance(model, x_nom, t0=0.0, horizon=0.5, gait="stance", cmd=None))
-    st = abi.default_settings(model, sqp_iteration=6, create_value_function=1)
+    insts.insert(0, references.build_instance(model, x_nom, t0=0.0, horizon=0.3, gait="stance", cmd=None))
+    st = abi.default_settings(model, sqp_iteration=10, create_value_function=1)
     solver = B200SqpSolver(model, st)
     sol = solver.run(insts)
     P, p = solver.value_function()

@@ -75,12 +75,16 @@ for kid, name in [(0, "K1a lq_dyn_kernel"), (1, "K1b lq_proj_kernel"), (2, "K3 r
 buf = (C.c_longlong * 64)()
 n = L.b200sqp_debug_phase_clocks(3, buf, 32, -1)
 a = np.array(buf[:64], dtype=np.int64).reshape(32, 2)
-src = (ROOT / "wb_humanoid_mpc_b200" / "csrc" / "riccati.cuh").read_text().split("\n")
-tot = a[:, 1].sum()
-print(f"\n== K2 riccati_kernel (instance 0, cycles summed over all stages): {tot} cycles")
-for slot in range(32):
-    if a[slot, 1] > 0:
-        line = int(a[slot, 0])
-        # show the statement that precedes the barrier
-        ctx = " | ".join(t.strip()[:70] for t in src[max(0, line - 4):line - 1])
-        print(f"  slot {slot:2d} {a[slot, 1]:9d} {100.0 * a[slot, 1] / tot:5.1f}%  L{line:<4d} {ctx}")
+legacy = os.environ.get("B200SQP_K2_LEGACY") == "1"
+src = (ROOT / "wb_humanoid_mpc_b200" / "csrc" / ("riccati.cuh" if legacy else "riccati_wb.cuh")).read_text().split("\n")
+# riccati_wb.cuh: slots < 20 are thread 0 (GEMM warp 0), slots >= 20 thread 256 (the helper warp): two separate time lines
+for name, sel in [("GEMM warp 0" if not legacy else "thread 0", lambda sl: sl < 20), ("helper warp", lambda sl: sl >= 20)]:
+    tot = sum(a[sl, 1] for sl in range(32) if sel(sl))
+    if tot == 0:
+        continue
+    print(f"\n== K2 {'riccati_kernel' if legacy else 'riccati_bwd_kernel'} {name} (instance 0, cycles summed over all stages): {tot} cycles")
+    for slot in range(32):
+        if sel(slot) and a[slot, 1] > 0:
+            line = int(a[slot, 0])
+            ctx = " | ".join(t.strip()[:70] for t in src[max(0, line - 4):line - 1])
+            print(f"  slot {slot:2d} {a[slot, 1]:9d} {100.0 * a[slot, 1] / tot:5.1f}%  L{line:<4d} {ctx}")

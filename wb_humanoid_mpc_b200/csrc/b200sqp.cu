@@ -14,6 +14,7 @@
 
 #include "riccati.cuh"
 #include "riccati_cluster.cuh"
+#include "riccati_wb.cuh"
 #ifdef B200SQP_WITH_WB
 #include "wb_solver.cuh"
 #include "cen_dynamics.cuh"
@@ -55,15 +56,21 @@ cudaError_t set_riccati_smem_attributes(int nx, int numax) {
   cudaError_t e = cudaFuncSetAttribute(b200sqp::riccati_kernel<0, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, one);
   if (e == cudaSuccess) e = cudaFuncSetAttribute(b200sqp::riccati_cluster_kernel<0, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, clu);
   if (nx == 58 && numax == 23) {
+    if (e == cudaSuccess)
+      e = cudaFuncSetAttribute(b200sqp::ricwb::riccati_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(b200sqp::ricwb::BWD_SMEM_BYTES));
+    if (e == cudaSuccess)
+      e = cudaFuncSetAttribute(b200sqp::ricwb::riccati_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(b200sqp::ricwb::FWD_SMEM_BYTES));
     if (e == cudaSuccess) e = cudaFuncSetAttribute(b200sqp::riccati_kernel<58, 23>, cudaFuncAttributeMaxDynamicSharedMemorySize, one);
     if (e == cudaSuccess) e = cudaFuncSetAttribute(b200sqp::riccati_cluster_kernel<58, 23>, cudaFuncAttributeMaxDynamicSharedMemorySize, clu);
   }
   return e;
 }
 
-// K2 dispatch: the cluster variant (RC SMs per instance) for small batches, else one CTA per instance.
-// B200SQP_NO_CLUSTER=1 forces the one-CTA kernel (tests exercise both).
-void launch_riccati(const b200sqp::QpDeviceView& v, cudaStream_t st) {
+// K2 dispatch: the cluster variant (RC SMs per instance) for small batches; for the whole-body sizes the two-kernel form of riccati_wb.cuh
+// (backward factorisation with a helper warp + separate forward substitution); the generic one-CTA kernel for every other size.
+// B200SQP_NO_CLUSTER=1 skips the cluster variant, B200SQP_K2_LEGACY=1 forces the generic kernel (tests exercise all three).
+// Returns the number of kernels launched.
+int launch_riccati(const b200sqp::QpDeviceView& v, cudaStream_t st) {
   static int sms = 0;
   if (sms == 0) {
     int dev = 0;
@@ -79,10 +86,17 @@ void launch_riccati(const b200sqp::QpDeviceView& v, cudaStream_t st) {
     if (wb) b200sqp::riccati_cluster_kernel<58, 23><<<v.B * b200sqp::RC, 256, smem, st>>>(v);
     else b200sqp::riccati_cluster_kernel<0, 0><<<v.B * b200sqp::RC, 256, smem, st>>>(v);
   } else {
+    const char* legacy = std::getenv("B200SQP_K2_LEGACY");
+    if (wb && !(legacy && legacy[0] == '1')) {
+      b200sqp::ricwb::riccati_bwd_kernel<<<v.B, b200sqp::ricwb::BWD_THREADS, b200sqp::ricwb::BWD_SMEM_BYTES, st>>>(v);
+      b200sqp::ricwb::riccati_fwd_kernel<<<v.B, b200sqp::ricwb::FWD_THREADS, b200sqp::ricwb::FWD_SMEM_BYTES, st>>>(v);
+      return 2;
+    }
     const size_t smem = b200sqp::riccati_smem_doubles(v.nx, v.numax) * sizeof(double);
     if (wb) b200sqp::riccati_kernel<58, 23><<<v.B, 256, smem, st>>>(v);
     else b200sqp::riccati_kernel<0, 0><<<v.B, 256, smem, st>>>(v);
   }
+  return 1;
 }
 }  // namespace
 
