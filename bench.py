@@ -29,8 +29,9 @@ METRIC = "SQP solves/sec (G1 whole-body, N=100, batched)"
 SEED = 1234
 
 
-def build_batch(model, batch, rank, horizon, gaits):
-    """Instance distribution of SURVEY.md §8d (seed 1234): perturbed initial states, velocity commands, cold start."""
+def build_batch(model, batch, rank, horizon, gaits, random_phase=False):
+    """Instance distribution of SURVEY.md §8d (seed 1234): perturbed initial states, velocity commands, cold start.
+    random_phase: gait phase offset ~ U[0, period) per instance (BASELINE configs[4], the mixed contact-schedule sweep)."""
     rng = np.random.default_rng(SEED + 7919 * rank)
     nj = model["nj"]
     lo, hi = np.array(model["q_lower"]), np.array(model["q_upper"])
@@ -43,8 +44,13 @@ def build_batch(model, batch, rank, horizon, gaits):
         x0[6:6 + nj] = np.clip(x0[6:6 + nj] + rng.uniform(-0.1, 0.1, nj), lo + 0.05, hi - 0.05)
         x0[6 + nj:] += rng.uniform(-0.2, 0.2, 6 + nj)
         cmd = [rng.uniform(-0.5, 1.0), rng.uniform(-0.3, 0.3), model["reference"]["defaultBaseHeight"], rng.uniform(-0.5, 0.5)]
-        insts.append(references.build_instance(model, x0, t0=0.0, horizon=horizon, gait=gaits[i % len(gaits)], cmd=cmd))
-        insts[-1]["cmd"], insts[-1]["gait"] = cmd, gaits[i % len(gaits)]
+        g = gaits[i % len(gaits)]
+        start = None
+        if random_phase:
+            period = model["gaits"][g]["switchingTimes"][-1] if g != "stance" else 1.0
+            start = -rng.uniform(0.0, period)
+        insts.append(references.build_instance(model, x0, t0=0.0, horizon=horizon, gait=g, gait_start=start, cmd=cmd))
+        insts[-1]["cmd"], insts[-1]["gait"] = cmd, g
     return insts
 
 
@@ -119,6 +125,27 @@ def oracle_batch_solve(model, insts, settings, threads):
     return dt, x, u
 
 
+def effective_cores():
+    """host threads this process can actually keep busy: the CPU affinity mask, capped by the container's cgroup CPU quota (a box may expose
+    128 hardware threads and grant 12 CPUs worth of time; oversubscribing the quota only adds context switches)"""
+    n = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    quota = None
+    try:
+        q, per = Path("/sys/fs/cgroup/cpu.max").read_text().split()[:2]
+        if q != "max":
+            quota = float(q) / float(per)
+    except Exception:
+        try:
+            q = float(Path("/sys/fs/cgroup/cpu/cpu.cfs_quota_us").read_text())
+            per = float(Path("/sys/fs/cgroup/cpu/cpu.cfs_period_us").read_text())
+            if q > 0:
+                quota = q / per
+        except Exception:
+            pass
+    eff = n if quota is None else max(1, min(n, int(np.ceil(quota))))
+    return eff, n, quota
+
+
 def cpu_port_solve(model, insts, settings, threads, node_threads=1):
     """The TIMED CPU arm: the fast restatement of the reference's CPU path (oracle/fast/wb_fast.cu: analytic Jacobians per node, dense
     sequential Riccati, value-only roll-outs), pinned on the checker oracle by tests/test_oracle_fast.py.  -> oracle_lib.fast_wb_sqp_batch dict"""
@@ -151,6 +178,7 @@ def cpu_baseline_rows(model, insts, settings, cores, reps, warm=3):
     ta = np.array(ta)
     st = out["stage_s"] / len(sample)
     row = {"value": float(np.median(thr)), "unit": "solves/s", "cores": cores, "kind": "port",
+           "host": {"affinity_cpus": effective_cores()[1], "cgroup_cpu_quota": effective_cores()[2]},
            "what": "fast CPU restatement of the reference path (oracle/fast/wb_fast.cu: analytic per-node Jacobians on host threads, dense sequential Riccati, "
                    "value-only roll-outs), NOT the ocs2+HPIPM binary (not buildable here, DESIGN.md section 2); pinned on the checker oracle by tests/test_oracle_fast.py",
            "sample": f"CPU-B: {len(sample)} instances of the workload per repetition, one instance per thread on {cores} threads, {warm} warm-up + {reps} "
@@ -162,13 +190,111 @@ def cpu_baseline_rows(model, insts, settings, cores, reps, warm=3):
     return row, out, sample
 
 
+def run_mixed(args, model, settings, rank, world, local_rank, workload, cores):
+    """BASELINE configs[4]: the mixed contact-schedule sweep.  Instances with different event counts have different numbers of shooting nodes;
+    they are grouped by node count, one library handle per group, the groups solved concurrently (one host thread and CUDA stream per group).
+    `value`: device-resident (reset + solve of every group per step); `e2e`: upload from pinned host memory + solve + download of every group per
+    step.  Timed by wall clock between device synchronisations (CUDA events on one stream cannot bracket multi-stream work), max over ranks."""
+    from concurrent.futures import ThreadPoolExecutor
+
+    import torch
+
+    from wb_humanoid_mpc_b200.solver import B200SqpSolver, stack_instances
+
+    torch.cuda.set_device(local_rank)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    insts = build_batch(model, args.batch, rank, args.horizon, ["stance", "walk", "slow_walk"], random_phase=True)
+    by_n = {}
+    for i in insts:
+        by_n.setdefault(len(i["t_nodes"]), []).append(i)
+    groups = []
+    for n, gi in sorted(by_n.items()):
+        b = stack_instances(gi)
+        pinned = {k: torch.from_numpy(np.ascontiguousarray(v if v.dtype == np.uint8 else v.astype(np.float64))).pin_memory().numpy() for k, v in b.items()}
+        sv = B200SqpSolver(model, settings, device=local_rank)
+        sv.upload(pinned)
+        groups.append({"n": n, "B": len(gi), "solver": sv, "pinned": pinned, "stream": torch.cuda.Stream()})
+    pool = ThreadPoolExecutor(max_workers=len(groups))
+
+    def each(fn):
+        def work(g):
+            torch.cuda.set_device(local_rank)
+            fn(g)
+        list(pool.map(work, groups))
+
+    def resident(g):
+        g["solver"].reset()
+        g["solver"].solve(g["stream"].cuda_stream)
+
+    def e2e_step(g):
+        g["solver"].upload(g["pinned"])
+        g["solver"].solve(g["stream"].cuda_stream)
+        g["out"] = g["solver"].primal_solution()
+
+    def barrier():
+        torch.cuda.synchronize()
+        if dist is not None:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    def timed(fn, steps):
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(steps):
+            each(fn)
+        torch.cuda.synchronize()
+        dt = time.perf_counter() - t0
+        if dist is not None:
+            t = torch.tensor([dt], dtype=torch.float64, device="cuda")
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            dt = float(t.item())
+        barrier()
+        return dt
+
+    for _ in range(args.warmup):
+        each(resident)
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    dev_s = timed(resident, args.steps)
+    clocks = sampler.stop() if rank == 0 else None
+    launches = sum(g["solver"].launch_count() for g in groups) * args.steps
+    stage = {str(g["n"]): dict(zip(["lq", "qp", "linesearch", "lq_projection_share"], [float(v) for v in g["solver"].benchmarks()])) for g in groups}
+    each(e2e_step)
+    e2e_s = timed(e2e_step, args.steps)
+    assert all(not g["out"]["status"].any() for g in groups)
+    total = args.batch * world * args.steps
+    h2d = sum(sum(v.nbytes for v in g["pinned"].values()) for g in groups)
+    d2h = sum(g["B"] * g["n"] * 58 * 8 + g["B"] * (g["n"] - 1) * 35 * 8 + g["B"] * settings.sqp_iteration * 128 + g["B"] * 8 for g in groups)
+    line = {"metric": METRIC, "value": total / dev_s, "unit": "solves/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": 1e3 * dev_s / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": workload, "node_count_groups": {str(g["n"]): g["B"] for g in groups}, "batch_per_gpu": args.batch,
+                       "timing": "wall clock between device synchronisations (several CUDA streams), max over ranks",
+                       "l2": "stage records (GBs per GPU) exceed the 126 MB L2; no flush needed"},
+            "e2e": {"value": total / e2e_s, "unit": "solves/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
+                    "mode": "every group: upload from pinned host memory -> solve -> download, groups concurrent on their own streams"},
+            "gpu_launches": int(launches), "stage_ms_by_node_count": stage, "clocks": clocks,
+            "roofline": None}
+    if rank == 0:
+        print(json.dumps(line))
+    if dist is not None:
+        dist.destroy_process_group()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--batch", type=int, default=256, help="MPC instances per GPU")
+    ap.add_argument("--config", default="c3", choices=["c3", "c4", "c5"],
+                    help="BASELINE.json configs[2..4]: c3 = walk, 256 instances per GPU (the metric's configuration, default); c4 = walk, 1024 per GPU "
+                         "(8192 over 8 GPUs); c5 = mixed contact-schedule sweep stance/walk/slow_walk with random gait phase, 1024 per GPU (4096 over 4)")
+    ap.add_argument("--batch", type=int, default=0, help="MPC instances per GPU (default: what --config says)")
     ap.add_argument("--horizon", type=float, default=3.5, help="seconds; 3.5 s at dt = 0.035 s gives N = 100 intervals (+ event nodes)")
     ap.add_argument("--gait", default="walk")
     ap.add_argument("--cpu-sample", type=int, default=0, help="instances in the CPU-baseline sample (0 = 2 x cores)")
@@ -178,15 +304,23 @@ def main():
     ap.add_argument("--sqp-iteration", type=int, default=1, help="sqpIteration (1 = the shipped real-time iteration; 10 = the secondary number)")
     ap.add_argument("--global-step", action="store_true", help="one line-search step per iteration for the whole multi-GPU batch (NCCL)")
     args = ap.parse_args()
+    if args.batch <= 0:
+        args.batch = 256 if args.config == "c3" else 1024
 
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     model = model_loader.load_packaged_model()
     settings = abi.default_settings(model, sqp_iteration=args.sqp_iteration, global_step=int(args.global_step))
-    cores = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    cores, affinity_cpus, cpu_quota = effective_cores()
     n_int = int(round(args.horizon / model["sqp"]["dt"]))
     workload = f"G1 whole-body MPC (nx=58, nu=35), dt=0.035 s x {n_int} intervals, gait={args.gait}, batch={args.batch}/GPU, sqpIteration={args.sqp_iteration}, cold start" + (", global line-search step" if args.global_step else "")
+
+    if args.config == "c5":
+        workload = (f"G1 whole-body MPC (nx=58, nu=35), dt=0.035 s x {n_int} intervals, mixed contact-schedule sweep (stance / walk / slow_walk, random gait "
+                    f"phase), batch={args.batch}/GPU, sqpIteration={args.sqp_iteration}, cold start")
+        if args.impl != "reference":
+            return run_mixed(args, model, settings, rank, world, local_rank, workload, cores)
 
     if args.impl == "reference":
         # the reference's own CPU implementation of the path cannot be built here (no Eigen/Pinocchio/HPIPM): the arm
@@ -194,14 +328,25 @@ def main():
         if rank != 0:
             return
         sample = args.cpu_sample or 2 * cores
-        insts = build_batch(model, sample, 0, args.horizon, [args.gait])
+        if args.config == "c5":   # the mixed sweep: instances grouped by node count, the groups one after the other (each on all cores)
+            insts = build_batch(model, sample, 0, args.horizon, ["stance", "walk", "slow_walk"], random_phase=True)
+            by_n = {}
+            for i in insts:
+                by_n.setdefault(len(i["t_nodes"]), []).append(i)
+            groups = list(by_n.values())
+        else:
+            insts = build_batch(model, sample, 0, args.horizon, [args.gait])
+            groups = [insts]
         for _ in range(args.warmup):
-            cpu_port_solve(model, insts[: max(1, cores // 2)], settings, cores)
+            cpu_port_solve(model, groups[0][: max(1, cores // 2)], settings, cores)
         times, stage = [], np.zeros(3)
         for _ in range(args.steps):
-            o = cpu_port_solve(model, insts, settings, cores)
-            times.append(o["seconds"])
-            stage += o["stage_s"]
+            tstep = 0.0
+            for g in groups:
+                o = cpu_port_solve(model, g, settings, cores)
+                tstep += o["seconds"]
+                stage += o["stage_s"]
+            times.append(tstep)
         total = sum(times)
         val = sample * args.steps / total
         ta = [cpu_port_solve(model, insts[:1], settings, 1, node_threads=4)["seconds"] for _ in range(8)][3:]
@@ -209,6 +354,7 @@ def main():
                 "ms_per_step": 1e3 * total / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
                 "data": "synthetic", "config": {"workload": workload, "n_nodes": len(insts[0]["t_nodes"]), "sample_instances_per_step": sample},
                 "cpu_baseline": {"value": val, "unit": "solves/s", "cores": cores, "kind": "port",
+                                 "host": {"affinity_cpus": affinity_cpus, "cgroup_cpu_quota": cpu_quota},
                                  "what": "fast CPU restatement of the reference path (oracle/fast/wb_fast.cu), NOT the ocs2+HPIPM binary (not buildable here)",
                                  "sample": f"{sample} instances per step, one instance per thread, {cores} threads",
                                  "median_step_solves_per_s": float(np.median(sample / np.array(times))),

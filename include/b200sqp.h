@@ -157,15 +157,21 @@ int b200sqp_solve(b200sqp_handle h, void* stream);
  * those calls return. */
 int b200sqp_own_stream(b200sqp_handle h, void** stream);
 
-/* Global-step mode (settings.global_step = 1; SURVEY.md section 8e, not a reference semantic): one line-search step size per SQP iteration
- * for the whole, possibly multi-GPU, batch.  Per iteration b200sqp_solve evaluates the fixed ladder alpha_j = alpha_decay^j >= alpha_min
- * for every active instance with the reference's filter test (FilterLinesearch.cpp:34-57) and leaves
+/* Global-step mode (settings.global_step = 1; SURVEY.md section 8e, not a reference semantic -- the reference searches per instance,
+ * SqpSolver.cpp:517-565): one line-search step size per SQP iteration for the whole, possibly multi-GPU, batch.  Per iteration b200sqp_solve
+ * walks the fixed ladder alpha_j = alpha_decay^j >= alpha_min from the largest candidate: one roll-out of every active instance, the
+ * reference's filter test (FilterLinesearch.cpp:34-57), and
  *   stats[j] = { #instances that accept alpha_j, sum of their trial merits, max trial constraint violation, #active instances }
- * in DEVICE memory.  The callback combines the statistics of all ranks (one small collective on `stream`) and returns the index of the
- * chosen candidate, or -1 for a zero step; every rank must return the same index.  Without a callback the local statistics decide:
- * the largest alpha_j accepted by every active instance.  b200sqp_global_ladder reports the candidates. */
-typedef int (*b200sqp_global_step_fn)(void* user, double* stats_device /* [n_alpha][4] */, int n_alpha, void* stream);
-int b200sqp_set_global_step_callback(b200sqp_handle h, b200sqp_global_step_fn fn, void* user);
+ * combined over all ranks by two NCCL all-reduces (4 doubles SUM + 1 double MAX, on `stream`) when a communicator has been set; it stops at
+ * the first candidate every active instance of every rank accepts and applies it (a zero step when none is).  Every rank takes the same
+ * decisions from the same reduced numbers.
+ *
+ * b200sqp_set_comm: the ncclComm_t of this process' rank (created by the caller with ncclCommInitRank; void* so that hosts without nccl.h
+ * can forward it), n_ranks = its size.  NULL / 1 = single process.  The library resolves libnccl.so.2 at run time.
+ * b200sqp_global_stats: combined statistics of the last iteration of the last solve, stats [32][4]; candidates [0, n_evaluated) were
+ * evaluated; chosen = index of the applied candidate or -1. */
+int b200sqp_set_comm(b200sqp_handle h, void* nccl_comm, int n_ranks);
+int b200sqp_global_stats(b200sqp_handle h, double* stats /* [32][4] */, int32_t* n_evaluated, int32_t* chosen);
 int b200sqp_global_ladder(b200sqp_handle h, double* alpha /* [32] */, int32_t* n_alpha);
 
 /* per-instance iteration record: mirrors sqp::LogEntry / PerformanceIndex (SqpLogging.h, PerformanceIndex.h) */

@@ -200,6 +200,7 @@ void rolloutNode(const WbDeviceModel& m, Inst& I, int k, double alpha, NodeWs& w
     return;
   }
   constexpr int NT = 128;
+  DynWs& W = *r.dyn;
 #define PHASE(...)                      \
   for (int t_ = 0; t_ < NT; ++t_) {     \
     Par P{t_, NT};                      \

@@ -46,8 +46,7 @@ def test_single_instance_matches_per_instance_mode(model):
     assert np.array_equal(res[0]["x"], res[1]["x"]) and np.array_equal(res[0]["u"], res[1]["u"])
 
 
-@pytest.mark.parametrize("with_callback", [False, True])
-def test_batch_takes_one_admissible_step(model, with_callback):
+def test_batch_takes_one_admissible_step(model):
     from wb_humanoid_mpc_b200.solver import B200SqpSolver
 
     rng = np.random.default_rng(11)
@@ -56,8 +55,7 @@ def test_batch_takes_one_admissible_step(model, with_callback):
     per = B200SqpSolver(model, abi.default_settings(model, sqp_iteration=1, global_step=0))
     r0 = per.run(insts)
     glob = B200SqpSolver(model, abi.default_settings(model, sqp_iteration=1, global_step=1))
-    if with_callback:
-        glob.enable_global_step()
+    glob.enable_global_step()   # single process: no communicator, the local statistics decide
     r1 = glob.run(insts)
     ladder = glob.global_ladder()
     assert ladder[0] == 1.0 and np.allclose(ladder[1:] / ladder[:-1], 0.5) and ladder[-1] >= 1e-4
@@ -70,10 +68,29 @@ def test_batch_takes_one_admissible_step(model, with_callback):
     # instances whose own search stopped at the global candidate end at the same iterate
     same = np.isclose(lg(r0, "step_size")[:, 0], a[0])
     assert np.allclose(r0["x"][same], r1["x"][same], rtol=0, atol=1e-12)
-    if with_callback and a[0] > 0:
-        idx, g = glob.global_step_log[-1]
+    g, idx = glob.global_stats()
+    if a[0] > 0:
+        assert len(g) == idx + 1, "the ladder is walked lazily: nothing beyond the applied candidate is rolled out"
         assert ladder[idx] == a[0] and g[idx, 0] == g[idx, 3] == len(insts)
         assert np.all(g[:idx, 0] < g[:idx, 3]), "a larger candidate accepted by everybody would have been chosen"
+
+
+def test_centroidal_handle_global_step():
+    """the global-step mode on a centroidal handle: two instances take one common admissible step"""
+    from test_gpu_cen_ocp import make_instance
+    from wb_humanoid_mpc_b200.solver import B200SqpSolver
+
+    cmodel = model_loader.load_packaged_model("g1_centroidal")
+    rng = np.random.default_rng(4)
+    insts = [make_instance(cmodel, rng, "walk", 0.2, [0.3, 0.0, 0.7925, 0.0]), make_instance(cmodel, rng, "stance", 0.2, [0.0, 0.1, 0.7925, 0.1])]
+    if len(insts[0]["t_nodes"]) != len(insts[1]["t_nodes"]):
+        insts[1] = make_instance(cmodel, rng, "walk", 0.2, [0.0, 0.1, 0.7925, 0.1])
+    s = B200SqpSolver(cmodel, abi.default_settings(cmodel, sqp_iteration=1, global_step=1))
+    r = s.run(insts)
+    a = lg(r, "step_size")[:, 0]
+    assert a[0] == a[1] and (a[0] == 0.0 or np.any(np.isclose(s.global_ladder(), a[0])))
+    g, idx = s.global_stats()
+    assert idx == len(g) - 1 if a[0] > 0 else idx == -1
 
 
 def test_two_rank_nccl(model):

@@ -2,6 +2,7 @@
 #include "../../include/b200sqp.h"
 
 #include <cuda_runtime.h>
+#include <dlfcn.h>
 
 #include <cstdarg>
 #include <cstdio>

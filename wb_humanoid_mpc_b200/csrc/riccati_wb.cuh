@@ -236,8 +236,9 @@ __global__ void __launch_bounds__(BWD_THREADS, 1) riccati_bwd_kernel(QpDeviceVie
     for (int i = t0; i < NXR; i += nt) v.p[(iN1 + kk) * NXR + i] = Pc[NXR * NXR + i];
   };
   if (v.keepP) storeP(PQ[cur], N, tid, blockDim.x);
-  // stage record k -> operand set `set`, its [Q | q] -> qdst; issued by the helper warp only
-  auto prefetch = [&](int k, int set, double* qdst) {
+  // stage record k -> operand set `set`, its [Q | q] -> qdst; issued by the helper warp only, in two parts: the six bulk copies (one lane)
+  // before the factorisation, the 8-byte cp.async of r and R (whose HBM addresses are only 8-byte aligned) after it
+  auto prefetchBulk = [&](int k, int set, double* qdst) {
     const size_t sk = iN + k;
     const int nu = v.nu ? v.nu[sk] : NMR;
     if (lane == 0) {
@@ -252,18 +253,30 @@ __global__ void __launch_bounds__(BWD_THREADS, 1) riccati_bwd_kernel(QpDeviceVie
         bulk_g2s(Y[set], v.S + sk * NMR * NXR, NMR * NXR * 8, bar);
       }
     }
+  };
+  auto prefetchSmall = [&](int k, int set) {
+    const size_t sk = iN + k;
+    const int nu = v.nu ? v.nu[sk] : NMR;
     if (nu > 0) {
       if (lane < nu) __pipeline_memcpy_async(Y[set] + NMR * NXR + lane, v.r + sk * NMR + lane, 8);
       const double* Rg = v.R + sk * NMR * NMR;
+      int c = 0, r = lane;   // (r, c) of element i = lane + 32 j, without divisions
       for (int i = lane; i < NMR * NMR; i += 32) {
-        const int c = i / NMR, r = i - c * NMR;
+        while (r >= NMR) {
+          r -= NMR;
+          ++c;
+        }
         __pipeline_memcpy_async(Rs[set] + r + c * LMR, Rg + i, 8);
+        r += 32;
       }
     }
     __pipeline_commit();
   };
   unsigned parity = 0;
-  if (!gemmWarp) prefetch(N - 1, 0, PQ[1 - cur]);
+  if (!gemmWarp) {
+    prefetchBulk(N - 1, 0, PQ[1 - cur]);
+    prefetchSmall(N - 1, 0);
+  }
   WB_CLOCK_BEGIN()
 
   for (int k = N - 1; k >= 0; --k) {
@@ -300,7 +313,7 @@ __global__ void __launch_bounds__(BWD_THREADS, 1) riccati_bwd_kernel(QpDeviceVie
     //          over; GEMM warps: R~ first, then Q~ (lower tiles) and [S~ | r~] ---------------------------------------------------------------
     const double* Bk = ABk + NXR * NX1R;
     if (!gemmWarp) {
-      if (k > 0) prefetch(k - 1, 1 - set, Pc);
+      if (k > 0) prefetchBulk(k - 1, 1 - set, Pc);
       WB_TICK(22, 256)
       if (nu > 0) {
         named_sync(1, 128);
@@ -308,6 +321,8 @@ __global__ void __launch_bounds__(BWD_THREADS, 1) riccati_bwd_kernel(QpDeviceVie
         warp_chol_inverse_reg<24>(nu, Rk, LMR, v.reg, Linv, LMR, &ok);
         WB_TICK(24, 256)
       }
+      if (k > 0) prefetchSmall(k - 1, 1 - set);
+      WB_TICK(27, 256)
     } else {
       if (nu > 0 && warp >= 1 && warp <= 3) {
         const int tn[3] = {0, 1, 2};

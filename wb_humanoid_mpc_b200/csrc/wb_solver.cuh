@@ -16,7 +16,14 @@ namespace b200sqp {
 
 constexpr int LQA_THREADS = 128;
 constexpr int LQB_THREADS = 256;
-constexpr int RO_THREADS = 128;
+// K3 can pack RO_PACK shooting nodes per CTA on thread slices rotated by 64 lanes (the phases are narrow).  Measured on B200 (r2d): three
+// nodes per 192-thread CTA shorten the per-node phase time by 27 % but halve the nodes in flight per SM in practice; 2.6 ms per trial against
+// 1.26 ms for one node per 128-thread CTA, so the shipped configuration is RO_PACK = 1.
+#ifndef B200SQP_RO_PACK
+#define B200SQP_RO_PACK 1
+#endif
+constexpr int RO_PACK = B200SQP_RO_PACK;
+constexpr int RO_THREADS = RO_PACK == 1 ? 128 : 64 * RO_PACK;
 constexpr double kWeakEps = 1e-9;  // numeric_traits::weakEpsilon (ocs2_core/include/ocs2_core/NumericTraits.h:51)
 
 enum InstD { I_BASE_MERIT = 0, I_BASE_COST, I_BASE_DYN, I_BASE_EQ, I_ARMIJO, I_DXN, I_DUN, I_ALPHA, I_STEP, I_STEPTYPE, I_NEW_MERIT, I_NEW_COST,
@@ -362,60 +369,106 @@ __global__ void __launch_bounds__(128) prep_kernel(WbDev d, int mode) {
   }
 }
 
+// K3.  RO_PACK shooting nodes per CTA (see RO_PACK above): every PHASE body is instantiated once per node on a slice of the threads rotated by
+// 64 lanes; the nodes of a CTA share the barriers.
 __global__ void __launch_bounds__(RO_THREADS) rollout_kernel(WbDev d) {
   extern __shared__ double smem[];
-  const int k = blockIdx.x, b = blockIdx.y;
+  const int b = blockIdx.y, k0 = blockIdx.x * RO_PACK;
   if (d.flags[b * F_NF + F_CONVERGED] || d.flags[b * F_NF + F_LSDONE]) return;
   __shared__ WbDeviceModel msh;
-  for (int i = threadIdx.x; i < static_cast<int>(sizeof(WbDeviceModel) / 8); i += blockDim.x)
+  __shared__ NodeIn nsh[RO_PACK];
+  const int tid = threadIdx.x;
+  for (int i = tid; i < static_cast<int>(sizeof(WbDeviceModel) / 8); i += blockDim.x)
     reinterpret_cast<double*>(&msh)[i] = reinterpret_cast<const double*>(d.model)[i];
-  __syncthreads();
   const WbDeviceModel& m = msh;
   const int N = d.N;
-  const size_t node = static_cast<size_t>(b) * (N + 1) + k, stage = static_cast<size_t>(b) * N + k;
   const double alpha = d.inst[b * I_ND + I_ALPHA];
-  RoWs r;
-  roWsMap(smem, r);
-  NodeIn n;
-  loadNode(d, b, k, n);
-  double* perfOut = d.lsNode + node * 4;
-  for (int i = threadIdx.x; i < NX; i += blockDim.x) {
-    r.xa[i] = fma(alpha, d.qp.dx[node * NX + i], d.x[node * NX + i]);
-    if (k < N) r.xna[i] = fma(alpha, d.qp.dx[(node + 1) * NX + i], d.x[(node + 1) * NX + i]);
+  const size_t roStride = roWsDoubles();
+  const size_t node0 = static_cast<size_t>(b) * (N + 1) + k0, stage0 = static_cast<size_t>(b) * N + k0;
+  double* const perfBase = d.lsNode + node0 * 4;
+  bool live[RO_PACK];
+#pragma unroll
+  for (int h = 0; h < RO_PACK; ++h) {
+    const int k = k0 + h;
+    live[h] = k <= N;
+    if (!live[h]) continue;
+    RoWs r;
+    roWsMap(smem + h * roStride, r);
+    if (tid == 0) {
+      NodeIn n;
+      loadNode(d, b, k, n);
+      n.x = r.xa;
+      n.u = r.ua;
+      n.xnext = r.xna;
+      nsh[h] = n;
+    }
+    for (int i = tid; i < NX; i += blockDim.x) {
+      r.xa[i] = fma(alpha, d.qp.dx[(node0 + h) * NX + i], d.x[(node0 + h) * NX + i]);
+      if (k < N) r.xna[i] = fma(alpha, d.qp.dx[(node0 + h + 1) * NX + i], d.x[(node0 + h + 1) * NX + i]);
+    }
+    if (k < N)
+      for (int i = tid; i < NU; i += blockDim.x) r.ua[i] = fma(alpha, d.du[(stage0 + h) * NU + i], d.u[(stage0 + h) * NU + i]);
   }
-  if (k < N)
-    for (int i = threadIdx.x; i < NU; i += blockDim.x) r.ua[i] = fma(alpha, d.du[stage * NU + i], d.u[stage * NU + i]);
   __syncthreads();
-  n.x = r.xa;
-  n.u = r.ua;
-  n.xnext = r.xna;
-  if (k == N || n.event == 1) {
-    double part = 0.0;
-    for (int i = threadIdx.x; i < NX; i += blockDim.x) {
-      if (k == N) {
-        const double dx = r.xa[i] - n.xref[i];
-        part += 0.5 * m.Qfd[i] * dx * dx;
-      } else {
-        const double df = r.xa[i] - r.xna[i];
-        part += df * df;
+  // terminal and pre-event nodes: one short sum each, by the first thread of the node's slice
+#pragma unroll
+  for (int h = 0; h < RO_PACK; ++h) {
+    if (!live[h]) continue;
+    const int k = k0 + h;
+    const NodeIn& n = nsh[h];
+    if (k == N || n.event == 1) {
+      live[h] = false;
+      if (tid == 64 * h) {
+        RoWs r;
+        roWsMap(smem + h * roStride, r);
+        double c = 0.0;
+        for (int i = 0; i < NX; ++i) {
+          if (k == N) {
+            const double dx = r.xa[i] - n.xref[i];
+            c += 0.5 * m.Qfd[i] * dx * dx;
+          } else {
+            const double df = r.xa[i] - r.xna[i];
+            c += df * df;
+          }
+        }
+        double* perfOut = perfBase + 4 * h;
+        perfOut[0] = (k == N) ? c : 0.0;
+        perfOut[1] = (k == N) ? 0.0 : c;
+        perfOut[2] = 0.0;
       }
     }
-    r.pv[threadIdx.x] = 0.0;
-    __syncthreads();
-    double* red = r.fs;  // 4*58 >= 128 doubles
-    red[threadIdx.x] = part;
-    __syncthreads();
-    if (threadIdx.x == 0) {
-      double c = 0.0;
-      for (int i = 0; i < blockDim.x; ++i) c += red[i];
-      perfOut[0] = (k == N) ? c : 0.0;
-      perfOut[1] = (k == N) ? 0.0 : c;
-      perfOut[2] = 0.0;
-    }
-    return;
   }
+  bool any = false;
+#pragma unroll
+  for (int h = 0; h < RO_PACK; ++h) any = any || live[h];
+  if (!any) return;
   PHASE_CLOCK_BEGIN(2)
+#define RO_NODE(h_, ...)                                             \
+  if (live[h_]) {                                                    \
+    RoWs r;                                                          \
+    roWsMap(smem + (h_) * roStride, r);                              \
+    const NodeIn& n = nsh[h_];                                       \
+    DynWs& W = *r.dyn;                                               \
+    double* const perfOut = perfBase + 4 * (h_);                     \
+    const Par P = rot(Par{tid, RO_THREADS}, 64 * (h_));              \
+    __VA_ARGS__                                                      \
+  }
+#undef PHASE
+#if B200SQP_RO_PACK == 1
+#define RO_NODES(...) RO_NODE(0, __VA_ARGS__)
+#elif B200SQP_RO_PACK == 2
+#define RO_NODES(...) RO_NODE(0, __VA_ARGS__) RO_NODE(1, __VA_ARGS__)
+#else
+#define RO_NODES(...) RO_NODE(0, __VA_ARGS__) RO_NODE(1, __VA_ARGS__) RO_NODE(2, __VA_ARGS__)
+#endif
+#define PHASE(...)           \
+  { RO_NODES(__VA_ARGS__) }  \
+  __syncthreads();           \
+  PHASE_TICK()
 #include "wb_rollout_body.inc"
+#undef PHASE
+#undef RO_NODES
+#undef RO_NODE
 }
 
 // trial PerformanceIndex of one instance at its current alpha (sums over the per-node results of K3) and the filter test

@@ -124,7 +124,8 @@ EXPORTED_SYMBOLS = [
     "b200sqp_reset",
     "b200sqp_solve",
     "b200sqp_own_stream",
-    "b200sqp_set_global_step_callback",
+    "b200sqp_set_comm",
+    "b200sqp_global_stats",
     "b200sqp_global_ladder",
     "b200sqp_download",
     "b200sqp_download_value_function",

@@ -57,44 +57,49 @@ class B200SqpSolver:
             _l.check(L.b200sqp_stage_doubles(self._h, C.c_int(0), C.byref(per)))
             self._raw_per = per.value
         self.batch = self.n_nodes = 0
-        self._gs_cb = None
-        self.global_step_log = []   # (chosen index, combined statistics) per SQP iteration of the last solves (global-step mode)
+        self._nccl = self._comm = None
 
     # -- global-step mode --------------------------------------------------------------------------------
-    def enable_global_step(self, quorum: float = 1.0):
-        """Register the cross-rank combiner of the global-step mode (settings.global_step must be 1).  The per-candidate statistics stay
-        in device memory; with an initialised torch.distributed process group they are combined with ONE all_gather (NCCL over NVLink),
-        and every rank picks the same candidate: the largest alpha accepted by >= quorum of all active instances."""
+    def enable_global_step(self):
+        """Cross-rank global-step mode (settings.global_step must be 1): hands the library an NCCL communicator of this rank
+        (b200sqp_set_comm); the all-reduces of the per-candidate statistics then run INSIDE b200sqp_solve on its stream, exactly as for a C++
+        host.  The communicator is created here with ncclCommInitRank (ctypes on the process' libnccl.so.2), its unique id broadcast through
+        torch.distributed, which is only the bootstrap plumbing.  Without an initialised process group (or world size 1) nothing is
+        registered: the local statistics decide."""
         import torch
         import torch.distributed as dist
 
-        solver = self
+        if not (dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1):
+            return
+        world, rank = dist.get_world_size(), dist.get_rank()
+        nccl = C.CDLL("libnccl.so.2")   # the copy torch already loaded (same soname)
 
-        class _DevView:  # zero-copy view of the statistics the library keeps in device memory
-            def __init__(self, ptr, n):
-                self.__cuda_array_interface__ = {"shape": (n, 4), "typestr": "<f8", "data": (ptr, False), "version": 3}
+        class UniqueId(C.Structure):
+            _fields_ = [("internal", C.c_byte * 128)]
 
-        def combine(_user, stats_ptr, n_alpha, _stream):
-            try:
-                t = torch.as_tensor(_DevView(stats_ptr, n_alpha), device="cuda")
-                if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
-                    allr = torch.empty((dist.get_world_size(), n_alpha, 4), dtype=torch.float64, device=t.device)
-                    dist.all_gather_into_tensor(allr, t.contiguous())
-                    glob = torch.stack([allr[:, :, 0].sum(0), allr[:, :, 1].sum(0), allr[:, :, 2].amax(0), allr[:, :, 3].sum(0)], dim=1)
-                else:
-                    glob = t.clone()
-                g = glob.cpu().numpy()
-                ok = np.nonzero(g[:, 0] >= quorum * g[:, 3] - 1e-9)[0]
-                idx = int(ok[0]) if len(ok) and g[0, 3] > 0 else -1
-                solver.global_step_log.append((idx, g))
-                return idx
-            except Exception as e:  # never unwind through the C frame
-                print(f"b200sqp global-step combiner failed: {e!r}", flush=True)
-                return -1
+        uid = UniqueId()
+        if rank == 0:
+            rc = nccl.ncclGetUniqueId(C.byref(uid))
+            assert rc == 0, f"ncclGetUniqueId failed ({rc})"
+        t = torch.frombuffer(bytearray(bytes(uid)), dtype=torch.uint8).clone()
+        dev = torch.device("cuda", torch.cuda.current_device()) if dist.get_backend() == "nccl" else torch.device("cpu")
+        t = t.to(dev)
+        dist.broadcast(t, src=0)
+        C.memmove(C.byref(uid), bytes(t.cpu().numpy().tobytes()), 128)
+        comm = C.c_void_p()
+        nccl.ncclCommInitRank.argtypes = [C.POINTER(C.c_void_p), C.c_int, UniqueId, C.c_int]
+        rc = nccl.ncclCommInitRank(C.byref(comm), world, uid, rank)
+        assert rc == 0, f"ncclCommInitRank failed ({rc})"
+        self._nccl, self._comm = nccl, comm
+        _l.check(_l.lib().b200sqp_set_comm(self._h, comm, C.c_int(world)))
 
-        CB = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p)
-        self._gs_cb = CB(combine)
-        _l.check(_l.lib().b200sqp_set_global_step_callback(self._h, self._gs_cb, None))
+    def global_stats(self):
+        """(statistics [n_evaluated, 4] = {#accept, sum of merits, max violation, #active} over all ranks, index of the applied candidate or -1)
+        of the last iteration of the last solve in the global-step mode"""
+        st = np.zeros((32, 4))
+        n, ch = C.c_int32(), C.c_int32()
+        _l.check(_l.lib().b200sqp_global_stats(self._h, _p(st), C.byref(n), C.byref(ch)))
+        return st[: n.value].copy(), ch.value
 
     def global_ladder(self) -> np.ndarray:
         a = np.zeros(32)
@@ -106,6 +111,9 @@ class B200SqpSolver:
         if self._h:
             _l.lib().b200sqp_destroy(self._h)
             self._h = C.c_void_p()
+        if getattr(self, "_comm", None):
+            self._nccl.ncclCommDestroy(self._comm)
+            self._comm = None
 
     def __del__(self):
         try:
