@@ -174,6 +174,44 @@ int b200sqp_set_comm(b200sqp_handle h, void* nccl_comm, int n_ranks);
 int b200sqp_global_stats(b200sqp_handle h, double* stats /* [32][4] */, int32_t* n_evaluated, int32_t* chosen);
 int b200sqp_global_ladder(b200sqp_handle h, double* alpha /* [32] */, int32_t* n_alpha);
 
+/* ------------------------------------------------------------------------------------------------------------------
+ * Device-side instance builder: what SolverBase::preRun + the top of SqpSolver::runImpl compute per instance on the
+ * host -- SwitchedModelReferenceManager::modifyReferences (GaitSchedule::getModeSchedule, SwingTrajectoryPlanner::update), the velocity-command
+ * target trajectories (WBMpcTargetTrajectoriesCalculator.cpp:82-136), timeDiscretizationWithEvents, initializeStateInputTrajectories with the
+ * WeightCompInitializer -- evaluated on the GPU from a few numbers per instance.  b200sqp_build_instances replaces
+ * b200sqp_upload_instances for batches whose instances share the horizon [t0, t0 + horizon] (a batch of synchronous MPC cycles).
+ * ------------------------------------------------------------------------------------------------------------------ */
+#define B200SQP_MAX_GAITS 16
+#define B200SQP_MAX_GAIT_MODES 8
+typedef struct b200sqp_builder_desc {
+  int32_t n_gaits;
+  int32_t gait_n_modes[B200SQP_MAX_GAITS];                            /* ModeSequenceTemplate::modeSequence length (gait.info) */
+  int32_t gait_modes[B200SQP_MAX_GAITS][B200SQP_MAX_GAIT_MODES];      /* 0 FLY, 1 RF, 2 LF, 3 STANCE (MotionPhaseDefinition.h) */
+  double gait_switching_times[B200SQP_MAX_GAITS][B200SQP_MAX_GAIT_MODES + 1];
+  double swing[8];                /* swing_trajectory_config: liftOffVelocity, touchDownVelocity, swingHeight, touchDownHeightOffset, swingTimeScale,
+                                     impactProximityFactor lift-off velocity, touch-down velocity, mid-point value (task.info:64-74) */
+  double default_joint_state[B200SQP_MAX_BODIES];                     /* reference.info defaultJointState */
+  double total_mass;
+  double dt;                      /* sqp dt */
+} b200sqp_builder_desc;
+int b200sqp_set_builder(b200sqp_handle h, const b200sqp_builder_desc* desc);
+
+/* One synchronous MPC cycle of `batch` whole-body instances over [t0, t0 + horizon]:
+ *   x0 [B][nx] measured states; gait [B] index into the gait table (its template is tiled from gait_start[b] <= 0.5, STANCE before;
+ *   the table's "stance" template reproduces the default schedule of GaitSchedule); cmd [B][4] = (v_x, v_y, pelvis height, yaw rate).
+ *   warm = 0: cold start (x_k = x0, WeightCompInitializer inputs); warm = 1: the iterate left on the device by the previous solve of this
+ *   handle is the previous primal solution and is shifted by the reference's rule (Initialization.cpp:35-79) -- no host copy of x / u.
+ * Every instance must produce the same number of shooting nodes (same event count inside the horizon); *n_nodes returns it, B200SQP_EINVAL
+ * otherwise (group such instances by gait phase on the host).  Host pointers; ~0.5 kB per instance cross PCIe. */
+int b200sqp_build_instances(b200sqp_handle h, int batch, double t0, double horizon, const double* x0, const int32_t* gait, const double* gait_start,
+                            const double* cmd, int warm, int32_t* n_nodes);
+
+/* The per-instance inputs as they currently lie on the device (the arrays of b200sqp_upload_instances, whoever produced them: the upload or the
+ * device-side builder), e.g. to log the references a batch was solved with.  x_init / u_init are the initial guess (what b200sqp_reset restores).
+ * Any pointer may be NULL. */
+int b200sqp_download_instances(b200sqp_handle h, double* x0, double* x_init, double* u_init, double* t_nodes, uint8_t* node_event, uint8_t* contact_flags,
+                               double* swing_ref, double* impact_factor, double* arm_phase, double* x_ref);
+
 /* per-instance iteration record: mirrors sqp::LogEntry / PerformanceIndex (SqpLogging.h, PerformanceIndex.h) */
 typedef struct b200sqp_iter_log {
   double base_merit, base_cost, base_dyn_sse, base_eq_sse;

@@ -187,3 +187,51 @@ def cen_desc(model: dict) -> CenDesc:
     for k in range(3):
         c.com_to_base_nominal[k] = model["srbd_nominal"]["com_to_base"][k]
     return c
+
+
+MAX_GAITS = 16
+MAX_GAIT_MODES = 8
+MODE_NUMBER = {"FLY": 0, "RF": 1, "LF": 2, "STANCE": 3}
+
+
+class BuilderDesc(C.Structure):
+    _fields_ = [
+        ("n_gaits", C.c_int32),
+        ("gait_n_modes", C.c_int32 * MAX_GAITS),
+        ("gait_modes", (C.c_int32 * MAX_GAIT_MODES) * MAX_GAITS),
+        ("gait_switching_times", (C.c_double * (MAX_GAIT_MODES + 1)) * MAX_GAITS),
+        ("swing", C.c_double * 8),
+        ("default_joint_state", C.c_double * MAX_BODIES),
+        ("total_mass", C.c_double),
+        ("dt", C.c_double),
+    ]
+
+
+def builder_desc(model: dict) -> tuple[BuilderDesc, list[str]]:
+    """b200sqp_builder_desc of the device-side instance builder + the gait names in table order (gait id = index).  The "stance" entry is the
+    default schedule of GaitSchedule (STANCE phases of 0.5 s)."""
+    d = BuilderDesc()
+    names = list(model["gaits"].keys())
+    assert len(names) <= MAX_GAITS
+    d.n_gaits = len(names)
+    for g, name in enumerate(names):
+        gt = model["gaits"][name]
+        modes = [m if isinstance(m, int) else MODE_NUMBER[m] for m in gt["modeSequence"]]
+        assert 1 <= len(modes) <= MAX_GAIT_MODES
+        times = [float(t) for t in gt["switchingTimes"]]
+        if any(b <= a for a, b in zip(times, times[1:])):
+            continue   # gait.info's "skip" template has a decreasing switching time (0.75 -> 0.08): left out of the device table (n_modes = 0)
+        d.gait_n_modes[g] = len(modes)
+        for i, m in enumerate(modes):
+            d.gait_modes[g][i] = m
+        for i, t in enumerate(gt["switchingTimes"]):
+            d.gait_switching_times[g][i] = float(t)
+    sw = model["swing"]
+    for i, k in enumerate(["liftOffVelocity", "touchDownVelocity", "swingHeight", "touchDownHeightOffset", "swingTimeScale", "ipfLiftOffVelocity",
+                           "ipfTouchDownVelocity", "ipfMidPointValue"]):
+        d.swing[i] = float(sw[k])
+    for j, q in enumerate(model["reference"]["defaultJointState"]):
+        d.default_joint_state[j] = float(q)
+    d.total_mass = float(sum(model["mass"]))
+    d.dt = float(model["sqp"]["dt"])
+    return d, names

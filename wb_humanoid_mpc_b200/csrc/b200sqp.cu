@@ -18,6 +18,7 @@
 #include "riccati_wb.cuh"
 #ifdef B200SQP_WITH_WB
 #include "wb_solver.cuh"
+#include "wb_builder.cuh"
 #include "cen_dynamics.cuh"
 #include "wb_torque.cuh"
 #include "cen_kernels.cuh"

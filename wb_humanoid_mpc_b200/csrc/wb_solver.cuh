@@ -451,6 +451,8 @@ __global__ void __launch_bounds__(RO_THREADS) rollout_kernel(WbDev d) {
     DynWs& W = *r.dyn;                                               \
     double* const perfOut = perfBase + 4 * (h_);                     \
     const Par P = rot(Par{tid, RO_THREADS}, 64 * (h_));              \
+    (void)n;                                                         \
+    (void)perfOut;                                                   \
     __VA_ARGS__                                                      \
   }
 #undef PHASE

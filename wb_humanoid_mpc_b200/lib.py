@@ -124,6 +124,9 @@ EXPORTED_SYMBOLS = [
     "b200sqp_reset",
     "b200sqp_solve",
     "b200sqp_own_stream",
+    "b200sqp_set_builder",
+    "b200sqp_build_instances",
+    "b200sqp_download_instances",
     "b200sqp_set_comm",
     "b200sqp_global_stats",
     "b200sqp_global_ladder",

@@ -134,6 +134,38 @@ class B200SqpSolver:
         _l.check(_l.lib().b200sqp_upload_instances(self._h, _p(k[0]), _p(k[1]), _p(k[2]), _p(k[3]), k[4].ctypes.data_as(_l.u8p),
                                                    k[5].ctypes.data_as(_l.u8p), _p(k[6]), _p(k[7]), _p(k[8]), _p(k[9])))
 
+    def build_instances(self, t0: float, horizon: float, x0, gaits, gait_start, cmd, warm: bool = False) -> int:
+        """Device-side instance builder (b200sqp_build_instances): one synchronous MPC cycle of len(x0) instances over [t0, t0 + horizon] from
+        x0 [B, nx], gait names (or ids) [B], gait start times [B] and velocity commands [B, 4]; warm = shift the iterate left on the device by
+        the previous solve.  Returns the common number of shooting nodes."""
+        L = _l.lib()
+        if not getattr(self, "_builder_set", False):
+            self._bdesc, self._gait_names = abi.builder_desc(self.model)
+            _l.check(L.b200sqp_set_builder(self._h, C.byref(self._bdesc)))
+            self._builder_set = True
+        x0 = _f(x0)
+        B = x0.shape[0]
+        gid = np.ascontiguousarray([g if isinstance(g, (int, np.integer)) else self._gait_names.index(g) for g in gaits], dtype=np.int32)
+        gs, cm = _f(gait_start), _f(cmd)
+        assert gid.shape == (B,) and gs.shape == (B,) and cm.shape == (B, 4)
+        n = C.c_int32()
+        _l.check(L.b200sqp_build_instances(self._h, C.c_int(B), C.c_double(t0), C.c_double(horizon), _p(x0), gid.ctypes.data_as(_l.ip), _p(gs), _p(cm),
+                                           C.c_int(int(warm)), C.byref(n)))
+        self.batch, self.n_nodes = B, n.value
+        return n.value
+
+    def download_instances(self) -> dict:
+        """the per-instance inputs as they lie on the device (b200sqp_download_instances), in the layout of stack_instances"""
+        B, n, nx, nu = self.batch, self.n_nodes, self.nx, self.nu
+        out = dict(x0=np.zeros((B, nx)), x_init=np.zeros((B, n, nx)), u_init=np.zeros((B, n - 1, nu)), t_nodes=np.zeros((B, n)),
+                   node_event=np.zeros((B, n), dtype=np.uint8), contact_flags=np.zeros((B, n, 2), dtype=np.uint8), swing_ref=np.zeros((B, n, 2, 3)),
+                   impact_factor=np.zeros((B, n, 2)), arm_phase=np.zeros((B, n)), x_ref=np.zeros((B, n, nx)))
+        u8 = lambda a: a.ctypes.data_as(_l.u8p)
+        _l.check(_l.lib().b200sqp_download_instances(self._h, _p(out["x0"]), _p(out["x_init"]), _p(out["u_init"]), _p(out["t_nodes"]), u8(out["node_event"]),
+                                                     u8(out["contact_flags"]), _p(out["swing_ref"]), _p(out["impact_factor"]), _p(out["arm_phase"]),
+                                                     _p(out["x_ref"])))
+        return out
+
     def reset(self):
         """SqpSolver::reset(): restore the uploaded initial guess on the device"""
         _l.check(_l.lib().b200sqp_reset(self._h))
