@@ -593,6 +593,36 @@ def main():
     except Exception as e:   # the host layer is optional for the bench line
         host_api = {"unavailable": repr(e)}
 
+    # ---- the same with the DEVICE-SIDE INSTANCE BUILDER (b200sqp_build_instances): per step the host hands over x0, gait id, gait start and the
+    # velocity command of every instance (~0.5 kB each, pinned), the GPU builds mode schedule / swing references / targets / time grid / initial
+    # guess, solves, and the primal solution comes back -- the end-to-end path without the 150 kB per instance of per-node host arrays
+    device_builder = None
+    try:
+        bx0 = pin(np.array([i["x0"] for i in insts]))
+        bcmd = pin(np.array([i["cmd"] for i in insts], dtype=np.float64))
+        bstart = pin(np.zeros(B))
+        bgait = [i["gait"] for i in insts]
+        sb = B200SqpSolver(model, settings, device=local_rank)
+        for _ in range(min(args.warmup, 2)):
+            sb.build_instances(0.0, args.horizon, bx0, bgait, bstart, bcmd)
+            sb.solve()
+            rb = sb.primal_solution()
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            sb.build_instances(0.0, args.horizon, bx0, bgait, bstart, bcmd)
+            sb.solve()
+            rb = sb.primal_solution()
+        torch.cuda.synchronize()
+        b_s = max_over_ranks(time.perf_counter() - t0)
+        barrier()
+        device_builder = {"value": total_solves / b_s, "unit": "solves/s", "h2d_bytes_per_step": int(bx0.nbytes + bcmd.nbytes + bstart.nbytes + 4 * B),
+                          "d2h_bytes_per_step": int(d2h), "call": "b200sqp_build_instances + b200sqp_solve + b200sqp_download (serial, one handle)",
+                          "max_abs_diff_x_vs_upload_path": float(np.abs(rb["x"] - sol["x"]).max())}
+        sb.close()
+    except Exception as e:
+        device_builder = {"unavailable": repr(e)}
+
     # ---- per-kernel roofline -------------------------------------------------------------------------------------------
     # Device ms per stage are CUDA events recorded by the library on the launching stream (b200sqp_get_stage_times): ms[0] = K1a + K1b,
     # ms[3] = K1b alone, ms[1] = K2 (+ remap), ms[2] = the line search = n_ls x (K3 + accept).
@@ -657,7 +687,7 @@ def main():
             "e2e": {"value": e2e, "unit": "solves/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
                     "mode": "double-buffered: 2 handles in flight on 2 CUDA streams, every step uploads its inputs from and downloads its results to "
                             "pinned host memory" if e2e_pipe else "serial upload -> solve -> download",
-                    "pipelined": e2e_pipe, "serial": {"value": e2e_serial, "unit": "solves/s"}, "host_api": host_api},
+                    "pipelined": e2e_pipe, "serial": {"value": e2e_serial, "unit": "solves/s"}, "host_api": host_api, "device_builder": device_builder},
             "gpu_launches": int(launches), "roofline": roofline, "clocks": clocks}
 
     if rank == 0 and world == 1 and not args.no_cpu_baseline:

@@ -201,6 +201,8 @@ int b200sqp_set_builder(b200sqp_handle h, const b200sqp_builder_desc* desc);
  *   the table's "stance" template reproduces the default schedule of GaitSchedule); cmd [B][4] = (v_x, v_y, pelvis height, yaw rate).
  *   warm = 0: cold start (x_k = x0, WeightCompInitializer inputs); warm = 1: the iterate left on the device by the previous solve of this
  *   handle is the previous primal solution and is shifted by the reference's rule (Initialization.cpp:35-79) -- no host copy of x / u.
+ *   With warm = 1, x0 may be NULL: the measured state is then the previous plan interpolated at t0 on the device (perfect tracking, the dummy
+ *   simulation of the reference's launch files), which closes the MPC loop without any per-cycle state transfer.
  * Every instance must produce the same number of shooting nodes (same event count inside the horizon); *n_nodes returns it, B200SQP_EINVAL
  * otherwise (group such instances by gait phase on the host).  Host pointers; ~0.5 kB per instance cross PCIe. */
 int b200sqp_build_instances(b200sqp_handle h, int batch, double t0, double horizon, const double* x0, const int32_t* gait, const double* gait_start,

@@ -75,7 +75,11 @@ def test_solve_after_device_build_equals_the_upload_path(model):
     host = [references.build_instance(model, x0s[b], t0=0.0, horizon=1.1, gait="walk", cmd=list(cmds[b])) for b in range(B)]
     rb = B200SqpSolver(model, st).run(host)
     assert np.array_equal(ra["log"][:, :, 8], rb["log"][:, :, 8])
-    assert np.max(np.abs(ra["x"] - rb["x"])) < 1e-9 and np.max(np.abs(ra["u"] - rb["u"])) < 1e-7
+    # the two input sets agree to 1e-16 relative; that is enough to resolve an exact tie of the complete-pivoting LU differently at some node, and
+    # the two (equally valid) bases of the projected QP then give answers that differ by its conditioning: 1e-5 relative
+    assert np.max(np.abs(ra["x"] - rb["x"])) < 1e-5 * np.max(np.abs(rb["x"])) and np.max(np.abs(ra["u"] - rb["u"])) < 1e-5 * np.max(np.abs(rb["u"]))
+    for j in (0, 1, 2, 3, 4, 5, 6, 7):
+        assert np.allclose(ra["log"][:, :, j], rb["log"][:, :, j], rtol=1e-7, atol=1e-9)
 
 
 def test_receding_horizon_on_the_device(model):
@@ -105,6 +109,36 @@ def test_receding_horizon_on_the_device(model):
         compare(dev, host)
         assert not np.allclose(dev["u_init"][:, 0], dev["u_init"][:, -1])   # the overlap is interpolated, the tail is the initializer
     assert len(counts) >= 1
+
+
+def test_closed_loop_without_state_transfer(model):
+    """x0 = NULL with warm = 1: the measured state of the next cycle is the plan interpolated at the new initial time on the device; 12 cycles of
+    a walking batch stay feasible and the constraint violation of the real-time iteration falls"""
+    from wb_humanoid_mpc_b200.solver import B200SqpSolver
+
+    rng = np.random.default_rng(11)
+    B, horizon = 8, 1.1
+    x0s, cmds = make_inputs(model, rng, B)
+    solver = B200SqpSolver(model, abi.default_settings(model, sqp_iteration=1))
+    solver.build_instances(0.0, horizon, x0s, ["walk"] * B, [0.0] * B, cmds)
+    solver.solve()
+    first = solver.iterations_log()[:, 0]
+    prev = solver.primal_solution()
+    prev_t = solver.download_instances()["t_nodes"]
+    for c in range(1, 13):
+        t1 = c / 60.0
+        solver.build_instances(t1, horizon, None, ["walk"] * B, [0.0] * B, cmds, warm=True)
+        inp = solver.download_instances()
+        # the state the device took as measurement is the previous plan at t1
+        want = np.array([references.linear_interpolate(t1, prev_t[b], prev["x"][b]) for b in range(B)])
+        assert np.max(np.abs(inp["x0"] - want)) < 1e-12
+        solver.solve()
+        prev = solver.primal_solution()
+        prev_t = inp["t_nodes"]
+        assert not prev["status"].any()
+    last = solver.iterations_log()[:, 0]
+    g0, g1 = np.sqrt(first[:, 2] + first[:, 3]), np.sqrt(last[:, 2] + last[:, 3])
+    assert np.median(g1) < 0.2 * np.median(g0)
 
 
 def test_mixed_node_counts_are_refused(model):

@@ -209,7 +209,8 @@ __global__ void __launch_bounds__(BWD_THREADS, 1) riccati_bwd_kernel(QpDeviceVie
   double* Y[2] = {W + W_D, W + W_D + Y_D};
   double* Rs[2] = {Y[1] + Y_D, Y[1] + Y_D + R_D};
   double* Linv = Rs[1] + R_D;
-  unsigned long long* bar = reinterpret_cast<unsigned long long*>(Linv + R_D);
+  unsigned long long* bar = reinterpret_cast<unsigned long long*>(Linv + R_D);   // [A | b | B], S of the next stage
+  unsigned long long* barQ = bar + 1;                                            // [Q | q] of the next stage
   __shared__ int ok;
   const bool gemmWarp = warp < GEMM_WARPS;
   const size_t iN = static_cast<size_t>(inst) * N, iN1 = static_cast<size_t>(inst) * (N + 1);
@@ -217,6 +218,7 @@ __global__ void __launch_bounds__(BWD_THREADS, 1) riccati_bwd_kernel(QpDeviceVie
   if (tid == 0) {
     ok = 1;
     mbar_init(bar, 1);
+    mbar_init(barQ, 1);
     mbar_fence_init();
   }
   int cur = 0;
@@ -236,22 +238,29 @@ __global__ void __launch_bounds__(BWD_THREADS, 1) riccati_bwd_kernel(QpDeviceVie
     for (int i = t0; i < NXR; i += nt) v.p[(iN1 + kk) * NXR + i] = Pc[NXR * NXR + i];
   };
   if (v.keepP) storeP(PQ[cur], N, tid, blockDim.x);
-  // stage record k -> operand set `set`, its [Q | q] -> qdst; issued by the helper warp only, in two parts: the six bulk copies (one lane)
-  // before the factorisation, the 8-byte cp.async of r and R (whose HBM addresses are only 8-byte aligned) after it
-  auto prefetchBulk = [&](int k, int set, double* qdst) {
+  // Stage record k -> operand set `set`, issued by the helper warp only, in three parts: the bulk copies of [A | b | B] and S (one lane) as soon
+  // as that set is free; the bulk copies of [Q | q] once the buffer that takes them ([P | p] of the previous stage) is dead; the 8-byte cp.async
+  // of r and R (whose HBM addresses are only 8-byte aligned) after the factorisation.
+  auto prefetchBulk = [&](int k, int set) {
     const size_t sk = iN + k;
     const int nu = v.nu ? v.nu[sk] : NMR;
     if (lane == 0) {
       fence_proxy_async();
-      mbar_expect_tx(bar, static_cast<unsigned>((2 * NXR * NX1R + NXR * nu + (nu > 0 ? NMR * NXR : 0)) * 8));
+      mbar_expect_tx(bar, static_cast<unsigned>((NXR * NX1R + NXR * nu + (nu > 0 ? NMR * NXR : 0)) * 8));
       bulk_g2s(AB[set], v.A + sk * NXR * NXR, NXR * NXR * 8, bar);
       bulk_g2s(AB[set] + NXR * NXR, v.b + sk * NXR, NXR * 8, bar);
-      bulk_g2s(qdst, v.Q + (iN1 + k) * NXR * NXR, NXR * NXR * 8, bar);
-      bulk_g2s(qdst + NXR * NXR, v.q + (iN1 + k) * NXR, NXR * 8, bar);
       if (nu > 0) {
         bulk_g2s(AB[set] + NXR * NX1R, v.Bm + sk * NXR * NMR, static_cast<unsigned>(NXR * nu * 8), bar);
         bulk_g2s(Y[set], v.S + sk * NMR * NXR, NMR * NXR * 8, bar);
       }
+    }
+  };
+  auto prefetchQ = [&](int k, double* qdst) {
+    if (lane == 0) {
+      fence_proxy_async();
+      mbar_expect_tx(barQ, static_cast<unsigned>(NXR * NX1R * 8));
+      bulk_g2s(qdst, v.Q + (iN1 + k) * NXR * NXR, NXR * NXR * 8, barQ);
+      bulk_g2s(qdst + NXR * NXR, v.q + (iN1 + k) * NXR, NXR * 8, barQ);
     }
   };
   auto prefetchSmall = [&](int k, int set) {
@@ -272,9 +281,10 @@ __global__ void __launch_bounds__(BWD_THREADS, 1) riccati_bwd_kernel(QpDeviceVie
     }
     __pipeline_commit();
   };
-  unsigned parity = 0;
+  unsigned parity = 0, parityQ = 0;
   if (!gemmWarp) {
-    prefetchBulk(N - 1, 0, PQ[1 - cur]);
+    prefetchBulk(N - 1, 0);
+    prefetchQ(N - 1, PQ[1 - cur]);
     prefetchSmall(N - 1, 0);
   }
   WB_CLOCK_BEGIN()
@@ -288,32 +298,29 @@ __global__ void __launch_bounds__(BWD_THREADS, 1) riccati_bwd_kernel(QpDeviceVie
     double* ABk = AB[set];
     double* Yk = Y[set];
     double* Rk = Rs[set];
-    // ---- the stage record has landed ---------------------------------------------------------------------------------------------------
+    const double* Bk = ABk + NXR * NX1R;
+    const int tilesN = (NX1R + nu + 7) >> 3;
+    // ---- [A | b | B], S, r, R of this stage have landed ----------------------------------------------------------------------------------------
     if (!gemmWarp) __pipeline_wait_prior(0);
     mbar_wait(bar, parity);
     parity ^= 1;
     __syncthreads();
     WB_TICK(1, 0)
     WB_TICK(20, 256)
-    // ---- P1: W = P [A | b | B] (58 x (59 + nu)), column b additionally gets p ------------------------------------------------------------
+    // ---- P1a: the columns of W = P [A | b | B] that R~ needs first: column tiles 7.. = [A_56 A_57 | b | B] (column b additionally gets p) --------
     if (gemmWarp) {
-      const int tilesN = (NX1R + nu + 7) >> 3;
-      for (int ng = 0; ng < tilesN; ng += 4) {
-        const int tn[4] = {ng, ng + 1, ng + 2, ng + 3};
-        const int cnt = tilesN - ng < 4 ? tilesN - ng : 4;
-        mma_item<false, false, 4, NXR, true>(lane, NXR, NX1R + nu, 0, 1.0, Pc, NXR, warp, ABk, NXR, tn, cnt, W, LWR, Pc + NXR * NXR, NXR);
-      }
+      const int tn[4] = {7, 8, 9, 10};
+      mma_item<false, false, 4, NXR, true>(lane, NXR, NX1R + nu, 0, 1.0, Pc, NXR, warp, ABk, NXR, tn, tilesN - 7, W, LWR, Pc + NXR * NXR, NXR);
     } else if (v.keepP && k < N - 1) {
-      storeP(Pc, k + 1, lane, 32);   // (the cost-to-go of stage k+1 is complete and read-only during this phase)
+      storeP(Pc, k + 1, lane, 32);   // (the cost-to-go of stage k+1 is complete and read-only until the [Q | q] copy below)
     }
     __syncthreads();
     WB_TICK(2, 0)
     WB_TICK(21, 256)
-    // ---- P2: helper warp: stream stage k-1 ([P | p] is dead: its buffer takes [Q | q]), then factorise R~ as soon as the GEMM warps hand it
-    //          over; GEMM warps: R~ first, then Q~ (lower tiles) and [S~ | r~] ---------------------------------------------------------------
-    const double* Bk = ABk + NXR * NX1R;
+    // ---- P1b / P2: helper warp: stream [A | b | B], S of stage k-1, then factorise R~ as soon as three GEMM warps hand it over -- the
+    //      factorisation (latency bound, one warp) runs WHILE the GEMM warps finish W (column tiles 0..6), and form Q~ (lower tiles) and [S~ | r~]
     if (!gemmWarp) {
-      if (k > 0) prefetchBulk(k - 1, 1 - set, Pc);
+      if (k > 0) prefetchBulk(k - 1, 1 - set);
       WB_TICK(22, 256)
       if (nu > 0) {
         named_sync(1, 128);
@@ -324,12 +331,20 @@ __global__ void __launch_bounds__(BWD_THREADS, 1) riccati_bwd_kernel(QpDeviceVie
       if (k > 0) prefetchSmall(k - 1, 1 - set);
       WB_TICK(27, 256)
     } else {
-      if (nu > 0 && warp >= 1 && warp <= 3) {
+      if (nu > 0 && warp >= 1 && warp <= 3) {   // R~ = R + B'W_B
         const int tn[3] = {0, 1, 2};
         mma_item<true, true, 3, NXR>(lane, nu, nu, 0, 1.0, Bk, NXR, warp - 1, W + LWR * NX1R, LWR, tn, 3, Rk, LMR);
         __threadfence_block();
         named_arrive(1, 128);
       }
+      {   // the rest of W: column tiles 0..6 of row strip `warp`
+        const int ta[4] = {0, 1, 2, 3}, tb[4] = {4, 5, 6, 0};
+        mma_item<false, false, 4, NXR, true>(lane, NXR, NX1R + nu, 0, 1.0, Pc, NXR, warp, ABk, NXR, ta, 4, W, LWR);
+        mma_item<false, false, 4, NXR, true>(lane, NXR, NX1R + nu, 0, 1.0, Pc, NXR, warp, ABk, NXR, tb, 3, W, LWR);
+      }
+      named_sync(2, 32 * GEMM_WARPS);   // W is complete (the helper warp is not part of this barrier)
+      WB_TICK(7, 0)
+      mbar_wait(barQ, parityQ);         // [Q | q] of this stage has landed in Pn
       const signed char* sched = nu > 0 ? kP2Sched[warp] : kP2SchedNoInput[warp];
       for (int j = 0; j < 4; ++j) {
         const int it = sched[j];
@@ -345,10 +360,13 @@ __global__ void __launch_bounds__(BWD_THREADS, 1) riccati_bwd_kernel(QpDeviceVie
         }
       }
     }
+    parityQ ^= 1;
     WB_TICK(8, 0)
     __syncthreads();
     WB_TICK(3, 0)
     WB_TICK(25, 256)
+    // [P | p] of the previous stage is dead now: its buffer takes [Q | q] of stage k-1 (needed at P2 of the next stage)
+    if (!gemmWarp && k > 0) prefetchQ(k - 1, Pc);
     double* Yl = W;
     double* Kout = W + KOUT_OFF;
     if (nu > 0) {

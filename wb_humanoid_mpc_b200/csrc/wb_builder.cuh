@@ -462,7 +462,20 @@ HD void bldNode(const WbDev& d, const BldDev& b, int k, int i, int tid, int nt) 
   }
 }
 
+// Perfect-tracking closed loop (the dummy simulation of the reference's launch files, WBMpcRobotSim.cpp: the next measured state is the planned
+// one): x0 = the previous primal solution interpolated at the new initial time, on the device.
+HD void bldX0FromPrevious(const WbDev& d, const BldDev& b, int i, int tid, int nt) {
+  const int pn = b.prevN + 1;
+  const double* pT = b.prevT + static_cast<size_t>(i) * pn;
+  const double* pX = b.prevX + static_cast<size_t>(i) * pn * NX;
+  int idx;
+  double alpha;
+  bldInterpIndex(pT, pn, b.t0, idx, alpha);
+  for (int j = tid; j < NX; j += nt) d.x0[static_cast<size_t>(i) * NX + j] = alpha * pX[static_cast<size_t>(idx) * NX + j] + (1.0 - alpha) * pX[static_cast<size_t>(idx + 1) * NX + j];
+}
+
 #ifdef __CUDACC__
+__global__ void builder_x0_kernel(WbDev d, BldDev b) { bldX0FromPrevious(d, b, blockIdx.x, threadIdx.x, blockDim.x); }
 __global__ void builder_grid_kernel(WbDev d, BldDev b) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < d.B) bldGridInstance(d, b, i);

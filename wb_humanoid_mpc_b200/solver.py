@@ -137,19 +137,23 @@ class B200SqpSolver:
     def build_instances(self, t0: float, horizon: float, x0, gaits, gait_start, cmd, warm: bool = False) -> int:
         """Device-side instance builder (b200sqp_build_instances): one synchronous MPC cycle of len(x0) instances over [t0, t0 + horizon] from
         x0 [B, nx], gait names (or ids) [B], gait start times [B] and velocity commands [B, 4]; warm = shift the iterate left on the device by
-        the previous solve.  Returns the common number of shooting nodes."""
+        the previous solve; x0 = None (with warm): the planned state at t0 is the measured state (closed loop on the device).  Returns the common
+        number of shooting nodes."""
         L = _l.lib()
         if not getattr(self, "_builder_set", False):
             self._bdesc, self._gait_names = abi.builder_desc(self.model)
             _l.check(L.b200sqp_set_builder(self._h, C.byref(self._bdesc)))
             self._builder_set = True
-        x0 = _f(x0)
-        B = x0.shape[0]
+        if x0 is None:
+            B = len(gaits)
+        else:
+            x0 = _f(x0)
+            B = x0.shape[0]
         gid = np.ascontiguousarray([g if isinstance(g, (int, np.integer)) else self._gait_names.index(g) for g in gaits], dtype=np.int32)
         gs, cm = _f(gait_start), _f(cmd)
         assert gid.shape == (B,) and gs.shape == (B,) and cm.shape == (B, 4)
         n = C.c_int32()
-        _l.check(L.b200sqp_build_instances(self._h, C.c_int(B), C.c_double(t0), C.c_double(horizon), _p(x0), gid.ctypes.data_as(_l.ip), _p(gs), _p(cm),
+        _l.check(L.b200sqp_build_instances(self._h, C.c_int(B), C.c_double(t0), C.c_double(horizon), None if x0 is None else _p(x0), gid.ctypes.data_as(_l.ip), _p(gs), _p(cm),
                                            C.c_int(int(warm)), C.byref(n)))
         self.batch, self.n_nodes = B, n.value
         return n.value
