@@ -146,10 +146,16 @@ void b200sqp_host_free(void* p);
  * (device-to-device restore, no host traffic). */
 int b200sqp_reset(b200sqp_handle h);
 
-/* SqpSolver::runImpl for every instance.  All kernels are enqueued on `stream` (NULL = the legacy default stream); the call returns when the
- * last of them has finished: the filter line search reads the number of pending instances after every trial, like the reference's
- * synchronous runImpl.  Several handles driven from several host threads overlap on the device (b200sqp_own_stream). */
+/* SqpSolver::runImpl for every instance, ASYNCHRONOUS on `stream` (NULL = the legacy default stream): every kernel of up to sqp_iteration SQP
+ * iterations is enqueued and the call returns; nothing on the host waits for the device.  The filter line search needs no host decision: an
+ * instance needs at most ceil(log(alpha_min) / log(alpha_decay)) + 1 trials, all of them are enqueued, and the thread blocks of an instance
+ * whose search has ended return at their first instruction (likewise every kernel for a converged instance).  b200sqp_wait -- or any entry
+ * point that reads results or re-uses the handle (download*, get_stage_times, reset, upload / build_instances, set_batch, destroy) -- waits for
+ * the stream first.  One solve per handle in flight; several handles on several streams overlap on the device.  (The global-step mode takes a
+ * host decision per candidate step and returns when the solve has finished.) */
 int b200sqp_solve(b200sqp_handle h, void* stream);
+/* Blocks until the last b200sqp_solve of this handle has finished; reports CUDA errors of the asynchronous work. */
+int b200sqp_wait(b200sqp_handle h);
 
 /* A non-blocking CUDA stream owned by the handle, for callers without CUDA headers: b200sqp_solve(h, stream) on it lets several handles
  * (e.g. two b200sqp::host::SqpSolver objects double-buffering a workload) overlap on the device instead of serialising on the legacy

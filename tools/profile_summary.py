@@ -50,9 +50,13 @@ WANT = ["gpu__time_duration.sum", "launch__grid_size", "launch__block_size", "la
         "smsp__average_warps_issue_stalled_math_pipe_throttle_per_issue_active.ratio", "smsp__average_warps_issue_stalled_mio_throttle_per_issue_active.ratio"]
 for short, name in kernels:
     rep = GO / f"prof_{short}_{tag}.ncu-rep"
-    if not rep.exists():
+    rawcsv = GO / f"ncuraw_{short}_{tag}.csv"   # `ncu -i <rep> --page raw --csv` run on the GPU box (the .ncu-rep files are too big to bring back)
+    if rawcsv.exists():
+        raw = rawcsv.read_text()
+    elif rep.exists():
+        raw = subprocess.run(["ncu", "-i", str(rep), "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    else:
         continue
-    raw = subprocess.run(["ncu", "-i", str(rep), "--page", "raw", "--csv"], capture_output=True, text=True).stdout
     rows = list(csv.reader(raw.splitlines()))
     h, units, v = rows[0], rows[1], rows[-1]
     out += [f"## {name}  (`ncu --set full`, {FULL_NOTE})", "", "| metric | unit | value |", "|---|---|---|"]
@@ -74,6 +78,7 @@ for short, name in kernels:
     if "gpu__time_duration.sum" in h:
         i = h.index("gpu__time_duration.sum")
         rawd["gpu_time_ms"] = float(v[i].replace(",", "")) * tmult.get(units[i], 1.0)
+    rawd["batch"] = int(os.environ.get("PROFILE_BATCH", "64"))   # instances per GPU of the captured launch (bench.py scales `traffic` by it)
     (PR / f"ncu_{short}_{tag}_raw.json").write_text(json.dumps(rawd, indent=0))
 bench = GO / f"bench_{tag}.json"
 if bench.exists():

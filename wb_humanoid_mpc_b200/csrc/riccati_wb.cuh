@@ -190,6 +190,10 @@ __constant__ SymItem kSymItems[13] = {
 // warp, which runs the latency-bound factorisation during this phase, and get little work.
 __constant__ signed char kP2Sched[8][4] = {{7, 11, -1, -1}, {0, 13, -1, -1}, {1, 14, -1, -1}, {2, 15, -1, -1},
                                            {18, -1, -1, -1}, {3, 16, 8, -1}, {4, 17, 9, -1},  {5, 6, 10, 12}};
+// the rest of W (item = 2 * row strip + {0: column tiles 0-3, 1: column tiles 4-6}) over the six worker warps
+__constant__ signed char kP1bItems[6][3] = {{0, 1, 15}, {2, 3, -1}, {4, 5, -1}, {6, 7, 8}, {9, 10, 11}, {12, 13, 14}};
+// P2 item order for the six worker warps (round robin): the fourteen 4-tile items first, the five short ones last
+__constant__ signed char kP2Order[19] = {0, 1, 2, 3, 4, 5, 6, 7, 13, 14, 15, 16, 17, 18, 8, 9, 10, 11, 12};
 // stages without inputs (event nodes): only the 13 symmetric items
 __constant__ signed char kP2SchedNoInput[8][4] = {{0, 8, -1, -1}, {1, 9, -1, -1}, {2, 10, -1, -1}, {3, 11, -1, -1},
                                                   {4, 12, -1, -1}, {5, -1, -1, -1}, {6, -1, -1, -1}, {7, -1, -1, -1}};
@@ -330,31 +334,41 @@ __global__ void __launch_bounds__(BWD_THREADS, 1) riccati_bwd_kernel(QpDeviceVie
       }
       if (k > 0) prefetchSmall(k - 1, 1 - set);
       WB_TICK(27, 256)
-    } else {
-      if (nu > 0 && warp >= 1 && warp <= 3) {   // R~ = R + B'W_B
+    } else if ((warp & 3) != 0) {
+      // worker warps 1,2,3,5,6,7: the warps 0 and 4 share their scheduler (and its fp64 / shuffle issue slots) with the helper warp and sit this
+      // phase out while it factorises
+      const int wk = warp - 1 - (warp > 4);   // 0..5
+      if (nu > 0 && warp <= 3) {   // R~ = R + B'W_B
         const int tn[3] = {0, 1, 2};
         mma_item<true, true, 3, NXR>(lane, nu, nu, 0, 1.0, Bk, NXR, warp - 1, W + LWR * NX1R, LWR, tn, 3, Rk, LMR);
         __threadfence_block();
         named_arrive(1, 128);
       }
-      {   // the rest of W: column tiles 0..6 of row strip `warp`
-        const int ta[4] = {0, 1, 2, 3}, tb[4] = {4, 5, 6, 0};
-        mma_item<false, false, 4, NXR, true>(lane, NXR, NX1R + nu, 0, 1.0, Pc, NXR, warp, ABk, NXR, ta, 4, W, LWR);
-        mma_item<false, false, 4, NXR, true>(lane, NXR, NX1R + nu, 0, 1.0, Pc, NXR, warp, ABk, NXR, tb, 3, W, LWR);
-      }
-      named_sync(2, 32 * GEMM_WARPS);   // W is complete (the helper warp is not part of this barrier)
-      WB_TICK(7, 0)
-      mbar_wait(barQ, parityQ);         // [Q | q] of this stage has landed in Pn
-      const signed char* sched = nu > 0 ? kP2Sched[warp] : kP2SchedNoInput[warp];
-      for (int j = 0; j < 4; ++j) {
-        const int it = sched[j];
+      // the rest of W: column tiles 0..6 of the eight row strips, 16 items over the six workers (the three that formed R~ take two each)
+      for (int j = 0; j < 3; ++j) {
+        const int it = kP1bItems[wk][j];
         if (it < 0) break;
-        if (it < 13) {
-          const SymItem s = kSymItems[it];
+        const int strip = it >> 1;
+        if (it & 1) {
+          const int tb[4] = {4, 5, 6, 0};
+          mma_item<false, false, 4, NXR, true>(lane, NXR, NX1R + nu, 0, 1.0, Pc, NXR, strip, ABk, NXR, tb, 3, W, LWR);
+        } else {
+          const int ta[4] = {0, 1, 2, 3};
+          mma_item<false, false, 4, NXR, true>(lane, NXR, NX1R + nu, 0, 1.0, Pc, NXR, strip, ABk, NXR, ta, 4, W, LWR);
+        }
+      }
+      named_sync(2, 32 * 6);   // W is complete (barrier of the six workers)
+      WB_TICK(7, 32)
+      mbar_wait(barQ, parityQ);         // [Q | q] of this stage has landed in Pn
+      const int nItems = nu > 0 ? 19 : 13;
+      for (int it = wk; it < nItems; it += 6) {
+        const int id = nu > 0 ? kP2Order[it] : it;
+        if (id < 13) {
+          const SymItem s = kSymItems[id];
           const int tn[4] = {s.n[0], s.n[1], s.n[2], s.n[3]};
           mma_item<true, true, 4, NXR>(lane, NXR, NX1R, 0, 1.0, ABk, NXR, s.m, W, LWR, tn, s.cnt, Pn, NXR);
         } else {
-          const int tm = (it - 13) >> 1, g = ((it - 13) & 1) * 4;
+          const int tm = (id - 13) >> 1, g = ((id - 13) & 1) * 4;
           const int tn[4] = {g, g + 1, g + 2, g + 3};
           mma_item<true, true, 4, NXR>(lane, nu, NX1R, 0, 1.0, Bk, NXR, tm, W, LWR, tn, 4, Yk, NMR);
         }

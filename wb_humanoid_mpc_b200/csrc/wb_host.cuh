@@ -51,6 +51,7 @@ inline const char* makeDeviceModel(const b200sqp_model_desc& d, WbDeviceModel& m
     m.qhi[j] = d.q_upper[j];
   }
   for (int f = 0; f < NFRAMES; ++f) {
+    if (d.frame_body[f] < 0 || d.frame_body[f] >= NB) return "frame_body[] entry is not a body index";
     m.frameBody[f] = d.frame_body[f];
     for (int k = 0; k < 3; ++k) m.frameP[f][k] = d.frame_p[f][k];
   }
@@ -92,7 +93,10 @@ inline const char* makeDeviceModel(const b200sqp_model_desc& d, WbDeviceModel& m
   m.collDelta = d.coll_delta;
   m.rFoot = d.coll_r_foot;
   m.rKnee = d.coll_r_knee;
-  for (int k = 0; k < 4; ++k) m.armJoint[k] = d.arm_swing_joint[k];
+  for (int k = 0; k < 4; ++k) {
+    if (d.arm_swing_joint[k] < 0 || d.arm_swing_joint[k] >= NJ) return "arm_swing_joint[] entry is not a joint index";
+    m.armJoint[k] = d.arm_swing_joint[k];
+  }
   return nullptr;
 }
 

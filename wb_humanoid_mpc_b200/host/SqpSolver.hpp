@@ -85,6 +85,7 @@ class SqpSolver {
     if (static_cast<int>(initStates.size()) != batch_) throw std::invalid_argument("[b200sqp::host::SqpSolver] run: one initial state per instance");
     std::vector<Instance> inst(batch_);
     bench_ = Benchmarks();
+    failedInstances_.clear();
     const auto tPre = now();
     parallelFor(batch_, [&](int b) {
       rm_[b].preSolverRun(initTime, finalTime);
@@ -288,7 +289,10 @@ class SqpSolver {
     const int iters = settings_.sqp_iteration;
     std::vector<b200sqp_iter_log> log(static_cast<size_t>(Bg) * iters);
     std::vector<int32_t> nIter(Bg), status(Bg);
-    check(b200sqp_download(G.h, x, u, nullptr, log.data(), nIter.data(), status.data()));
+    // a failed QP of some instances (B200SQP_EQP) is a partial success: the arrays of every instance have been downloaded; the good ones are
+    // unpacked below (their warm starts stay valid), the failed ones keep their previous primal solution, and the call throws afterwards
+    const int rcDownload = b200sqp_download(G.h, x, u, nullptr, log.data(), nIter.data(), status.data());
+    if (rcDownload != 0 && rcDownload != B200SQP_EQP) check(rcDownload);
     if (settings_.create_value_function) {
       G.P.resize(static_cast<size_t>(Bg) * n * nx * nx);
       G.p.resize(static_cast<size_t>(Bg) * n * nx);
@@ -302,11 +306,12 @@ class SqpSolver {
     local.solveQp = ms[1];
     local.linesearch = ms[2];
     local.projectionShareOfLq = ms[3];
-    for (int s = 0; s < Bg; ++s)
-      if (status[s] != 0) throw std::runtime_error("[SqpSolver] Failed to solve QP");  // SqpSolver.cpp:306-308
+    int nFailed = 0;
+    for (int s = 0; s < Bg; ++s) nFailed += status[s] != 0;
     const int gid = nNodes;
     parallelFor(Bg, [&](int s) {
       const int b = members[s];
+      if (status[s] != 0) return;   // keeps primal_[b] / log_[b] of its last successful solve
       groupOf_[b] = gid;
       slotOf_[b] = s;
       primal_[b] = toPrimalSolution(inst[b], x + static_cast<size_t>(s) * n * nx, u + static_cast<size_t>(s) * (n - 1) * nu, nx, nu);
@@ -336,7 +341,22 @@ class SqpSolver {
     bench_.solveQp += local.solveQp;
     bench_.linesearch += local.linesearch;
     bench_.projectionShareOfLq += local.projectionShareOfLq;
+    if (nFailed > 0) {   // SqpSolver.cpp:306-308 throws per solver; here after the other instances of the batch have been kept
+      {
+        std::lock_guard<std::mutex> lf(benchMutex_);
+        for (int s = 0; s < Bg; ++s)
+          if (status[s] != 0) failedInstances_.push_back(members[s]);
+      }
+      throw std::runtime_error("[SqpSolver] Failed to solve QP for " + std::to_string(nFailed) + " of " + std::to_string(Bg) + " instances");
+    }
   }
+
+ public:
+  /** instances whose QP failed in the last run() (their primal solution is the one of their last successful solve) */
+  const std::vector<int>& failedInstances() const { return failedInstances_; }
+
+ private:
+  std::vector<int> failedInstances_;
 
   static std::mutex& deviceToken(int device) {
     static std::mutex tokens[16];

@@ -123,6 +123,7 @@ EXPORTED_SYMBOLS = [
     "b200sqp_host_free",
     "b200sqp_reset",
     "b200sqp_solve",
+    "b200sqp_wait",
     "b200sqp_own_stream",
     "b200sqp_set_builder",
     "b200sqp_build_instances",

@@ -174,8 +174,15 @@ class B200SqpSolver:
         """SqpSolver::reset(): restore the uploaded initial guess on the device"""
         _l.check(_l.lib().b200sqp_reset(self._h))
 
-    def solve(self, stream=None):
+    def solve(self, stream=None, wait: bool = True):
+        """b200sqp_solve enqueues the whole solve and returns; wait = True (default) then blocks in b200sqp_wait like the reference's synchronous
+        run(); wait = False leaves the work in flight (call wait() or read results later)"""
         _l.check(_l.lib().b200sqp_solve(self._h, C.c_void_p(stream or 0)))
+        if wait:
+            self.wait()
+
+    def wait(self):
+        _l.check(_l.lib().b200sqp_wait(self._h))
 
     def run(self, instances):
         batch = stack_instances(instances) if isinstance(instances, list) else instances
@@ -184,8 +191,10 @@ class B200SqpSolver:
         return self.primal_solution()
 
     # -- results -------------------------------------------------------------------------------------------------------------
-    def primal_solution(self, with_gains: bool | None = None, out: dict | None = None):
-        """out = {"x": [B, n, nx], "u": [B, n-1, nu]} lets the caller supply (page-locked) destination arrays for the download"""
+    def primal_solution(self, with_gains: bool | None = None, out: dict | None = None, raise_on_failure: bool = True):
+        """out = {"x": [B, n, nx], "u": [B, n-1, nu]} lets the caller supply (page-locked) destination arrays for the download.
+        A failed QP of some instance raises like the reference (SqpSolver.cpp:306-308) unless raise_on_failure = False, in which case the dict
+        is returned with the per-instance `status` array (the arrays of the other instances are valid either way)."""
         B, n, nx, nu = self.batch, self.n_nodes, self.nx, self.nu
         if out is not None:
             x, u = out["x"], out["u"]
@@ -196,8 +205,10 @@ class B200SqpSolver:
         K = np.zeros((B, n - 1, nx, nu)) if with_gains else None
         log = (abi.IterLog * (B * self.settings.sqp_iteration))()
         n_iter, status = np.zeros(B, dtype=np.int32), np.zeros(B, dtype=np.int32)
-        _l.check(_l.lib().b200sqp_download(self._h, _p(x), _p(u), None if K is None else _p(K), log, n_iter.ctypes.data_as(_l.ip),
-                                           status.ctypes.data_as(_l.ip)))
+        rc = _l.lib().b200sqp_download(self._h, _p(x), _p(u), None if K is None else _p(K), log, n_iter.ctypes.data_as(_l.ip),
+                                       status.ctypes.data_as(_l.ip))
+        if rc != 0 and (raise_on_failure or rc != -4):   # -4 = B200SQP_EQP: every array has been filled, status says which instances failed
+            _l.check(rc)
         logs = np.frombuffer(log, dtype=np.float64).reshape(B, self.settings.sqp_iteration, 16).copy()
         out = dict(x=x, u=u, n_iter=n_iter, status=status, log=logs)
         if K is not None:
