@@ -219,3 +219,41 @@ def test_example_application_compiles_links_and_fails_loudly_without_a_gpu(tmp_p
     if not torch.cuda.is_available():
         run = subprocess.run([str(exe), str(pkg / "data" / "g1_wb_model.txt"), "2"], capture_output=True, text=True, cwd=tmp_path)
         assert run.returncode == 1 and "no CPU fallback" in run.stderr
+
+
+# ---- mpc_flattened_controller packing (MPC_ROS_Interface.cpp:98-178) -----------------------------------------------------------------
+@pytest.mark.parametrize("linear", [False, True])
+def test_policy_message_packing_round_trip(model, linear):
+    """createMpcPolicyMsg restated on plain structs: the feed-forward policy packs the inputs, the linear one [uff_i, K_i,:] per input with
+    uff = u - K x; unflattening a sample and evaluating it at its own state gives the planned input back (float32 wire precision)"""
+    import ctypes as C
+
+    rng = np.random.default_rng(8)
+    inst = references.build_instance(model, np.array(model["x_init"], float), t0=0.0, horizon=1.1, gait="walk")
+    n, nx, nu = len(inst["t_nodes"]), 58, 35
+    x, u = rng.normal(size=(n, nx)), rng.normal(size=(n - 1, nu))
+    K = rng.normal(size=(n - 1, nx, nu)) * 0.1 if linear else None     # column-major (nu x nx) per stage = [n-1][nx][nu] in C order
+    L = host_lib.lib()
+    stride = nu * (1 + nx) if linear else nu
+    data = np.zeros((n, stride), dtype=np.float32)
+    post = np.zeros(n, dtype=np.uint16)
+    n_post = C.c_int(0)
+    probe = 7
+    u_probe = np.zeros(nu)
+    dp, u8p = C.POINTER(C.c_double), C.POINTER(C.c_uint8)
+    ev = np.ascontiguousarray(inst["node_event"], dtype=np.uint8)
+    tt = np.ascontiguousarray(inst["t_nodes"], dtype=np.float64)
+    L.b200host_policy_msg.restype = C.c_int
+    rc = L.b200host_policy_msg(n, nx, nu, tt.ctypes.data_as(dp), ev.ctypes.data_as(u8p), x.ctypes.data_as(dp), u.ctypes.data_as(dp),
+                               None if K is None else K.ctypes.data_as(dp), data.ctypes.data_as(C.POINTER(C.c_float)), data.size,
+                               post.ctypes.data_as(C.POINTER(C.c_uint16)), C.byref(n_post), probe, x[probe].ctypes.data_as(dp), u_probe.ctypes.data_as(dp))
+    assert rc == stride, host_lib.lib().b200host_last_error()
+    prim = references.to_primal_solution(inst["t_nodes"], inst["node_event"], x, u)
+    assert list(post[: n_post.value]) == [i for i in range(n) if inst["node_event"][i] == 2]
+    if not linear:
+        assert np.allclose(data, np.asarray(prim["u"], dtype=np.float32))
+    else:
+        Kk = K[probe].T                                  # nu x nx
+        assert np.allclose(data[probe].reshape(nu, 1 + nx)[:, 1:], Kk.astype(np.float32))
+        assert np.allclose(data[probe].reshape(nu, 1 + nx)[:, 0], (prim["u"][probe] - Kk @ x[probe]).astype(np.float32), atol=1e-5)
+    assert np.allclose(u_probe, prim["u"][probe], atol=2e-4)   # u = uff + K x at the sample's own state

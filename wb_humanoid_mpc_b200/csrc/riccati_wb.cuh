@@ -95,25 +95,33 @@ __device__ __forceinline__ void named_sync(int id, int count) { asm volatile("ba
 // NG is a compile-time count (mma_item dispatches on the number of tiles) so that the unrolled DMMA stream carries no per-tile branches.
 // SYM_A (only with !TRANS_A, M = K): A is symmetric and only its lower triangle is valid: element (m, k) is read from (max, min).
 // vadd != nullptr: column vcol of the result additionally gets the vector vadd (W_b = P b + p without a separate pass).
-template <bool TRANS_A, bool ACC, int NG, int KC, bool SYM_A>
+// PERM_A / PERM_B: the operand has leading dimension 58 with the contraction index running fastest (A' stored K x M, or B): lane group fr then
+// takes row / column perm8(fr) = (0, 2, 4, 6, 1, 3, 5, 7)[fr] of the tile instead of fr.  A half-warp's fragment load touches the doubles
+// {k + 58 n : k = 0..3, n = four rows / columns}: with n = 0, 1, 2, 3 the bank offsets 10 n (mod 16) = 0, 10, 4, 14 make the 4-wide runs of
+// n = 0 and n = 3 collide (a two-way conflict on every load); with n = 0, 2, 4, 6 (and 1, 3, 5, 7 in the other half-warp) they are 0, 4, 8, 12:
+// conflict free.  Which tile row a lane group feeds is arbitrary as long as the result is stored accordingly, which the epilogue does.
+__device__ __forceinline__ int perm8(int j) { return j < 4 ? 2 * j : 2 * (j - 4) + 1; }
+template <bool TRANS_A, bool ACC, int NG, int KC, bool SYM_A, bool PERM_A, bool PERM_B>
 __device__ __forceinline__ void mma_item_ng(int lane, int M, int N, int Krt, double alpha, const double* __restrict__ A, int lda, int tm,
                                             const double* __restrict__ B, int ldb, const int* tn, double* __restrict__ C, int ldc,
                                             const double* __restrict__ vadd, int vcol) {
   const int K = KC ? KC : Krt;
   const int fr = lane >> 2, fk = lane & 3;
   const int Kmain = K & ~3;
-  const int ar = (tm << 3) + fr;
+  const int ar = (tm << 3) + (PERM_A ? perm8(fr) : fr);
   const bool arok = ar < M;
   const int arc = arok ? ar : 0;
   const double* Ap = TRANS_A ? A + fk + arc * lda : A + arc + fk * lda;
   const double* ApU = A + fk + arc * lda;   // SYM_A: the mirrored element (k, m)
   const int astep = TRANS_A ? 4 : 4 * lda;
+  const int frB = PERM_B ? perm8(fr) : fr;
+  const int cj0 = PERM_B ? perm8(2 * fk) : 2 * fk, cj1 = PERM_B ? perm8(2 * fk + 1) : 2 * fk + 1;   // tile columns of this lane's two results
   const double* Bp[NG];
   bool bok[NG];
   double c0[NG], c1[NG];
 #pragma unroll
   for (int g = 0; g < NG; ++g) {
-    const int bn = (tn[g] << 3) + fr;
+    const int bn = (tn[g] << 3) + frB;
     bok[g] = bn < N;
     Bp[g] = B + fk + (bok[g] ? bn : 0) * ldb;
     c0[g] = c1[g] = 0.0;
@@ -150,31 +158,31 @@ __device__ __forceinline__ void mma_item_ng(int lane, int M, int N, int Krt, dou
   if (arok) {
 #pragma unroll
     for (int g = 0; g < NG; ++g) {
-      const int cn = (tn[g] << 3) + 2 * fk;
-      if (cn < N) {
-        double* c = &C[ar + cn * ldc];
+      const int cn0 = (tn[g] << 3) + cj0, cn1 = (tn[g] << 3) + cj1;
+      if (cn0 < N) {
+        double* c = &C[ar + cn0 * ldc];
         double r = ACC ? fma(alpha, c0[g], *c) : alpha * c0[g];
-        if (vadd && cn == vcol) r += vadd[ar];
+        if (vadd && cn0 == vcol) r += vadd[ar];
         *c = r;
       }
-      if (cn + 1 < N) {
-        double* c = &C[ar + (cn + 1) * ldc];
+      if (cn1 < N) {
+        double* c = &C[ar + cn1 * ldc];
         double r = ACC ? fma(alpha, c1[g], *c) : alpha * c1[g];
-        if (vadd && cn + 1 == vcol) r += vadd[ar];
+        if (vadd && cn1 == vcol) r += vadd[ar];
         *c = r;
       }
     }
   }
 }
-template <bool TRANS_A, bool ACC, int NG, int KC, bool SYM_A = false>
+template <bool TRANS_A, bool ACC, int NG, int KC, bool SYM_A = false, bool PERM_A = false, bool PERM_B = false>
 __device__ __forceinline__ void mma_item(int lane, int M, int N, int Krt, double alpha, const double* __restrict__ A, int lda, int tm,
                                          const double* __restrict__ B, int ldb, const int (&tn)[NG], int cnt, double* __restrict__ C, int ldc,
                                          const double* __restrict__ vadd = nullptr, int vcol = -1) {
   // (warp-uniform dispatch; NG bounds the tile count)
-  if (NG >= 4 && cnt == 4) mma_item_ng<TRANS_A, ACC, (NG >= 4 ? 4 : NG), KC, SYM_A>(lane, M, N, Krt, alpha, A, lda, tm, B, ldb, tn, C, ldc, vadd, vcol);
-  else if (NG >= 3 && cnt == 3) mma_item_ng<TRANS_A, ACC, (NG >= 3 ? 3 : NG), KC, SYM_A>(lane, M, N, Krt, alpha, A, lda, tm, B, ldb, tn, C, ldc, vadd, vcol);
-  else if (NG >= 2 && cnt == 2) mma_item_ng<TRANS_A, ACC, (NG >= 2 ? 2 : NG), KC, SYM_A>(lane, M, N, Krt, alpha, A, lda, tm, B, ldb, tn, C, ldc, vadd, vcol);
-  else if (cnt == 1) mma_item_ng<TRANS_A, ACC, 1, KC, SYM_A>(lane, M, N, Krt, alpha, A, lda, tm, B, ldb, tn, C, ldc, vadd, vcol);
+  if (NG >= 4 && cnt == 4) mma_item_ng<TRANS_A, ACC, (NG >= 4 ? 4 : NG), KC, SYM_A, PERM_A, PERM_B>(lane, M, N, Krt, alpha, A, lda, tm, B, ldb, tn, C, ldc, vadd, vcol);
+  else if (NG >= 3 && cnt == 3) mma_item_ng<TRANS_A, ACC, (NG >= 3 ? 3 : NG), KC, SYM_A, PERM_A, PERM_B>(lane, M, N, Krt, alpha, A, lda, tm, B, ldb, tn, C, ldc, vadd, vcol);
+  else if (NG >= 2 && cnt == 2) mma_item_ng<TRANS_A, ACC, (NG >= 2 ? 2 : NG), KC, SYM_A, PERM_A, PERM_B>(lane, M, N, Krt, alpha, A, lda, tm, B, ldb, tn, C, ldc, vadd, vcol);
+  else if (cnt == 1) mma_item_ng<TRANS_A, ACC, 1, KC, SYM_A, PERM_A, PERM_B>(lane, M, N, Krt, alpha, A, lda, tm, B, ldb, tn, C, ldc, vadd, vcol);
 }
 
 // Work items of a symmetric 58 x 59 update (the [P | p] shape): row strip m needs the column tiles 0..m of the lower triangle plus tile 7,
@@ -314,7 +322,7 @@ __global__ void __launch_bounds__(BWD_THREADS, 1) riccati_bwd_kernel(QpDeviceVie
     // ---- P1a: the columns of W = P [A | b | B] that R~ needs first: column tiles 7.. = [A_56 A_57 | b | B] (column b additionally gets p) --------
     if (gemmWarp) {
       const int tn[4] = {7, 8, 9, 10};
-      mma_item<false, false, 4, NXR, true>(lane, NXR, NX1R + nu, 0, 1.0, Pc, NXR, warp, ABk, NXR, tn, tilesN - 7, W, LWR, Pc + NXR * NXR, NXR);
+      mma_item<false, false, 4, NXR, true, false, true>(lane, NXR, NX1R + nu, 0, 1.0, Pc, NXR, warp, ABk, NXR, tn, tilesN - 7, W, LWR, Pc + NXR * NXR, NXR);
     } else if (v.keepP && k < N - 1) {
       storeP(Pc, k + 1, lane, 32);   // (the cost-to-go of stage k+1 is complete and read-only until the [Q | q] copy below)
     }
@@ -340,7 +348,7 @@ __global__ void __launch_bounds__(BWD_THREADS, 1) riccati_bwd_kernel(QpDeviceVie
       const int wk = warp - 1 - (warp > 4);   // 0..5
       if (nu > 0 && warp <= 3) {   // R~ = R + B'W_B
         const int tn[3] = {0, 1, 2};
-        mma_item<true, true, 3, NXR>(lane, nu, nu, 0, 1.0, Bk, NXR, warp - 1, W + LWR * NX1R, LWR, tn, 3, Rk, LMR);
+        mma_item<true, true, 3, NXR, false, true, false>(lane, nu, nu, 0, 1.0, Bk, NXR, warp - 1, W + LWR * NX1R, LWR, tn, 3, Rk, LMR);
         __threadfence_block();
         named_arrive(1, 128);
       }
@@ -351,10 +359,10 @@ __global__ void __launch_bounds__(BWD_THREADS, 1) riccati_bwd_kernel(QpDeviceVie
         const int strip = it >> 1;
         if (it & 1) {
           const int tb[4] = {4, 5, 6, 0};
-          mma_item<false, false, 4, NXR, true>(lane, NXR, NX1R + nu, 0, 1.0, Pc, NXR, strip, ABk, NXR, tb, 3, W, LWR);
+          mma_item<false, false, 4, NXR, true, false, true>(lane, NXR, NX1R + nu, 0, 1.0, Pc, NXR, strip, ABk, NXR, tb, 3, W, LWR);
         } else {
           const int ta[4] = {0, 1, 2, 3};
-          mma_item<false, false, 4, NXR, true>(lane, NXR, NX1R + nu, 0, 1.0, Pc, NXR, strip, ABk, NXR, ta, 4, W, LWR);
+          mma_item<false, false, 4, NXR, true, false, true>(lane, NXR, NX1R + nu, 0, 1.0, Pc, NXR, strip, ABk, NXR, ta, 4, W, LWR);
         }
       }
       named_sync(2, 32 * 6);   // W is complete (barrier of the six workers)
@@ -366,11 +374,11 @@ __global__ void __launch_bounds__(BWD_THREADS, 1) riccati_bwd_kernel(QpDeviceVie
         if (id < 13) {
           const SymItem s = kSymItems[id];
           const int tn[4] = {s.n[0], s.n[1], s.n[2], s.n[3]};
-          mma_item<true, true, 4, NXR>(lane, NXR, NX1R, 0, 1.0, ABk, NXR, s.m, W, LWR, tn, s.cnt, Pn, NXR);
+          mma_item<true, true, 4, NXR, false, true, false>(lane, NXR, NX1R, 0, 1.0, ABk, NXR, s.m, W, LWR, tn, s.cnt, Pn, NXR);
         } else {
           const int tm = (id - 13) >> 1, g = ((id - 13) & 1) * 4;
           const int tn[4] = {g, g + 1, g + 2, g + 3};
-          mma_item<true, true, 4, NXR>(lane, nu, NX1R, 0, 1.0, Bk, NXR, tm, W, LWR, tn, 4, Yk, NMR);
+          mma_item<true, true, 4, NXR, false, true, false>(lane, nu, NX1R, 0, 1.0, Bk, NXR, tm, W, LWR, tn, 4, Yk, NMR);
         }
       }
     }

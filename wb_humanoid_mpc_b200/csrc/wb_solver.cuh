@@ -371,16 +371,8 @@ __global__ void __launch_bounds__(128) prep_kernel(WbDev d, int mode) {
 
 // K3.  RO_PACK shooting nodes per CTA (see RO_PACK above): every PHASE body is instantiated once per node on a slice of the threads rotated by
 // 64 lanes; the nodes of a CTA share the barriers.
-__global__ void __launch_bounds__(RO_THREADS) rollout_kernel(WbDev d) {
-  extern __shared__ double smem[];
-  const int b = blockIdx.y, k0 = blockIdx.x * RO_PACK;
-  if (d.flags[b * F_NF + F_CONVERGED] || d.flags[b * F_NF + F_LSDONE]) return;
-  __shared__ WbDeviceModel msh;
-  __shared__ NodeIn nsh[RO_PACK];
+__device__ __forceinline__ void rolloutNodes(const WbDev& d, const WbDeviceModel& m, NodeIn* nsh, double* smem, int b, int k0) {
   const int tid = threadIdx.x;
-  for (int i = tid; i < static_cast<int>(sizeof(WbDeviceModel) / 8); i += blockDim.x)
-    reinterpret_cast<double*>(&msh)[i] = reinterpret_cast<const double*>(d.model)[i];
-  const WbDeviceModel& m = msh;
   const int N = d.N;
   const double alpha = d.inst[b * I_ND + I_ALPHA];
   const size_t roStride = roWsDoubles();
@@ -471,6 +463,27 @@ __global__ void __launch_bounds__(RO_THREADS) rollout_kernel(WbDev d) {
 #undef PHASE
 #undef RO_NODES
 #undef RO_NODE
+}
+
+// One CTA walks the instances b = blockIdx.y, blockIdx.y + gridDim.y, ...: the first trials of the line search are launched with one instance per
+// CTA row; the later ones -- in which almost every instance has finished and its thread blocks would only be launched to return -- with an
+// eighth of the rows (the asynchronous solve enqueues the whole back-tracking ladder, wb_capi.inc).
+__global__ void __launch_bounds__(RO_THREADS) rollout_kernel(WbDev d) {
+  extern __shared__ double smem[];
+  __shared__ WbDeviceModel msh;
+  __shared__ NodeIn nsh[RO_PACK];
+  const int k0 = blockIdx.x * RO_PACK;
+  bool staged = false;
+  for (int b = blockIdx.y; b < d.B; b += gridDim.y) {
+    if (d.flags[b * F_NF + F_CONVERGED] || d.flags[b * F_NF + F_LSDONE]) continue;   // uniform over the CTA
+    if (!staged) {
+      for (int i = threadIdx.x; i < static_cast<int>(sizeof(WbDeviceModel) / 8); i += blockDim.x)
+        reinterpret_cast<double*>(&msh)[i] = reinterpret_cast<const double*>(d.model)[i];
+      staged = true;
+    }
+    rolloutNodes(d, msh, nsh, smem, b, k0);
+    __syncthreads();   // the workspace is reused by the next instance
+  }
 }
 
 // trial PerformanceIndex of one instance at its current alpha (sums over the per-node results of K3) and the filter test

@@ -3,6 +3,7 @@
 #include <cstring>
 #include <string>
 
+#include "MpcPolicyMsg.hpp"
 #include "SqpLogging.hpp"
 #include "SqpSolver.hpp"
 
@@ -103,6 +104,27 @@ int b200host_build_instance(void* model, double t0, const double* x0, double hor
     std::copy(I.x_init.begin(), I.x_init.end(), x_init);
     std::copy(I.u_init.begin(), I.u_init.end(), u_init);
     return n;
+  });
+}
+
+// createMpcPolicyMsg on flat arrays (test entry point): t [n], event [n], x [n][nx], u [n-1][nu], K [n-1][nu*nx] or null -> data [n][stride] (floats),
+// post-event indices; returns the per-sample data length, -1 on error; evaluates the packed policy at sample `probe` for state x_probe into u_probe
+int b200host_policy_msg(int n, int nx, int nu, const double* t, const uint8_t* event, const double* x, const double* u, const double* K, float* data, int data_cap,
+                        uint16_t* post, int* n_post, int probe, const double* x_probe, double* u_probe) {
+  return guarded([&] {
+    Instance inst;
+    inst.t_nodes.assign(t, t + n);
+    inst.node_event.assign(event, event + n);
+    const PrimalSolution p = toPrimalSolution(inst, x, u, nx, nu);
+    const MpcFlattenedController m = createMpcPolicyMsg(p, t[0], vector_t(x, x + nx), K, nx, nu);
+    const int stride = static_cast<int>(m.data.front().size());
+    if (stride * n > data_cap) throw std::runtime_error("policy_msg: data buffer too small");
+    for (int k = 0; k < n; ++k) std::copy(m.data[k].begin(), m.data[k].end(), data + static_cast<size_t>(k) * stride);
+    *n_post = static_cast<int>(m.postEventIndices.size());
+    std::copy(m.postEventIndices.begin(), m.postEventIndices.end(), post);
+    const auto up = evaluatePolicySample(m, static_cast<size_t>(probe), vector_t(x_probe, x_probe + nx));
+    std::copy(up.begin(), up.end(), u_probe);
+    return stride;
   });
 }
 
