@@ -230,7 +230,9 @@ typedef struct b200sqp_iter_log {
 
 /* primalSolution / getRiccatiFeedback / getIterationsLog:
  *   x [B][n_nodes][nx], u [B][n_nodes-1][nu], K [B][n_nodes-1][nu*nx] (remapped gains, may be NULL),
- *   log [B][sqp_iteration], n_iter [B], status [B]. Synchronises. */
+ *   log [B][sqp_iteration], n_iter [B], status [B]: 0 ok; 1 QP failed (Cholesky of the projected input Hessian, NaN); 2 a whole-body
+ *   constraint Jacobian D lost full row rank under Eigen::FullPivLU's threshold (the reference's luConstraintProjection would continue with a
+ *   larger null space; this path reports it).  Any non-zero status makes the call return B200SQP_EQP. Synchronises. */
 int b200sqp_download(b200sqp_handle h, double* x, double* u, double* K, b200sqp_iter_log* log, int32_t* n_iter, int32_t* status);
 
 /* SqpSolver::getValueFunction data (needs settings.create_value_function): quadratic cost-to-go of the last iteration's QP,

@@ -14,8 +14,22 @@
 
 namespace b200sqp {
 
-constexpr int LQA_THREADS = 128;
-constexpr int LQB_THREADS = 256;
+// CTA widths: compile-time, overridable for the occupancy sweeps of tools/dev/variant_sweep.py (every phase loops `for (i = tid; i < n; i += nt)`,
+// so any multiple of 32 gives the same results).
+#ifndef B200SQP_LQA_THREADS
+#define B200SQP_LQA_THREADS 128
+#endif
+#ifndef B200SQP_LQA_CTAS
+#define B200SQP_LQA_CTAS 3
+#endif
+#ifndef B200SQP_LQB_THREADS
+#define B200SQP_LQB_THREADS 256
+#endif
+#ifndef B200SQP_RO_THREADS
+#define B200SQP_RO_THREADS 128
+#endif
+constexpr int LQA_THREADS = B200SQP_LQA_THREADS;
+constexpr int LQB_THREADS = B200SQP_LQB_THREADS;
 // K3 can pack RO_PACK shooting nodes per CTA on thread slices rotated by 64 lanes (the phases are narrow).  Measured on B200 (r2d): three
 // nodes per 192-thread CTA shorten the per-node phase time by 27 % but halve the nodes in flight per SM in practice; 2.6 ms per trial against
 // 1.26 ms for one node per 128-thread CTA, so the shipped configuration is RO_PACK = 1.
@@ -23,12 +37,12 @@ constexpr int LQB_THREADS = 256;
 #define B200SQP_RO_PACK 1
 #endif
 constexpr int RO_PACK = B200SQP_RO_PACK;
-constexpr int RO_THREADS = RO_PACK == 1 ? 128 : 64 * RO_PACK;
+constexpr int RO_THREADS = RO_PACK == 1 ? B200SQP_RO_THREADS : 64 * RO_PACK;
 constexpr double kWeakEps = 1e-9;  // numeric_traits::weakEpsilon (ocs2_core/include/ocs2_core/NumericTraits.h:51)
 
 enum InstD { I_BASE_MERIT = 0, I_BASE_COST, I_BASE_DYN, I_BASE_EQ, I_ARMIJO, I_DXN, I_DUN, I_ALPHA, I_STEP, I_STEPTYPE, I_NEW_MERIT, I_NEW_COST,
              I_NEW_DYN, I_NEW_EQ, I_ND = 16 };
-enum InstF { F_CONVERGED = 0, F_LSDONE, F_ITER, F_STATUS, F_CONVCODE, F_NF = 8 };
+enum InstF { F_CONVERGED = 0, F_LSDONE, F_ITER, F_STATUS, F_CONVCODE, F_RANKDEF, F_NF = 8 };
 
 struct WbDev {
   int B, N;  // N intervals, N+1 nodes
@@ -48,6 +62,8 @@ struct WbDev {
   int* flags;        // [B][F_NF]
   int* pending;      // number of instances whose line search is still running
   double* mid;       // K1a -> K1b records [B][N][Mid::SIZE]
+  double* luRec;     // lu_kernel -> K1b: LU factors of D in position order [B][N][LU_LD * NU]
+  int* luPerm;       // ... and the row / column permutations [B][N][52] (rowOf[16], colOf[36])
   double* gstats;    // global-step mode: per-candidate statistics [32][4]
   double* raw;       // optional [B][N][rawPer]
   long long rawPer;
@@ -195,7 +211,7 @@ __device__ __forceinline__ bool lqTerminalOrEventNode(const WbDev& d, const Node
 }
 
 // K1a: node physics.  Intermediate nodes write their Mid record; terminal and event nodes are finished here.
-__global__ void __launch_bounds__(LQA_THREADS, 3) lq_dyn_kernel(WbDev d) {
+__global__ void __launch_bounds__(LQA_THREADS, B200SQP_LQA_CTAS) lq_dyn_kernel(WbDev d) {
   extern __shared__ double smem[];
   const int k = blockIdx.x, b = blockIdx.y;
   if (d.flags[b * F_NF + F_CONVERGED]) return;
@@ -222,7 +238,37 @@ __global__ void __launch_bounds__(LQA_THREADS, 3) lq_dyn_kernel(WbDev d) {
 #include "wb_node_a.inc"
 }
 
-// K1b: projection + change of input variables of the intermediate nodes, from the Mid records.
+// Complete-pivoting LU of the constraint Jacobian D of every intermediate node (Eigen::FullPivLU semantics, luPhaseFactor), one warp per node.
+// The factorisation is a chain of 12-14 dependent pivot steps (40 k cycles inside K1b, a third of that kernel, with seven warps waiting);
+// as its own kernel 32 nodes are resident per SM and hide each other's latency.
+constexpr int LU_PERM = 52;
+__global__ void __launch_bounds__(32) lu_kernel(WbDev d) {
+  const int k = blockIdx.x, b = blockIdx.y;
+  if (d.flags[b * F_NF + F_CONVERGED]) return;
+  const size_t node = static_cast<size_t>(b) * (d.N + 1) + k, stage = static_cast<size_t>(b) * d.N + k;
+  if (d.event[node] == 1) return;
+  __shared__ double LU[LU_LD * NU];
+  __shared__ int perm[LU_PERM];
+  const double* __restrict__ const mid = d.mid + stage * Mid::SIZE;
+  const int nc = static_cast<int>(mid[Mid::META + 0]);
+  const int lane = threadIdx.x;
+  for (int i = lane; i < NC_MAX * NU; i += 32) LU[(i % NC_MAX) + LU_LD * (i / NC_MAX)] = mid[Mid::CD + NC_MAX * NX + i];
+  for (int i = lane; i < NC_MAX; i += 32) perm[i] = i;
+  for (int i = lane; i < NU; i += 32) perm[16 + i] = i;
+  __syncwarp();
+  luPhaseFactor(Par{lane, 32}, nc, LU, perm, perm + 16);
+  __syncwarp();
+  // Eigen::FullPivLU's rank test (threshold eps * min(rows, cols) * |largest pivot|; the largest pivot of a complete-pivoting LU is the first).
+  // luConstraintProjection would carry on with a larger null space; this path assumes full row rank (nut = NU - nc), so a rank-deficient D
+  // (singular leg configuration, redundant rows) is reported as status 2 of the instance instead of dividing by a vanishing pivot silently.
+  if (lane < nc && !(fabs(LU[lane + LU_LD * lane]) > 2.220446049250313e-16 * nc * fabs(LU[0]))) d.flags[b * F_NF + F_RANKDEF] = 1;
+  double* out = d.luRec + stage * (LU_LD * NU);
+  for (int i = lane; i < LU_LD * NU; i += 32) out[i] = LU[i];
+  int* po = d.luPerm + stage * LU_PERM;
+  for (int i = lane; i < LU_PERM; i += 32) po[i] = perm[i];
+}
+
+// K1b: projection + change of input variables of the intermediate nodes, from the Mid records and the LU factors.
 __global__ void __launch_bounds__(LQB_THREADS, 2) lq_proj_kernel(WbDev d) {
   extern __shared__ double smem[];
   const int k = blockIdx.x, b = blockIdx.y;
@@ -230,12 +276,16 @@ __global__ void __launch_bounds__(LQB_THREADS, 2) lq_proj_kernel(WbDev d) {
   const size_t node = static_cast<size_t>(b) * (d.N + 1) + k, stage = static_cast<size_t>(b) * d.N + k;
   if (d.event[node] == 1) return;
   const double* __restrict__ const mid = d.mid + stage * Mid::SIZE;
+  const double* __restrict__ const luRec = d.luRec + stage * (LU_LD * NU);
+  const int* __restrict__ const luPerm = d.luPerm + stage * LU_PERM;
   const double dt = mid[Mid::META + 3];
   PjWs s;
   pjWsMap(smem, s);
   NodeOut out = nodeOut(d, node, stage);
   PHASE_CLOCK_BEGIN(1)
+#define B200SQP_LU_PRECOMPUTED
 #include "wb_node_b.inc"
+#undef B200SQP_LU_PRECOMPUTED
 }
 
 // ---- K4a: remap the projected QP solution, Armijo metric and norms (one CTA per (instance, stage)) --------------------------------------------
@@ -362,7 +412,9 @@ __global__ void __launch_bounds__(128) prep_kernel(WbDev d, int mode) {
       in[I_ALPHA] = 1.0;
       in[I_STEP] = 0.0;
       d.flags[b * F_NF + F_LSDONE] = 0;
-      if (d.qp.status[b]) {  // QP failed: no step, report through status
+      if (d.flags[b * F_NF + F_RANKDEF]) {  // constraint Jacobian without full row rank (lu_kernel): the projected QP is not the reference's
+        d.flags[b * F_NF + F_STATUS] = 2;
+      } else if (d.qp.status[b]) {  // QP failed: no step, report through status
         d.flags[b * F_NF + F_STATUS] = 1;
       }
     }

@@ -98,6 +98,18 @@ class SqpSolver {
     std::map<int, std::vector<int>> members;
     for (int b = 0; b < batch_; ++b) members[inst[b].n_nodes()].push_back(b);
     bench_.hostPreRun = since(tPre);
+    // A receding horizon walks through a handful of node counts (115..117 for `walk`); random schedules could visit many more. Every group
+    // owns device buffers sized for its batch, so groups this solve does not use are dropped once more than kMaxGroups are held.
+    if (groups_.size() + members.size() > static_cast<size_t>(kMaxGroups))
+      for (auto it = groups_.begin(); it != groups_.end();) {
+        if (members.count(it->first) == 0 && groups_.size() > members.size()) {
+          it->second.st.release();
+          if (it->second.h) b200sqp_destroy(it->second.h);
+          it = groups_.erase(it);
+        } else {
+          ++it;
+        }
+      }
     if (members.size() == 1 || exclusiveSolve_) {
       for (auto& kv : members) solveGroup(kv.first, kv.second, inst);
       return;
@@ -139,7 +151,9 @@ class SqpSolver {
     if (!settings_.create_value_function) throw std::runtime_error("[SqpSolver] createValueFunction is false");
     const int g = groupOf_.at(b);
     if (g < 0) throw std::runtime_error("[SqpSolver] getValueFunction: no problem solved yet");
-    const Group& G = groups_.at(g);
+    const auto git = groups_.find(g);
+    if (git == groups_.end()) throw std::runtime_error("[SqpSolver] getValueFunction: the handle of this instance's last successful solve was released");
+    const Group& G = git->second;
     const int nx = model_.nx, n = G.nNodes, s = slotOf_[b];
     const vector_t& tt = primal_[b].timeTrajectory_;
     // LinearInterpolation over the node times
@@ -232,10 +246,12 @@ class SqpSolver {
                               : b200sqp_create(&model_.desc, &settings_, device_, &G.h));
     const size_t B_ = static_cast<size_t>(Bg), n_ = static_cast<size_t>(n);
     if (G.capacity != Bg || G.nNodes != n) {
-      check(b200sqp_set_batch(G.h, Bg, n));
-      G.capacity = Bg;
-      G.nNodes = n;
+      // Invalidate first: if set_batch or a pinned allocation throws, the next call re-enters this branch
+      // instead of reusing released (null) staging.
+      G.capacity = 0;
+      G.nNodes = 0;
       G.st.release();
+      check(b200sqp_set_batch(G.h, Bg, n));
       Staging& S = G.st;
       S.x0 = pinned<double>(B_ * nx);
       S.xi = pinned<double>(B_ * n_ * nx);
@@ -249,6 +265,8 @@ class SqpSolver {
       S.u = pinned<double>(B_ * (n_ - 1) * nu);
       S.ev = pinned<uint8_t>(B_ * n_);
       S.cf = pinned<uint8_t>(B_ * n_ * 2);
+      G.capacity = Bg;
+      G.nNodes = n;
     }
     double *x0 = G.st.x0, *xi = G.st.xi, *ui = G.st.ui, *tn = G.st.tn, *sw = G.st.sw, *imp = G.st.imp, *arm = G.st.arm, *xr = G.st.xr;
     uint8_t *ev = G.st.ev, *cf = G.st.cf;
@@ -362,6 +380,7 @@ class SqpSolver {
     static std::mutex tokens[16];
     return tokens[(device % 16 + 16) % 16];
   }
+  static constexpr int kMaxGroups = 6;
   bool exclusiveSolve_ = false;
   std::mutex benchMutex_;
   HostModel model_;
