@@ -42,9 +42,9 @@ int emu_dyn(const b200sqp_model_desc* d, const double* x, const double* u, doubl
     RUN_PHASE(NT, dynPhaseJacobian(P, m, w, G));
   } else {
     RUN_PHASE(NT, dynPhaseJoints<false>(P, m, x, w));
-    RUN_PHASE(NT, dynPhaseBodies(P, m, x, u, w));
+    RUN_PHASE(NT, dynPhaseBodies<false>(P, m, x, u, w));
     RUN_PHASE(NT, dynPhaseComposite<false>(P, m, w));
-    RUN_PHASE(NT, dynPhaseFinal(P, m, u, w));
+    RUN_PHASE(NT, dynPhaseFinal<false>(P, m, u, w));
     RUN_PHASE(NT, dynWriteFlow(P, x, u, w, xdot));
   }
   return 0;

@@ -22,17 +22,27 @@ namespace b200sqp {
 
 // shared-memory workspace of one evaluation point (doubles)
 struct DynWs {
+  // ---- what the value-only path (K3) needs: the first DYN_VALUE_DOUBLES doubles ------------------------------------------------------
   // base
   double Rb[9], Sz[9], SzInv[9], v0[6], a0[6];
-  double dv0[9][6], da0[9][6], dRb[3][9], dSz[3][9];  // tangents w.r.t. th(3), pdot(3), thdot(3)
   // bodies (pelvis coordinates)
   double Rj[NB][9];  // joint placement times joint rotation (parent-relative), computed body-parallel before the chain sweep
-  double R[NB][9], p[NB][3], S[NB][6], v[NB][6], a[NB][6], psd[NB][6], psdd[NB][6];
-  double I[NB][36], Bm[NB][36], f[NB][6];  // per body; folded IN PLACE into subtree composites by dynPhaseComposite
+  double R[NB][9], p[NB][3], S[NB][6], v[NB][6], a[NB][6];
+  double f[NB][6];   // per body; folded IN PLACE into subtree composites by dynPhaseComposite
   // finals
   double pc[2][3], lf[2][3], lm[2][3];  // contact points, local contact force / moment
   double N[6], IcInv[9], y[3], qddb[6];
+  // Spatial inertia per body, folded in place into subtree composites.  The value-only path keeps just the rotational 3 x 3 block of every
+  // body, packed as [NB][9] at the start of this array (it needs the root composite's block only): its workspace ends after NB * 9 doubles.
+  double I[NB][36];
+  // ---- derivative path (K1a) only -----------------------------------------------------------------------------------------------------
+  double psd[NB][6], psdd[NB][6], Bm[NB][36];
+  double dv0[9][6], da0[9][6], dRb[3][9], dSz[3][9];  // tangents w.r.t. th(3), pdot(3), thdot(3)
 };
+// doubles of the value-only prefix of DynWs (through the packed [NB][9] inertia blocks)
+constexpr int DYN_VALUE_DOUBLES = 9 + 9 + 9 + 6 + 6 + NB * (9 + 9 + 3 + 6 + 6 + 6 + 6) + 18 + 6 + 9 + 3 + 6 + NB * 9;
+static_assert(offsetof(DynWs, I) + NB * 9 * sizeof(double) == DYN_VALUE_DOUBLES * sizeof(double), "value-only prefix of DynWs");
+
 
 // Base kinematics with one tangent direction (dir in 0..8 = th, pdot, thdot; dir < 0: values only).  Straight-line code: the value lane and
 // the nine tangent lanes of a warp run the same instruction stream.
@@ -137,6 +147,7 @@ HD void dynPhaseJoints(Par P, const WbDeviceModel& m, const double* x, DynWs& w)
 //   psd_k = v_parent(k) x S_k,  a_i = a0 + sum (S_k qdd_k + psd_k qd_k),  psdd_k = a_parent(k) x S_k + v_parent(k) x psd_k
 // so one thread per body walks its own path, recomputing its ancestors' cheap quantities instead of waiting for them behind barriers
 // (this replaces five barrier-separated sweeps), and finishes with the body's spatial inertia and force in the same item.
+template <bool DERIV = true>
 HD void dynPhaseBodies(Par P, const WbDeviceModel& m, const double* x, const double* u, DynWs& w) {
   for (int i = P.tid; i < NB; i += P.nt) {
     double R[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1};
@@ -165,8 +176,10 @@ HD void dynPhaseBodies(Par P, const WbDeviceModel& m, const double* x, const dou
     st6(w.S[i], S);
     st6(w.v[i], v);
     st6(w.a[i], a);
-    st6(w.psd[i], psd);
-    st6(w.psdd[i], psdd);
+    if (DERIV) {
+      st6(w.psd[i], psd);
+      st6(w.psdd[i], psdd);
+    }
     // spatial inertia about the pelvis origin and the body force f = I a + v x* I v
     const V3 c = p + mv(R, ld3(m.com[i]));
     double T[9], Ir[9];
@@ -180,16 +193,20 @@ HD void dynPhaseBodies(Par P, const WbDeviceModel& m, const double* x, const dou
       for (int k = 0; k < 3; ++k) Ir[3 * r + k] = T[3 * r] * R[3 * k] + T[3 * r + 1] * R[3 * k + 1] + T[3 * r + 2] * R[3 * k + 2];
     const double ms = m.mass[i];
     const double C[9] = {0, -c.z, c.y, c.z, 0, -c.x, -c.y, c.x, 0};
-    double* I = w.I[i];
+    double* I = DERIV ? w.I[i] : &w.I[0][0] + 9 * i;
 #pragma unroll
     for (int r = 0; r < 3; ++r)
 #pragma unroll
       for (int k = 0; k < 3; ++k) {
         const double cc = C[3 * r] * C[k] + C[3 * r + 1] * C[3 + k] + C[3 * r + 2] * C[6 + k];
-        I[6 * r + k] = (r == k) ? ms : 0.0;
-        I[6 * r + 3 + k] = -ms * C[3 * r + k];
-        I[6 * (3 + r) + k] = ms * C[3 * r + k];
-        I[6 * (3 + r) + 3 + k] = Ir[3 * r + k] - ms * cc;
+        if (DERIV) {
+          I[6 * r + k] = (r == k) ? ms : 0.0;
+          I[6 * r + 3 + k] = -ms * C[3 * r + k];
+          I[6 * (3 + r) + k] = ms * C[3 * r + k];
+          I[6 * (3 + r) + 3 + k] = Ir[3 * r + k] - ms * cc;
+        } else {
+          I[3 * r + k] = Ir[3 * r + k] - ms * cc;
+        }
       }
     // f = I a + v x* (I v), with I = [m 1, -m c^ ; m c^, Ic] applied in closed form
     const V3 hl = ms * (v.l - cross(c, v.a)), ha = ms * cross(c, v.l) + mvIr(Ir, ms, c, v.a);
@@ -232,20 +249,22 @@ HD void dynPhaseComposite(Par P, const WbDeviceModel& m, DynWs& w) {
       }
     }
   } else {
-    for (int e = P.tid; e < 42; e += P.nt) {
+    for (int e = P.tid; e < 15; e += P.nt) {   // rotational block of the root composite inertia (packed [NB][9]) and the total force
       double s = 0.0;
-      if (e < 36) {
-        for (int i = 0; i < NB; ++i) s += w.I[i][e];
-        w.I[0][e] = s;
+      if (e < 9) {
+        double* const Iv = &w.I[0][0];
+        for (int i = 0; i < NB; ++i) s += Iv[9 * i + e];
+        Iv[e] = s;
       } else {
-        for (int i = 0; i < NB; ++i) s += w.f[i][e - 36];
-        w.f[0][e - 36] = s;
+        for (int i = 0; i < NB; ++i) s += w.f[i][e - 9];
+        w.f[0][e - 9] = s;
       }
     }
   }
 }
 
 // ---- phase 5: net wrench, base acceleration (single item) ----------------------------------------------------------------------------
+template <bool DERIV = true>
 HD void dynPhaseFinal(Par P, const WbDeviceModel& m, const double* u, DynWs& w) {
   if (P.tid != 0) return;
   V6 E{mk(0, 0, 0), mk(0, 0, 0)};
@@ -263,7 +282,7 @@ HD void dynPhaseFinal(Par P, const WbDeviceModel& m, const double* u, DynWs& w) 
   st6(w.N, N);
   double Ic[9];
   for (int r = 0; r < 3; ++r)
-    for (int k = 0; k < 3; ++k) Ic[3 * r + k] = w.I[0][6 * (3 + r) + 3 + k];
+    for (int k = 0; k < 3; ++k) Ic[3 * r + k] = DERIV ? w.I[0][6 * (3 + r) + 3 + k] : (&w.I[0][0])[3 * r + k];
   inv3(Ic, w.IcInv);
   const V3 y = mv(w.IcInv, N.a);
   st3(w.y, y);

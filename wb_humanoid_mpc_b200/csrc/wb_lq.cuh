@@ -108,6 +108,10 @@ HD void lqWsMap(double* base, LqWs& s) {
   static_assert(JU_MAX * NUC <= NB * 36, "structured rows must fit the Bm alias");
 }
 
+// Leading dimension of the LU work matrix (nc <= 14 rows x 35 columns, lane = column): odd, so that the 32 lanes walking a row hit distinct
+// shared-memory banks (ld 14 put lanes j and j + 8 on the same bank).
+constexpr int LU_LD = 15;
+
 // shared-memory map of K1b (projection + change of variables): <= 113 KB so that two CTAs share an SM.
 // The change of variables works in the pivoted variable order of the LU (u = [pivot vars (nc) ; free vars (nut)]), where
 //   Px = [X ; 0],  u0 = [x0 ; 0],  Pu = [K ; I]      (X | x0 = Xt, K = Kt)
@@ -122,6 +126,7 @@ struct PjWs {
   int* iw;                       // rowOf[16] colOf[36] posOf[36]
   // phase-1 views (projection)
   double *CD, *ev, *LU;
+  double* JS1;                   // dense rows of ONE swinging foot, 15 x 93 (ld 15), staged next to CD | e | LU (CUDA path)
   // dynamics views
   double *B1, *D12;              // 12 x nc (ld 12) ; 12 x (59 + nut) (ld 12)
   // Hessian view
@@ -129,7 +134,7 @@ struct PjWs {
   // cost change-of-variables views
   double *T11, *T12, *R11, *R21, *W, *V, *rr;   // nc x 58 (ld 14), nut x 58 (ld 23), nc x nc (ld 14), nut x nc (ld 23), nc x nut (ld 14), nut x nut (ld 23), 35 + 35
 };
-constexpr int PJ_SCRATCH = 3600;   // max over the phases: 1841 (projection), 1152 (dynamics), 2790 (swing rows), 3585 (cost change of variables)
+constexpr int PJ_SCRATCH = 3600;   // max over the phases: 1841 + 1395 (projection + staged swing rows), 1152 (dynamics), 2790 (swing rows), 3585 (cost change of variables)
 HD size_t pjWsDoubles() {
   return NX * NX + NU * NX + NU * NU + 1 + NZ + 1 + NX + NC_MAX * (NX + 1) + NC_MAX * NUT_MAX + 12 * NZ + JU_MAX * NUC + PJ_SCRATCH + 48;
 }
@@ -149,6 +154,7 @@ HD void pjWsMap(double* base, PjWs& s) {
   s.CD = s.scratch;                          // 14 x 93 = 1302
   s.ev = s.CD + NC_MAX * NZ;                 // 14
   s.LU = s.ev + NC_MAX;                      // 14 x 35 with ld LU_LD = 525
+  s.JS1 = s.LU + LU_LD * NU;                 // 15 x 93 = 1395   (ends at 3236)
   // dynamics change of variables
   s.B1 = s.scratch;                          // 12 x 14 = 168
   s.D12 = s.B1 + 12 * NC_MAX;                // 12 x 82 = 984
@@ -577,9 +583,6 @@ HD void costPhaseGradient(Par P, const NodeIn& n, const double* JU, const double
   for (int it = P.tid; it < JU_MAX * NUC; it += P.nt) midJU[it] = (it % JU_MAX < nr) ? JU[it] : 0.0;
 }
 
-// Leading dimension of the LU work matrix (nc <= 14 rows x 35 columns, lane = column): odd, so that the 32 lanes walking a row hit distinct
-// shared-memory banks (ld 14 put lanes j and j + 8 on the same bank).
-constexpr int LU_LD = 15;
 
 // ---- projection: Eigen::FullPivLU semantics (complete pivoting; particular solution with free variables = 0; kernel basis) ----------------
 // Whole factorisation by ONE warp: lane l owns columns l and l+32; pivot search = per-lane scan + shuffle arg-max with ties resolved
@@ -757,11 +760,11 @@ struct RoWs {
   RowWs rw;
 };
 HD size_t roWsDoubles() {
-  return (sizeof(DynWs) + 7) / 8 + 4 * NX + NX + 2 * FQ + 3 * NFRAMES + 96 + 2 * FQ + rowWsDoubles() + NC_MAX + 8 + 2 * NX + NU + 5;
+  return DYN_VALUE_DOUBLES + 4 * NX + NX + 2 * FQ + 3 * NFRAMES + 96 + 2 * FQ + rowWsDoubles() + NC_MAX + 8 + 2 * NX + NU + 5;
 }
 HD void roWsMap(double* base, RoWs& r) {
-  r.dyn = reinterpret_cast<DynWs*>(base);
-  r.fs = base + (sizeof(DynWs) + 7) / 8;
+  r.dyn = reinterpret_cast<DynWs*>(base);   // the value-only prefix: nothing behind DYN_VALUE_DOUBLES is touched by K3's phases
+  r.fs = base + DYN_VALUE_DOUBLES;
   r.xs = r.fs + 4 * NX;
   r.FV = r.xs + NX;
   r.FP = r.FV + 2 * FQ;

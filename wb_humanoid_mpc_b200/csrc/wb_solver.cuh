@@ -23,16 +23,29 @@ namespace b200sqp {
 #define B200SQP_LQA_CTAS 3
 #endif
 #ifndef B200SQP_LQB_THREADS
-#define B200SQP_LQB_THREADS 256
+#define B200SQP_LQB_THREADS 512
 #endif
 #ifndef B200SQP_RO_THREADS
-#define B200SQP_RO_THREADS 128
+#define B200SQP_RO_THREADS 32
+#endif
+#ifndef B200SQP_RO_GLOBAL_MODEL
+#define B200SQP_RO_GLOBAL_MODEL 1
+#endif
+#ifndef B200SQP_RO_CTAS
+#define B200SQP_RO_CTAS 12
+#endif
+#ifndef B200SQP_LQB_CTAS
+#define B200SQP_LQB_CTAS 2
 #endif
 constexpr int LQA_THREADS = B200SQP_LQA_THREADS;
 constexpr int LQB_THREADS = B200SQP_LQB_THREADS;
-// K3 can pack RO_PACK shooting nodes per CTA on thread slices rotated by 64 lanes (the phases are narrow).  Measured on B200 (r2d): three
-// nodes per 192-thread CTA shorten the per-node phase time by 27 % but halve the nodes in flight per SM in practice; 2.6 ms per trial against
-// 1.26 ms for one node per 128-thread CTA, so the shipped configuration is RO_PACK = 1.
+// K3 runs ONE WARP PER NODE (RO_THREADS = 32).  Its phases are narrow (24 bodies, 23 joints, 2 feet, a few 58-93 item loops), so in a wider
+// CTA one warp works while the others wait at the barrier, and what keeps an SM busy is the number of NODES resident on it, not the threads
+// per node.  Measured on B200 (r2k sweep, batch 256, both trials of the cold-start line search): 128 threads x 3 nodes/SM 3.20 ms,
+// 64 x 6 2.42 ms, 32 x 11 1.64 ms -- with the value-only workspace cut to 17.6 KB (DYN_VALUE_DOUBLES) and the model read through L1
+// instead of copied into every CTA's shared memory, so that shared memory allows 11 nodes per SM and the register cap (RO_CTAS) 12.
+// The older RO_PACK option (several nodes per CTA in lock-step on rotated thread slices) went the wrong way for the same reason: it made the
+// CTAs bigger, and fewer of them fit (2.6 ms per trial against 1.26 ms, r2d).
 #ifndef B200SQP_RO_PACK
 #define B200SQP_RO_PACK 1
 #endif
@@ -269,7 +282,7 @@ __global__ void __launch_bounds__(32) lu_kernel(WbDev d) {
 }
 
 // K1b: projection + change of input variables of the intermediate nodes, from the Mid records and the LU factors.
-__global__ void __launch_bounds__(LQB_THREADS, 2) lq_proj_kernel(WbDev d) {
+__global__ void __launch_bounds__(LQB_THREADS, B200SQP_LQB_CTAS) lq_proj_kernel(WbDev d) {
   extern __shared__ double smem[];
   const int k = blockIdx.x, b = blockIdx.y;
   if (d.flags[b * F_NF + F_CONVERGED]) return;
@@ -519,21 +532,37 @@ __device__ __forceinline__ void rolloutNodes(const WbDev& d, const WbDeviceModel
 
 // One CTA walks the instances b = blockIdx.y, blockIdx.y + gridDim.y, ...: the first trials of the line search are launched with one instance per
 // CTA row; the later ones -- in which almost every instance has finished and its thread blocks would only be launched to return -- with an
-// eighth of the rows (the asynchronous solve enqueues the whole back-tracking ladder, wb_capi.inc).
-__global__ void __launch_bounds__(RO_THREADS) rollout_kernel(WbDev d) {
+// sixteenth of the rows (the asynchronous solve enqueues the whole back-tracking ladder, wb_capi.inc).
+__global__ void __launch_bounds__(RO_THREADS, B200SQP_RO_CTAS) rollout_kernel(WbDev d) {
   extern __shared__ double smem[];
+#if B200SQP_RO_GLOBAL_MODEL
+  const WbDeviceModel& msh = *d.model;   // read through L1 (8.7 KB, shared by every CTA of the SM) instead of one copy per CTA
+#else
   __shared__ WbDeviceModel msh;
+#endif
   __shared__ NodeIn nsh[RO_PACK];
+  __shared__ int nAct, act[RO_THREADS];
   const int k0 = blockIdx.x * RO_PACK;
-  bool staged = false;
-  for (int b = blockIdx.y; b < d.B; b += gridDim.y) {
-    if (d.flags[b * F_NF + F_CONVERGED] || d.flags[b * F_NF + F_LSDONE]) continue;   // uniform over the CTA
-    if (!staged) {
-      for (int i = threadIdx.x; i < static_cast<int>(sizeof(WbDeviceModel) / 8); i += blockDim.x)
-        reinterpret_cast<double*>(&msh)[i] = reinterpret_cast<const double*>(d.model)[i];
-      staged = true;
+  // the instances of this CTA row that still search, found with ONE round of flag loads (a late trial walks sixteen instances per CTA and
+  // nearly all of them have finished: sixteen dependent load pairs cost more than the rest of such a launch)
+  if (threadIdx.x == 0) nAct = 0;
+  __syncthreads();
+  for (int j = threadIdx.x; blockIdx.y + j * gridDim.y < d.B; j += blockDim.x) {
+    const int b = blockIdx.y + j * gridDim.y;
+    if (!(d.flags[b * F_NF + F_CONVERGED] | d.flags[b * F_NF + F_LSDONE])) {
+      const int slot = atomicAdd(&nAct, 1);
+      if (slot < RO_THREADS) act[slot] = b;
     }
-    rolloutNodes(d, msh, nsh, smem, b, k0);
+  }
+  __syncthreads();
+  const int n = nAct;
+  if (n == 0) return;
+#if !B200SQP_RO_GLOBAL_MODEL
+  for (int i = threadIdx.x; i < static_cast<int>(sizeof(WbDeviceModel) / 8); i += blockDim.x)
+    reinterpret_cast<double*>(&msh)[i] = reinterpret_cast<const double*>(d.model)[i];
+#endif
+  for (int a = 0; a < n; ++a) {
+    rolloutNodes(d, msh, nsh, smem, act[a], k0);
     __syncthreads();   // the workspace is reused by the next instance
   }
 }

@@ -37,6 +37,8 @@ def sources():
 def needs_build() -> bool:
     if not SO.exists():
         return True
+    if os.environ.get("B200SQP_LIB"):
+        return False   # a development build made by hand (own -D flags): never rebuilt from here
     t = SO.stat().st_mtime
     return any(s.stat().st_mtime > t for s in sources())
 
