@@ -52,8 +52,9 @@ L.b200sqp_debug_phase_clocks(0, None, 0, node)
 for _ in range(2):
     solver.reset()
     solver.solve()
-files = {0: "wb_node_a.inc", 1: "wb_node_b.inc", 2: "wb_rollout_body.inc"}
-for kid, name in [(0, "K1a lq_dyn_kernel"), (1, "K1b lq_proj_kernel"), (2, "K3 rollout_kernel")]:
+files = {0: "wb_node_a.inc", 1: "wb_node_b2.inc", 2: "wb_rollout_body.inc", 4: "wb_node_b1.inc"}
+cost_src = (ROOT / "wb_humanoid_mpc_b200" / "csrc" / "wb_node_b_cost.inc").read_text().split("\n")
+for kid, name in [(0, "K1a lq_dyn_kernel"), (4, "K1b part 1 lq_projdyn_kernel"), (1, "K1b part 2 lq_proj_kernel"), (2, "K3 rollout_kernel")]:
     buf = (C.c_longlong * (2 * 512))()
     n = L.b200sqp_debug_phase_clocks(kid, buf, 512, -1)
     a = np.array(buf[:2 * n], dtype=np.int64).reshape(n, 2)
@@ -69,7 +70,7 @@ for kid, name in [(0, "K1a lq_dyn_kernel"), (1, "K1b lq_proj_kernel"), (2, "K3 r
         c, k = agg.get(line, (0, 0))
         agg[line] = (c + cyc, k + 1)
     for line, (cyc, k) in sorted(agg.items(), key=lambda kv: -kv[1][0])[:args.top]:
-        text = src[line - 1].strip()[:110] if 0 < line <= len(src) else "?"
+        text = (cost_src[line - 1000].strip()[:110] if line > 1000 else src[line - 1].strip()[:110]) if 0 < line <= 1000 + len(cost_src) else "?"
         print(f"  {cyc:8d} {100.0 * cyc / tot:5.1f}%  x{k:<2d} L{line:<4d} {text}")
 
 buf = (C.c_longlong * 64)()

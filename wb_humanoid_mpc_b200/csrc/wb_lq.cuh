@@ -170,6 +170,24 @@ HD void pjWsMap(double* base, PjWs& s) {
   s.rr = s.V + NUT_MAX * NUT_MAX;            // 70   (ends at 3585)
 }
 
+// shared-memory map of K1b part 1 (projection + dynamics, wb_node_b1.inc): the same PjWs views on a 34 KB workspace without the Hessian blocks
+HD size_t pjDynWsDoubles() { return NC_MAX * (NX + 1) + NC_MAX * NUT_MAX + 12 * NZ + NX + (NC_MAX * NZ + NC_MAX + LU_LD * NU) + 48; }
+HD void pjDynWsMap(double* base, PjWs& s) {
+  s.Q = s.S = s.R = s.gq = s.JU = s.JS1 = s.JRc = nullptr;
+  s.T11 = s.T12 = s.R11 = s.R21 = s.W = s.V = s.rr = nullptr;
+  s.Xt = base;
+  s.Kt = s.Xt + NC_MAX * (NX + 1);
+  s.AB12 = s.Kt + NC_MAX * NUT_MAX;
+  s.bvec = s.AB12 + 12 * NZ;
+  s.scratch = s.bvec + NX;
+  s.CD = s.scratch;                          // 14 x 93
+  s.ev = s.CD + NC_MAX * NZ;                 // 14
+  s.LU = s.ev + NC_MAX;                      // 14 x 35 with ld LU_LD
+  s.B1 = s.scratch;                          // 12 x 14, over the dead CD
+  s.D12 = s.B1 + 12 * NC_MAX;                // 12 x 82
+  s.iw = reinterpret_cast<int*>(s.LU + LU_LD * NU);
+}
+
 HD void penRelaxed(double mu, double delta, double h, double& v, double& d1, double& d2) {
   // RelaxedBarrierPenalty (ocs2_core/src/penalties/penalties/RelaxedBarrierPenalty.cpp:37-66)
   if (h > delta) {
@@ -748,6 +766,129 @@ HD void luPhaseScatter(Par P, int nc, const int* posOf, const double* Xt, const 
       Pu[i + NU * kk] = (kk < nut) ? ((pos < nc) ? Kt[pos + NC_MAX * kk] : (pos == nc + kk ? 1.0 : 0.0)) : 0.0;
     }
   }
+}
+
+
+// ---- K1b phase bodies shared by the host schedule (wb_node_b.inc) and the two CUDA schedules (wb_node_b1.inc / wb_node_b2.inc) -----------
+// dense swing-foot rows: [Q S'; S R] = JS' JS (JS: nsw x 93, ld nsw, in shared memory or straight from the record in HBM/L2)
+template <class PAR>
+HD void pjSwingRows(PAR P, int nsw, const double* __restrict__ JS, const PjWs& s) {
+  par_mma_gemm<true, false, 4>(P, NX, NX, nsw, 1.0, JS, nsw, JS, nsw, s.Q, NX);
+  par_mma_gemm<true, false, 4>(rot(P, 128), NU, NX, nsw, 1.0, JS + nsw * NX, nsw, JS, nsw, s.S, NU);
+  par_mma_gemm<true, false, 3>(rot(P, 64), NU, NU, nsw, 1.0, JS + nsw * NX, nsw, JS + nsw * NX, nsw, s.R, NU);
+}
+// structured rows: JU' JU on their 27-column support, added to the Hessian
+HD void pjPhaseStructRows(Par P, int nru, const PjWs& s) {
+  for (int it = P.tid; it < NUC * NUC; it += P.nt) {
+    const int a = it % NUC, c = it / NUC;
+    double v = 0.0;
+    for (int k = 0; k < nru; ++k) v = fma(s.JU[k + JU_MAX * a], s.JU[k + JU_MAX * c], v);
+    if (a < 15 && c < 15) s.Q[(3 + a) + NX * (3 + c)] += v;
+    else if (a >= 15 && c < 15) s.S[(a - 15) + NU * (3 + c)] += v;
+    else if (a >= 15 && c >= 15) s.R[(a - 15) + NU * (c - 15)] += v;
+  }
+}
+// Hessian: diagonal (tracking cost, joint limits, curvature shift) and the friction-cone blocks of the stance feet.  Touches entries the
+// structured rows also touch: never in the same phase as pjPhaseStructRows or a GEMM writing Q / R.
+HD void pjPhaseHessianDiag(Par P, const double* __restrict__ mid, const PjWs& s) {
+  for (int i = rot(P, 160).tid; i < NX; i += P.nt) s.Q[i + NX * i] += mid[Mid::HDG + i];
+  for (int i = rot(P, 64).tid; i < NU + 18; i += P.nt) {   // one item per touched entry of R: 35 diagonal, 12 off-diagonal friction entries
+    if (i < NU) {
+      double v = mid[Mid::HDG + NX + i];
+      if (i < 12 && i % 6 < 3) v += mid[Mid::FRIC + 9 * (i / 6) + 4 * (i % 6)];
+      s.R[i + NU * i] += v;
+    } else {
+      const int e = i - NU, c = e / 9, a = (e % 9) / 3, b = e % 3;
+      if (a != b) s.R[(6 * c + a) + NU * (6 * c + b)] += mid[Mid::FRIC + 9 * c + 3 * a + b];
+    }
+  }
+}
+// dynamics in the projected inputs: A~ = A + B Px, B~ = B Pu, b~ = b + B u0 -- dense rows from D12 = B1 [X | x0 | K], the others from the
+// fixed pattern of the integrator rows
+HD void pjPhaseDynamicsOut(Par P, int nc, int nut, double dt, const PjWs& s, const int* colOf, const int* posOf, const NodeOut& out) {
+  for (int it = P.tid; it < NX * (NX + 1 + nut); it += P.nt) {
+    const int r = it % NX, c = it / NX;
+    const int dense = r < 6 ? r : ((r >= NV && r < NV + 6) ? 6 + r - NV : -1);
+    double acc;
+    if (dense >= 0) {
+      acc = s.D12[dense + 12 * c];
+      if (c < NX) acc += s.AB12[dense + 12 * c];
+      else if (c == NX) acc += s.bvec[r];
+      else acc += s.AB12[dense + 12 * (NX + colOf[nc + c - NX - 1])];
+    } else {
+      const int j = (r < NV) ? r - 6 : r - NV - 6;
+      const double coef = (r < NV) ? 0.5 * dt * dt : dt;
+      const int pos = posOf[12 + j];
+      if (c <= NX) {
+        acc = (pos < nc) ? coef * s.Xt[pos + NC_MAX * c] : 0.0;
+        if (c < NX) acc += (c == r ? 1.0 : 0.0) + ((r < NV && c == NV + r) ? dt : 0.0);
+        else acc += s.bvec[r];
+      } else {
+        const int kk = c - NX - 1;
+        acc = (pos < nc) ? coef * s.Kt[pos + NC_MAX * kk] : (pos == nc + kk ? coef : 0.0);
+      }
+    }
+    if (c < NX) out.A[r + NX * c] = acc;
+    else if (c == NX) out.b[r] = acc;
+    else out.Bt[r + NX * (c - NX - 1)] = acc;
+  }
+}
+// gathers in pivot order: T11 = S1, T12 = S2, R11, R21, W = R12, V = R22, rr = r
+HD void pjPhaseGather(Par P, int nc, const int* colOf, const PjWs& s) {
+  for (int it = P.tid; it < NU * NX; it += P.nt) {
+    const int t = it % NU, c = it / NU;
+    const double v = s.S[colOf[t] + NU * c];
+    if (t < nc) s.T11[t + NC_MAX * c] = v;
+    else s.T12[(t - nc) + NUT_MAX * c] = v;
+  }
+  for (int it = P.tid; it < NU * NU; it += P.nt) {
+    const int t = it % NU, u = it / NU;
+    const double v = s.R[colOf[t] + NU * colOf[u]];
+    if (t < nc) {
+      if (u < nc) s.R11[t + NC_MAX * u] = v;
+      else s.W[t + NC_MAX * (u - nc)] = v;
+    } else {
+      if (u < nc) s.R21[(t - nc) + NUT_MAX * u] = v;
+      else s.V[(t - nc) + NUT_MAX * (u - nc)] = v;
+    }
+  }
+  for (int t = P.tid; t < NU; t += P.nt) s.rr[t] = s.gq[NX + colOf[t]];
+}
+// projected cost blocks, scaled by dt
+HD void pjPhaseOutputs(Par P, int nc, int nut, double dt, const PjWs& s, const NodeOut& out) {
+  for (int i = P.tid; i < NX * NX; i += P.nt) out.Q[i] = dt * s.Q[i];
+  for (int i = P.tid; i < NX; i += P.nt) out.q[i] = dt * s.gq[i];
+  for (int i = P.tid; i < nut * NX; i += P.nt) out.St[(i % nut) + NUT_MAX * (i / nut)] = dt * s.T12[(i % nut) + NUT_MAX * (i / nut)];
+  for (int i = P.tid; i < nut * nut; i += P.nt) out.Rt[(i % nut) + NUT_MAX * (i / nut)] = dt * s.V[(i % nut) + NUT_MAX * (i / nut)];
+  for (int i = P.tid; i < nut; i += P.nt) out.rt[i] = dt * s.rr[nc + i];
+  if (P.tid == 0) *out.nut = nut;
+}
+// optional raw (pre-projection) block dump, oracle layout; cost already multiplied by dt.  Part A: everything but the Hessian blocks.
+HD void pjPhaseRawA(Par P, int nc, double dt, const double* __restrict__ mid, double* o) {
+  for (int i = P.tid; i < NX * NZ; i += P.nt) o[i] = abEntry(mid + Mid::AB12, dt, i % NX, i / NX);
+  o += NX * NZ;
+  for (int i = P.tid; i < NX; i += P.nt) o[i] = mid[Mid::B_ + i];
+  o += NX;
+  o += NX * NX + NU * NX + NU * NU;   // Hessian blocks: pjPhaseRawB, once Q, S, R exist
+  for (int i = P.tid; i < NX; i += P.nt) o[i] = dt * mid[Mid::GQ + i];
+  o += NX;
+  for (int i = P.tid; i < NU; i += P.nt) o[i] = dt * mid[Mid::GQ + NX + i];
+  o += NU;
+  if (P.tid == 0) o[0] = mid[Mid::META + 4];
+  o += 1;
+  for (int i = P.tid; i < NC_MAX * NZ; i += P.nt) o[i] = (i % NC_MAX < nc) ? mid[Mid::CD + i] : 0.0;
+  o += NC_MAX * NZ;
+  for (int i = P.tid; i < NC_MAX; i += P.nt) o[i] = (i < nc) ? mid[Mid::E + i] : 0.0;
+  o += NC_MAX;
+  if (P.tid == 0) o[0] = nc;
+}
+HD void pjPhaseRawB(Par P, double dt, const PjWs& s, double* raw) {
+  double* o = raw + NX * NZ + NX;
+  for (int i = P.tid; i < NX * NX; i += P.nt) o[i] = dt * s.Q[i];
+  o += NX * NX;
+  for (int i = P.tid; i < NU * NX; i += P.nt) o[i] = dt * s.S[i];
+  o += NU * NX;
+  for (int i = P.tid; i < NU * NU; i += P.nt) o[i] = dt * s.R[i];
 }
 
 }  // namespace b200sqp

@@ -34,11 +34,18 @@ namespace b200sqp {
 #ifndef B200SQP_RO_CTAS
 #define B200SQP_RO_CTAS 12
 #endif
+#ifndef B200SQP_LQB1_THREADS
+#define B200SQP_LQB1_THREADS 64
+#endif
+#ifndef B200SQP_LQB1_CTAS
+#define B200SQP_LQB1_CTAS 6
+#endif
 #ifndef B200SQP_LQB_CTAS
 #define B200SQP_LQB_CTAS 2
 #endif
 constexpr int LQA_THREADS = B200SQP_LQA_THREADS;
 constexpr int LQB_THREADS = B200SQP_LQB_THREADS;
+constexpr int LQB1_THREADS = B200SQP_LQB1_THREADS;
 // K3 runs ONE WARP PER NODE (RO_THREADS = 32).  Its phases are narrow (24 bodies, 23 joints, 2 feet, a few 58-93 item loops), so in a wider
 // CTA one warp works while the others wait at the barrier, and what keeps an SM busy is the number of NODES resident on it, not the threads
 // per node.  Measured on B200 (r2k sweep, batch 256, both trials of the cold-start line search): 128 threads x 3 nodes/SM 3.20 ms,
@@ -75,7 +82,7 @@ struct WbDev {
   int* flags;        // [B][F_NF]
   int* pending;      // number of instances whose line search is still running
   double* mid;       // K1a -> K1b records [B][N][Mid::SIZE]
-  double* luRec;     // lu_kernel -> K1b: LU factors of D in position order [B][N][LU_LD * NU]
+  double* luRec;     // lu_kernel -> K1b part 1: LU factors of D in position order; part 1 -> part 2: [X | x0], K   [B][N][LU_REC]
   int* luPerm;       // ... and the row / column permutations [B][N][52] (rowOf[16], colOf[36])
   double* gstats;    // global-step mode: per-candidate statistics [32][4]
   double* raw;       // optional [B][N][rawPer]
@@ -108,8 +115,8 @@ __device__ __forceinline__ void loadNode(const WbDev& d, int b, int k, NodeIn& n
 // Development aid (never in the shipped build): with -DB200SQP_PHASE_CLOCK thread 0 of one CTA records (source line, clock64) after every
 // phase barrier; tools/phase_clock.py turns that into a per-phase cycle table.
 #ifdef B200SQP_PHASE_CLOCK
-__device__ long long g_phaseClk[4][512][2];
-__device__ int g_phaseCnt[4];
+__device__ long long g_phaseClk[5][512][2];
+__device__ int g_phaseCnt[5];
 __device__ int g_phaseNode = 20;
 #define PHASE_CLOCK_BEGIN(id)                                                                  \
   const int clkId_ = (id);                                                                     \
@@ -255,6 +262,8 @@ __global__ void __launch_bounds__(LQA_THREADS, B200SQP_LQA_CTAS) lq_dyn_kernel(W
 // The factorisation is a chain of 12-14 dependent pivot steps (40 k cycles inside K1b, a third of that kernel, with seven warps waiting);
 // as its own kernel 32 nodes are resident per SM and hide each other's latency.
 constexpr int LU_PERM = 52;
+constexpr int LU_XK = NC_MAX * (NX + 1) + NC_MAX * NUT_MAX;   // [X | x0] and K in pivot order (K1b part 1 -> part 2)
+constexpr int LU_REC = LU_LD * NU + LU_XK;                   // per-stage record: LU factors | [X | x0], K
 __global__ void __launch_bounds__(32) lu_kernel(WbDev d) {
   const int k = blockIdx.x, b = blockIdx.y;
   if (d.flags[b * F_NF + F_CONVERGED]) return;
@@ -275,13 +284,32 @@ __global__ void __launch_bounds__(32) lu_kernel(WbDev d) {
   // luConstraintProjection would carry on with a larger null space; this path assumes full row rank (nut = NU - nc), so a rank-deficient D
   // (singular leg configuration, redundant rows) is reported as status 2 of the instance instead of dividing by a vanishing pivot silently.
   if (lane < nc && !(fabs(LU[lane + LU_LD * lane]) > 2.220446049250313e-16 * nc * fabs(LU[0]))) d.flags[b * F_NF + F_RANKDEF] = 1;
-  double* out = d.luRec + stage * (LU_LD * NU);
+  double* out = d.luRec + stage * LU_REC;
   for (int i = lane; i < LU_LD * NU; i += 32) out[i] = LU[i];
   int* po = d.luPerm + stage * LU_PERM;
   for (int i = lane; i < LU_PERM; i += 32) po[i] = perm[i];
 }
 
-// K1b: projection + change of input variables of the intermediate nodes, from the Mid records and the LU factors.
+// K1b part 1: constraint projection (from the LU factors) and the dynamics in the projected inputs; 34 KB per node, six nodes per SM.
+__global__ void __launch_bounds__(LQB1_THREADS, B200SQP_LQB1_CTAS) lq_projdyn_kernel(WbDev d) {
+  extern __shared__ double smem[];
+  const int k = blockIdx.x, b = blockIdx.y;
+  if (d.flags[b * F_NF + F_CONVERGED]) return;
+  const size_t node = static_cast<size_t>(b) * (d.N + 1) + k, stage = static_cast<size_t>(b) * d.N + k;
+  if (d.event[node] == 1) return;
+  const double* __restrict__ const mid = d.mid + stage * Mid::SIZE;
+  const double* __restrict__ const luRec = d.luRec + stage * LU_REC;
+  const int* __restrict__ const luPerm = d.luPerm + stage * LU_PERM;
+  double* __restrict__ const xk = d.luRec + stage * LU_REC + LU_LD * NU;
+  const double dt = mid[Mid::META + 3];
+  PjWs s;
+  pjDynWsMap(smem, s);
+  NodeOut out = nodeOut(d, node, stage);
+  PHASE_CLOCK_BEGIN(4)
+#include "wb_node_b1.inc"
+}
+
+// K1b part 2: the node's Hessian and its change of input variables (the cost side of projectTranscription).
 __global__ void __launch_bounds__(LQB_THREADS, B200SQP_LQB_CTAS) lq_proj_kernel(WbDev d) {
   extern __shared__ double smem[];
   const int k = blockIdx.x, b = blockIdx.y;
@@ -289,15 +317,14 @@ __global__ void __launch_bounds__(LQB_THREADS, B200SQP_LQB_CTAS) lq_proj_kernel(
   const size_t node = static_cast<size_t>(b) * (d.N + 1) + k, stage = static_cast<size_t>(b) * d.N + k;
   if (d.event[node] == 1) return;
   const double* __restrict__ const mid = d.mid + stage * Mid::SIZE;
-  const double* __restrict__ const luRec = d.luRec + stage * (LU_LD * NU);
+  const double* __restrict__ const xk = d.luRec + stage * LU_REC + LU_LD * NU;
   const int* __restrict__ const luPerm = d.luPerm + stage * LU_PERM;
   const double dt = mid[Mid::META + 3];
   PjWs s;
   pjWsMap(smem, s);
   NodeOut out = nodeOut(d, node, stage);
   PHASE_CLOCK_BEGIN(1)
-#define B200SQP_LU_PRECOMPUTED
-#include "wb_node_b.inc"
+#include "wb_node_b2.inc"
 #undef B200SQP_LU_PRECOMPUTED
 }
 
