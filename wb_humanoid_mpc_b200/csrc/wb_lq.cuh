@@ -83,23 +83,29 @@ struct LqWs {
   double *valS, *JU;                   // swing-row values (2 x 18) ; structured rows (aliases dyn->Bm, free between stage 0 and stage 1)
   RowWs rw;
 };
+// Three nodes per SM was the limit of a 66.7 KB workspace; K1a is bound by the number of resident nodes (see K3), so the map overlays what is
+// never alive together: the local foot tangents JFl and the swing-foot gradients gfoot live only during the stage-0 phases and sit on the
+// Jacobian blocks of the stage points 1..3, which are written afterwards; the chain scratch tmpG sits on the body inertias of the dynamics
+// workspace, dead once the last stage Jacobian exists.  54.9 KB: four nodes per SM (with the model read through L1, not copied per CTA).
 HD size_t lqWsDoubles() {
   const size_t dynD = (sizeof(DynWs) + 7) / 8;
-  return dynD + 4 * 6 * NZ + 2 * FLOC * FQ + 3 * NFRAMES + NFRAMES * 15 * 3 + 6 * NX + 2 * FQ + 3 * NZ + NC_MAX + 96 + 16 + 2 * FQ + rowWsDoubles() + 9;
+  return dynD + 4 * 6 * NZ + 3 * NFRAMES + NFRAMES * 15 * 3 + 6 * NX + 2 * FQ + NZ + NC_MAX + 96 + 16 + 2 * FQ + rowWsDoubles() + 9;
 }
 HD void lqWsMap(double* base, LqWs& s) {
   const size_t dynD = (sizeof(DynWs) + 7) / 8;
   s.dyn = reinterpret_cast<DynWs*>(base);
   s.G = base + dynD;
-  s.JFl = s.G + 4 * 6 * NZ;
-  s.FP = s.JFl + 2 * FLOC * FQ;
+  s.JFl = s.G + 6 * NZ;                 // over G[1..3] (stage 0 only)
+  s.gfoot = s.JFl + 2 * FLOC * FQ;      // likewise
+  static_assert(2 * FLOC * FQ + 2 * NZ <= 3 * 6 * NZ, "JFl and gfoot must fit the stage blocks 1..3");
+  s.tmpG = &s.dyn->I[0][0];             // chain phases only: the dynamics workspace is dead by then
+  static_assert(6 * NZ <= NB * 36, "tmpG must fit the inertia alias");
+  s.FP = s.G + 4 * 6 * NZ;
   s.DFP = s.FP + 3 * NFRAMES;
-  s.tmpG = s.JFl;  // the local foot tangents are dead once the stage-0 Jacobians are assembled (6 x 93 <= 2 x 36 x 18)
   s.fs = s.DFP + NFRAMES * 15 * 3;
   s.FV = s.fs + 6 * NX;
   s.gq = s.FV + 2 * FQ;
-  s.gfoot = s.gq + NZ;
-  s.ev = s.gfoot + 2 * NZ;
+  s.ev = s.gq + NZ;
   s.pv = s.ev + NC_MAX;
   s.sc = s.pv + 96;
   s.valS = s.sc + 16;

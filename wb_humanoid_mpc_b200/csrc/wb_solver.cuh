@@ -17,10 +17,13 @@ namespace b200sqp {
 // CTA widths: compile-time, overridable for the occupancy sweeps of tools/dev/variant_sweep.py (every phase loops `for (i = tid; i < n; i += nt)`,
 // so any multiple of 32 gives the same results).
 #ifndef B200SQP_LQA_THREADS
-#define B200SQP_LQA_THREADS 128
+#define B200SQP_LQA_THREADS 96
+#endif
+#ifndef B200SQP_LQA_GLOBAL_MODEL
+#define B200SQP_LQA_GLOBAL_MODEL 1
 #endif
 #ifndef B200SQP_LQA_CTAS
-#define B200SQP_LQA_CTAS 3
+#define B200SQP_LQA_CTAS 4
 #endif
 #ifndef B200SQP_LQB_THREADS
 #define B200SQP_LQB_THREADS 512
@@ -35,7 +38,7 @@ namespace b200sqp {
 #define B200SQP_RO_CTAS 12
 #endif
 #ifndef B200SQP_LQB1_THREADS
-#define B200SQP_LQB1_THREADS 64
+#define B200SQP_LQB1_THREADS 128
 #endif
 #ifndef B200SQP_LQB1_CTAS
 #define B200SQP_LQB1_CTAS 6
@@ -246,11 +249,15 @@ __global__ void __launch_bounds__(LQA_THREADS, B200SQP_LQA_CTAS) lq_dyn_kernel(W
     n.xnext = d.x + (node + 1) * NX;
   }
   if (lqTerminalOrEventNode(d, n, k, node, stage, d.model->Qfd, NX, NU, smem)) return;
+#if B200SQP_LQA_GLOBAL_MODEL
+  const WbDeviceModel& m = *d.model;   // read through L1 (8.7 KB, shared by every CTA of the SM): the shared memory buys a fourth node
+#else
   __shared__ WbDeviceModel msh;  // model constants staged once per CTA: the kinematic phases read them in dependent sequences
   for (int i = threadIdx.x; i < static_cast<int>(sizeof(WbDeviceModel) / 8); i += blockDim.x)
     reinterpret_cast<double*>(&msh)[i] = reinterpret_cast<const double*>(d.model)[i];
   __syncthreads();
   const WbDeviceModel& m = msh;
+#endif
   LqWs s;
   lqWsMap(smem, s);
   double* const mid = d.mid + stage * Mid::SIZE;
