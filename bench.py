@@ -658,7 +658,7 @@ def main():
 
     # ---- per-kernel roofline -------------------------------------------------------------------------------------------
     # Device ms per stage are CUDA events recorded by the library on the launching stream (b200sqp_get_stage_times): ms[0] = K1a + K1b,
-    # ms[3] = lu_kernel + K1b, ms[1] = K2 (+ remap), ms[2] = the line search = n_ls x (K3 + accept).
+    # ms[3] = lu_kernel + the two K1b kernels, ms[1] = K2 (+ remap), ms[2] = the line search = n_ls x (K3 + accept).
     stage_ms = stage_acc / args.steps
     N = n_nodes - 1
     nut = 23
@@ -666,9 +666,9 @@ def main():
     # thread blocks of finished instances return at once; an instance accepted at alpha = decay^t ran t + 1 trials
     trials = np.where(alphas > 0, np.round(np.log(np.maximum(alphas, 1e-300)) / np.log(settings.alpha_decay)) + 1, 14)
     n_ls = max(1.0, float(np.mean(trials)))
-    k_ms = {"lq_dyn_kernel (K1a)": stage_ms[0] - stage_ms[3], "lu_kernel + lq_proj_kernel (K1b)": stage_ms[3], "riccati_bwd + riccati_fwd kernels (K2)": stage_ms[1],
+    k_ms = {"lq_dyn_kernel (K1a)": stage_ms[0] - stage_ms[3], "lu + lq_projdyn + lq_proj kernels (K1b)": stage_ms[3], "riccati_bwd + riccati_fwd kernels (K2)": stage_ms[1],
             "rollout_kernel (K3)": stage_ms[2] / n_ls}
-    k_share = {"lq_dyn_kernel (K1a)": k_ms["lq_dyn_kernel (K1a)"], "lu_kernel + lq_proj_kernel (K1b)": stage_ms[3], "riccati_bwd + riccati_fwd kernels (K2)": stage_ms[1],
+    k_share = {"lq_dyn_kernel (K1a)": k_ms["lq_dyn_kernel (K1a)"], "lu + lq_projdyn + lq_proj kernels (K1b)": stage_ms[3], "riccati_bwd + riccati_fwd kernels (K2)": stage_ms[1],
                "rollout_kernel (K3)": stage_ms[2]}
     # algorithmic bytes per launch: what each kernel must read + write given the kernel split (doubles x 8)
     rec = 8 * (58 * 58 + 58 * nut + 58 + 58 * 58 + nut * 58 + nut * nut + 58 + nut)            # projected stage record A B b Q S R q r
@@ -676,8 +676,8 @@ def main():
     node_in = 8 * (58 + 35 + 58 + 58 + 6 + 2 + 1 + 1) + 3                                   # x u x+ xref swing impact arm t, flags
     swing_rows = 15.0 * float((1 - batch["contact_flags"][:, :-1, :].astype(np.float64)).sum()) / (B * N)   # mean dense cost rows / node
     mid = 8 * (12 * 93 + 58 + 14 * 93 + 14 + 93 + 93 + 18 + 24 * 27 + 6 + swing_rows * 93)   # K1a -> K1b record (struct Mid)
-    lu = 8 * (14 * 35) + 2 * (8 * 15 * 35 + 4 * 52)                                         # lu_kernel: D in, factors + permutations out (and back in)
-    alg = {"lq_dyn_kernel (K1a)": B * N * (node_in + mid), "lu_kernel + lq_proj_kernel (K1b)": B * N * (mid + rec + proj + lu),
+    lu = 8 * (14 * 35) + 2 * (8 * 15 * 35 + 4 * 52) + 2 * 8 * (14 * 59 + 14 * 23) + 8 * (12 * 93 + 58 + 14 * 94)   # lu_kernel: D in, factors + permutations out (and back in); part 1 -> part 2: [X | x0], K out and back in; part 1 re-reads A/B rows, b, C, D, e
+    alg = {"lq_dyn_kernel (K1a)": B * N * (node_in + mid), "lu + lq_projdyn + lq_proj kernels (K1b)": B * N * (mid + rec + proj + lu),
            # backward sweep: the record in, K~ k out; forward sweep (own kernel): A, b, B~, K~, k in, dx, du~ out
            "riccati_bwd + riccati_fwd kernels (K2)": B * N * (rec + 8 * (nut * 58 + nut) + 8 * (58 * 58 + 58 + 58 * nut + nut * 58 + nut) + 8 * (58 + nut)),
            "rollout_kernel (K3)": B * N * (8 * (3 * 58 + 35 + 58 + 35) + 32)}
@@ -688,7 +688,7 @@ def main():
         pass
     peak = peaks.get("hbm_gbs", 6650.0)
     fp64_peak = 40.0   # TFLOP/s, nominal B200 fp64 (vector and DMMA); MEASURED_PEAKS.json carries bf16 only
-    short = {"lq_dyn_kernel (K1a)": ["lqa"], "lu_kernel + lq_proj_kernel (K1b)": ["lqb"], "riccati_bwd + riccati_fwd kernels (K2)": ["ricb", "ricf"],
+    short = {"lq_dyn_kernel (K1a)": ["lqa"], "lu + lq_projdyn + lq_proj kernels (K1b)": ["lqb", "lqp", "lu"], "riccati_bwd + riccati_fwd kernels (K2)": ["ricb", "ricf"],
              "rollout_kernel (K3)": ["ro"]}
     kernels = {}
     for name, ms in k_ms.items():
@@ -698,6 +698,8 @@ def main():
             e["traffic"], e["ncu_capture"], tflop = 0.0, [], 0.0
             for sh in short[name]:
                 raws = sorted((ROOT / "profiles").glob(f"ncu_{sh}_*_raw.json"))
+                if not raws:
+                    continue   # no capture of this kernel committed (yet)
                 raw = json.loads(raws[-1].read_text())
                 scale = B / float(raw.get("batch", 64))   # the r2 captures are taken at the benchmarked batch (256): scale 1
                 e["ncu_capture"].append(raws[-1].name)

@@ -12,7 +12,7 @@ timeout 300 python tools/phase_clock.py --node 37 --batch 256 > $o/phase_clock_$
 timeout 300 ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --csv --log-file $o/launches_${t}.csv python bench.py --steps 2 --warmup 1 --no-cpu-baseline > $o/${t}_ll.log 2>&1
 # -s: launches of that kernel to skip.  One solve launches every LQ / QP kernel once and rollout_kernel 14 times (the whole back-tracking
 # ladder): skip the warm-up solve (+ the upload solve) so that the capture is a steady-state launch; rollout: the FIRST trial of a solve.
-for k in ricb:riccati_bwd:2 ricf:riccati_fwd:2 lqa:lq_dyn_kernel:2 lqb:lq_proj:2 lu:lu_kernel:2 ro:rollout_kernel:28; do
+for k in ricb:riccati_bwd:2 ricf:riccati_fwd:2 lqa:lq_dyn_kernel:2 lqp:lq_projdyn_kernel:2 lqb:lq_proj_kernel:2 lu:lu_kernel:2 ro:rollout_kernel:28; do
   IFS=: read s n skip <<< "$k"
   timeout 400 ncu --set full --clock-control none -k regex:$n -s $skip -c 1 -f -o /tmp/prof_${s} python bench.py --steps 2 --warmup 1 --no-cpu-baseline > $o/${t}_ncu_$s.log 2>&1
   ncu -i /tmp/prof_${s}.ncu-rep --page raw --csv > $o/ncuraw_${s}_${t}.csv 2>/dev/null
