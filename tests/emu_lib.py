@@ -46,7 +46,8 @@ def dyn(desc, x, u, deriv=True):
     return xd, G.T.copy()
 
 
-def lq_node(desc, x, u, xnext, xref, dt, contact, swing, impact, arm_phase):
+def lq_node(desc, x, u, xnext, xref, dt, contact, swing, impact, arm_phase, mode=0):
+    """mode 0: one-pass K1b schedule; 1 / 2: the CUDA schedules (lu + part 1 + part 2; 2 = Q accumulated in place)."""
     NX, NU, NT = 58, 35, 23
     xs, us, xn, xr = F(x), F(u), F(xnext), F(xref)
     nin = EmuNodeIn(_p(xs), _p(us), _p(xn), _p(xr), dt, (C.c_int * 2)(*[int(c) for c in contact]), (C.c_double * 6)(*np.asarray(swing, float).reshape(6)),
@@ -58,8 +59,8 @@ def lq_node(desc, x, u, xnext, xref, dt, contact, swing, impact, arm_phase):
     perf = np.zeros(4)
     per = 2 * NX * NX + 2 * NX * NU + NU * NU + 2 * NX + NU + 1 + 14 * (NX + NU + 1) + 1
     raw = np.zeros(per)
-    rc = lib().emu_lq_node(C.byref(desc), C.byref(nin), _p(A), _p(Bt), _p(b), _p(Q), _p(St), _p(Rt), _p(q), _p(rt), _p(Pu), _p(Px), _p(u0),
-                           C.byref(nut), _p(perf), _p(raw))
+    rc = lib().emu_lq_node_mode(C.byref(desc), C.byref(nin), _p(A), _p(Bt), _p(b), _p(Q), _p(St), _p(Rt), _p(q), _p(rt), _p(Pu), _p(Px), _p(u0),
+                                C.byref(nut), _p(perf), _p(raw), C.c_int(mode))
     assert rc == 0
     n = nut.value
     return dict(A=A.T.copy(), B=Bt.T[:, :n].copy(), b=b, Q=Q.T.copy(), S=St.T[:n].copy(), R=Rt.T[:n, :n].copy(), q=q, r=rt[:n].copy(),

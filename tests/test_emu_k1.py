@@ -64,6 +64,30 @@ def test_lq_node_blocks_and_projection(model, wb, contact):
         assert rel(e[k], pr[k]) < 1e-10, k
 
 
+@pytest.mark.parametrize("contact", [(1, 1), (1, 0), (0, 0)])
+@pytest.mark.parametrize("mode", [1, 2])
+def test_cuda_k1b_schedules_equal_the_one_pass_schedule(model, wb, contact, mode):
+    """The GPU runs K1b as lu_kernel + wb_node_b1.inc (projection, dynamics) + wb_node_b2.inc (cost; mode 2: Q accumulated in place in its
+    output block, pre-scaled by dt).  The same includes on the CPU harness must reproduce the one-pass schedule that is checked against the oracle
+    above: identical arithmetic for every block but Q (exactly equal), Q up to the rounding of dt (a + b) vs dt a + dt b in mode 2."""
+    rng = np.random.default_rng(11 + sum(contact))
+    x, u = rand_state(model, rng, 0.5), rand_input(model, rng)
+    u[2] += 100
+    u[8] += 100
+    xn = x + rng.uniform(-0.01, 0.01, 58)
+    xref = np.array(model["x_init"])
+    swing = np.array([[0.03, 0.2, -1.0], [0.05, -0.1, 0.5]])
+    args = (wb.desc, x, u, xn, xref, 0.035, contact, swing, [0.7, 0.4], 0.3)
+    one = emu.lq_node(*args)
+    two = emu.lq_node(*args, mode=mode)
+    assert one["nut"] == two["nut"]
+    for k in ["A", "B", "b", "S", "R", "q", "r", "Pu", "Px", "u0"]:
+        assert np.array_equal(one[k], two[k]), k
+    assert rel(two["Q"], one["Q"]) < (1e-14 if mode == 2 else 1e-300) or np.array_equal(one["Q"], two["Q"])
+    for k in ["A", "B", "b", "Q", "S", "R", "q", "r", "C", "D", "e"]:
+        assert rel(two["raw"][k], one["raw"][k]) < 1e-14, k
+
+
 def test_joint_torque_map(model, wb):
     """computeJointTorques: the thread-per-node world-frame recursion (csrc/wb_torque.cuh) against the oracle (RNEA - J'W) and, for the
     oracle itself, the identity that the base rows of the same inverse dynamics vanish up to the dropped lin/ang coupling of M_bb"""

@@ -176,6 +176,28 @@ HD void pjWsMap(double* base, PjWs& s) {
   s.rr = s.V + NUT_MAX * NUT_MAX;            // 70   (ends at 3585)
 }
 
+// shared-memory map of K1b part 2 when Q accumulates in its final place in HBM/L2 (wb_node_b2.inc): no Q, no dynamics operands -- 70 KB,
+// three nodes per SM instead of two
+HD size_t pjCostWsDoubles() { return NU * NX + NU * NU + 1 + NZ + 1 + NC_MAX * (NX + 1) + NC_MAX * NUT_MAX + JU_MAX * NUC + PJ_SCRATCH + 48; }
+HD void pjCostWsMap(double* base, double* Qglobal, PjWs& s) {
+  pjWsMap(base, s);   // sets the scratch views relative to s.scratch below
+  s.Q = Qglobal;
+  s.S = base;
+  s.R = s.S + NU * NX;
+  s.gq = s.R + NU * NU + 1;
+  s.bvec = nullptr;
+  s.AB12 = nullptr;
+  s.Xt = s.gq + NZ + 1;
+  s.Kt = s.Xt + NC_MAX * (NX + 1);
+  s.JU = s.Kt + NC_MAX * NUT_MAX;
+  double* const scratch = s.JU + JU_MAX * NUC;
+  const ptrdiff_t shift = scratch - s.scratch;
+  s.scratch = scratch;
+  s.iw = reinterpret_cast<int*>(s.scratch + PJ_SCRATCH);
+  s.CD += shift; s.ev += shift; s.LU += shift; s.JS1 += shift; s.B1 += shift; s.D12 += shift; s.JRc += shift;
+  s.T11 += shift; s.T12 += shift; s.R11 += shift; s.R21 += shift; s.W += shift; s.V += shift; s.rr += shift;
+}
+
 // shared-memory map of K1b part 1 (projection + dynamics, wb_node_b1.inc): the same PjWs views on a 34 KB workspace without the Hessian blocks
 HD size_t pjDynWsDoubles() { return NC_MAX * (NX + 1) + NC_MAX * NUT_MAX + 12 * NZ + NX + (NC_MAX * NZ + NC_MAX + LU_LD * NU) + 48; }
 HD void pjDynWsMap(double* base, PjWs& s) {
@@ -777,27 +799,29 @@ HD void luPhaseScatter(Par P, int nc, const int* posOf, const double* Xt, const 
 
 // ---- K1b phase bodies shared by the host schedule (wb_node_b.inc) and the two CUDA schedules (wb_node_b1.inc / wb_node_b2.inc) -----------
 // dense swing-foot rows: [Q S'; S R] = JS' JS (JS: nsw x 93, ld nsw, in shared memory or straight from the record in HBM/L2)
+// qScale: factor on the contributions to Q alone (1 when Q is scaled with the other blocks on the way out; dt when Q accumulates in its
+// final place in HBM/L2, wb_node_b2.inc)
 template <class PAR>
-HD void pjSwingRows(PAR P, int nsw, const double* __restrict__ JS, const PjWs& s) {
-  par_mma_gemm<true, false, 4>(P, NX, NX, nsw, 1.0, JS, nsw, JS, nsw, s.Q, NX);
+HD void pjSwingRows(PAR P, int nsw, const double* __restrict__ JS, const PjWs& s, double qScale = 1.0) {
+  par_mma_gemm<true, false, 4>(P, NX, NX, nsw, qScale, JS, nsw, JS, nsw, s.Q, NX);
   par_mma_gemm<true, false, 4>(rot(P, 128), NU, NX, nsw, 1.0, JS + nsw * NX, nsw, JS, nsw, s.S, NU);
   par_mma_gemm<true, false, 3>(rot(P, 64), NU, NU, nsw, 1.0, JS + nsw * NX, nsw, JS + nsw * NX, nsw, s.R, NU);
 }
 // structured rows: JU' JU on their 27-column support, added to the Hessian
-HD void pjPhaseStructRows(Par P, int nru, const PjWs& s) {
+HD void pjPhaseStructRows(Par P, int nru, const PjWs& s, double qScale = 1.0) {
   for (int it = P.tid; it < NUC * NUC; it += P.nt) {
     const int a = it % NUC, c = it / NUC;
     double v = 0.0;
     for (int k = 0; k < nru; ++k) v = fma(s.JU[k + JU_MAX * a], s.JU[k + JU_MAX * c], v);
-    if (a < 15 && c < 15) s.Q[(3 + a) + NX * (3 + c)] += v;
+    if (a < 15 && c < 15) s.Q[(3 + a) + NX * (3 + c)] += qScale * v;
     else if (a >= 15 && c < 15) s.S[(a - 15) + NU * (3 + c)] += v;
     else if (a >= 15 && c >= 15) s.R[(a - 15) + NU * (c - 15)] += v;
   }
 }
 // Hessian: diagonal (tracking cost, joint limits, curvature shift) and the friction-cone blocks of the stance feet.  Touches entries the
 // structured rows also touch: never in the same phase as pjPhaseStructRows or a GEMM writing Q / R.
-HD void pjPhaseHessianDiag(Par P, const double* __restrict__ mid, const PjWs& s) {
-  for (int i = rot(P, 160).tid; i < NX; i += P.nt) s.Q[i + NX * i] += mid[Mid::HDG + i];
+HD void pjPhaseHessianDiag(Par P, const double* __restrict__ mid, const PjWs& s, double qScale = 1.0) {
+  for (int i = rot(P, 160).tid; i < NX; i += P.nt) s.Q[i + NX * i] += qScale * mid[Mid::HDG + i];
   for (int i = rot(P, 64).tid; i < NU + 18; i += P.nt) {   // one item per touched entry of R: 35 diagonal, 12 off-diagonal friction entries
     if (i < NU) {
       double v = mid[Mid::HDG + NX + i];
@@ -862,7 +886,8 @@ HD void pjPhaseGather(Par P, int nc, const int* colOf, const PjWs& s) {
 }
 // projected cost blocks, scaled by dt
 HD void pjPhaseOutputs(Par P, int nc, int nut, double dt, const PjWs& s, const NodeOut& out) {
-  for (int i = P.tid; i < NX * NX; i += P.nt) out.Q[i] = dt * s.Q[i];
+  if (s.Q != out.Q)   // (Q accumulated in place, already scaled: wb_node_b2.inc)
+    for (int i = P.tid; i < NX * NX; i += P.nt) out.Q[i] = dt * s.Q[i];
   for (int i = P.tid; i < NX; i += P.nt) out.q[i] = dt * s.gq[i];
   for (int i = P.tid; i < nut * NX; i += P.nt) out.St[(i % nut) + NUT_MAX * (i / nut)] = dt * s.T12[(i % nut) + NUT_MAX * (i / nut)];
   for (int i = P.tid; i < nut * nut; i += P.nt) out.Rt[(i % nut) + NUT_MAX * (i / nut)] = dt * s.V[(i % nut) + NUT_MAX * (i / nut)];
@@ -888,9 +913,9 @@ HD void pjPhaseRawA(Par P, int nc, double dt, const double* __restrict__ mid, do
   o += NC_MAX;
   if (P.tid == 0) o[0] = nc;
 }
-HD void pjPhaseRawB(Par P, double dt, const PjWs& s, double* raw) {
+HD void pjPhaseRawB(Par P, double dt, const PjWs& s, double* raw, double qScale = 1.0) {
   double* o = raw + NX * NZ + NX;
-  for (int i = P.tid; i < NX * NX; i += P.nt) o[i] = dt * s.Q[i];
+  for (int i = P.tid; i < NX * NX; i += P.nt) o[i] = (dt / qScale) * s.Q[i];
   o += NX * NX;
   for (int i = P.tid; i < NU * NX; i += P.nt) o[i] = dt * s.S[i];
   o += NU * NX;

@@ -26,7 +26,7 @@ namespace b200sqp {
 #define B200SQP_LQA_CTAS 4
 #endif
 #ifndef B200SQP_LQB_THREADS
-#define B200SQP_LQB_THREADS 512
+#define B200SQP_LQB_THREADS 256
 #endif
 #ifndef B200SQP_RO_THREADS
 #define B200SQP_RO_THREADS 32
@@ -43,8 +43,11 @@ namespace b200sqp {
 #ifndef B200SQP_LQB1_CTAS
 #define B200SQP_LQB1_CTAS 6
 #endif
+#ifndef B200SQP_K1B_Q_GLOBAL
+#define B200SQP_K1B_Q_GLOBAL 1
+#endif
 #ifndef B200SQP_LQB_CTAS
-#define B200SQP_LQB_CTAS 2
+#define B200SQP_LQB_CTAS 3
 #endif
 constexpr int LQA_THREADS = B200SQP_LQA_THREADS;
 constexpr int LQB_THREADS = B200SQP_LQB_THREADS;
@@ -328,8 +331,12 @@ __global__ void __launch_bounds__(LQB_THREADS, B200SQP_LQB_CTAS) lq_proj_kernel(
   const int* __restrict__ const luPerm = d.luPerm + stage * LU_PERM;
   const double dt = mid[Mid::META + 3];
   PjWs s;
-  pjWsMap(smem, s);
   NodeOut out = nodeOut(d, node, stage);
+#if B200SQP_K1B_Q_GLOBAL
+  pjCostWsMap(smem, out.Q, s);
+#else
+  pjWsMap(smem, s);
+#endif
   PHASE_CLOCK_BEGIN(1)
 #include "wb_node_b2.inc"
 #undef B200SQP_LU_PRECOMPUTED
