@@ -339,7 +339,6 @@ __global__ void __launch_bounds__(LQB_THREADS, B200SQP_LQB_CTAS) lq_proj_kernel(
 #endif
   PHASE_CLOCK_BEGIN(1)
 #include "wb_node_b2.inc"
-#undef B200SQP_LU_PRECOMPUTED
 }
 
 // ---- K4a: remap the projected QP solution, Armijo metric and norms (one CTA per (instance, stage)) --------------------------------------------
