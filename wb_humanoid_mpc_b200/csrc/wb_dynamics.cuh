@@ -94,7 +94,10 @@ HD void inv3(const double* A, double* Ai) {
 // ---- phase 1a: base quantities (warp 0: lane 0 values, lanes 1..9 tangents) and joint transforms (warp 1), all independent ---------
 template <bool DERIV>
 HD void dynPhaseJoints(Par P, const WbDeviceModel& m, const double* x, DynWs& w) {
-  for (int it = P.tid; it < 32 + NJ; it += P.nt) {
+  // item layout: the base-kinematics items (value + nine tangent directions) fill the first warp of the derivative path and the joints start on
+  // the next one; the value-only path (one base item, 23 joints) packs everything into 24 items -- a single round of the one-warp K3
+  constexpr int J0 = DERIV ? 32 : 1;
+  for (int it = P.tid; it < J0 + NJ; it += P.nt) {
     if (it < (DERIV ? 10 : 1)) {
       const int dir = it - 1;
       D1 R[9], S[9], v0[6], a0[6];
@@ -126,8 +129,8 @@ HD void dynPhaseJoints(Par P, const WbDeviceModel& m, const double* x, DynWs& w)
           }
         }
       }
-    } else if (it >= 32) {
-      const int i = it - 32 + 1;
+    } else if (it >= J0) {
+      const int i = it - J0 + 1;
       const double q = x[5 + i];
       const double* ax = m.axis[i];
       double s, c;
