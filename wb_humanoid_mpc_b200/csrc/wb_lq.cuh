@@ -809,8 +809,10 @@ HD void pjSwingRows(PAR P, int nsw, const double* __restrict__ JS, const PjWs& s
 }
 // structured rows: JU' JU on their 27-column support, added to the Hessian
 HD void pjPhaseStructRows(Par P, int nru, const PjWs& s, double qScale = 1.0) {
+  if (nru == 0) return;
   for (int it = P.tid; it < NUC * NUC; it += P.nt) {
     const int a = it % NUC, c = it / NUC;
+    if (a < 15 && c >= 15) continue;   // that block is S' : only S is stored
     double v = 0.0;
     for (int k = 0; k < nru; ++k) v = fma(s.JU[k + JU_MAX * a], s.JU[k + JU_MAX * c], v);
     if (a < 15 && c < 15) s.Q[(3 + a) + NX * (3 + c)] += qScale * v;

@@ -353,16 +353,22 @@ __global__ void __launch_bounds__(128) remap_kernel(WbDev d) {
   const double* dut = d.qp.du + stage * NUT_MAX;
   double* du = d.du + stage * NU;
   double arm = 0.0, dxn = 0.0, dun = 0.0;
+  // remapProjectedInput (ocs2_oc/src/multiple_shooting/Helpers.cpp:38-48): du = Pu dut + Px dx + u0.  35 outputs x 81 terms: three threads per
+  // output take every third term (fixed partition, so the result is deterministic), the operand vector is staged once.
+  __shared__ double zsh[NUT_MAX + NX], part[3][NU];
+  for (int j = threadIdx.x; j < nut + NX; j += blockDim.x) zsh[j] = j < nut ? dut[j] : dx[j - nut];
+  __syncthreads();
+  if (nut > 0 && threadIdx.x < 3 * NU) {
+    const int i = threadIdx.x % NU, p = threadIdx.x / NU;
+    const double* Pu = d.Pu + stage * NU * NUT_MAX;
+    const double* Px = d.Px + stage * NU * NX;
+    double acc = 0.0;
+    for (int j = p; j < nut + NX; j += 3) acc = fma(j < nut ? Pu[i + NU * j] : Px[i + NU * (j - nut)], zsh[j], acc);
+    part[p][i] = acc;
+  }
+  __syncthreads();
   for (int i = threadIdx.x; i < NU; i += blockDim.x) {
-    double s = 0.0;
-    if (nut > 0) {
-      // remapProjectedInput (ocs2_oc/src/multiple_shooting/Helpers.cpp:38-48)
-      s = d.u0p[stage * NU + i];
-      const double* Pu = d.Pu + stage * NU * NUT_MAX;
-      const double* Px = d.Px + stage * NU * NX;
-      for (int j = 0; j < nut; ++j) s = fma(Pu[i + NU * j], dut[j], s);
-      for (int j = 0; j < NX; ++j) s = fma(Px[i + NU * j], dx[j], s);
-    }
+    const double s = nut > 0 ? ((d.u0p[stage * NU + i] + part[0][i]) + part[1][i]) + part[2][i] : 0.0;
     du[i] = s;
     dun = fma(s, s, dun);
   }
