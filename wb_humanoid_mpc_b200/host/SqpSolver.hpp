@@ -298,6 +298,7 @@ class SqpSolver {
       // GPU idle during them).
       std::lock_guard<std::mutex> token(deviceToken(device_));
       check(b200sqp_solve(G.h, stream));
+      check(b200sqp_wait(G.h));   // the solve only enqueues (asynchronous): the token is kept until the device has finished it
     } else {
       check(b200sqp_solve(G.h, stream));
     }
