@@ -257,3 +257,34 @@ def test_policy_message_packing_round_trip(model, linear):
         assert np.allclose(data[probe].reshape(nu, 1 + nx)[:, 1:], Kk.astype(np.float32))
         assert np.allclose(data[probe].reshape(nu, 1 + nx)[:, 0], (prim["u"][probe] - Kk @ x[probe]).astype(np.float32), atol=1e-5)
     assert np.allclose(u_probe, prim["u"][probe], atol=2e-4)   # u = uff + K x at the sample's own state
+
+
+def test_cpp_config_loader_equals_the_flat_model_file():
+    """host/model_from_config.hpp reads the reference's OWN files (URDF + task.info + reference.info + gait.info: boost INFO subset, URDF subset,
+    welded fixed joints, Pinocchio joint order, frames, weights) -- what a node passes to WBMpcInterface -- and must produce the HostModel the flat
+    model file gives (that file is derived from the same config files by the Python loader, model_loader.py): every field of b200sqp_model_desc,
+    the settings, the reference-manager parameters and the gait table.  Needs the reference tree (absent on the GPU box: skipped there)."""
+    import ctypes as C
+    from pathlib import Path
+
+    from wb_humanoid_mpc_b200 import host_lib, model_loader
+
+    root = Path("/root/reference")
+    rel = model_loader.G1_REL
+    files = [root / rel["urdf"], root / rel["task"], root / rel["reference"], root / rel["gait"]]
+    if not all(f.exists() for f in files):
+        pytest.skip("reference config files not present")
+    a = host_lib.HostModel()                 # flat file
+    b = host_lib.HostModel(config=files)     # C++ loader of the config files
+    assert (a.nx, a.nu, a.dt, a.horizon) == (b.nx, b.nu, b.dt, b.horizon)
+    (da, sa), (db, sb) = a.desc_and_settings(), b.desc_and_settings()
+    for name, ctype in da._fields_:
+        va, vb = np.ctypeslib.as_array(getattr(da, name)) if hasattr(getattr(da, name), "_length_") else getattr(da, name), \
+            np.ctypeslib.as_array(getattr(db, name)) if hasattr(getattr(db, name), "_length_") else getattr(db, name)
+        assert np.allclose(va, vb, rtol=1e-14, atol=1e-15, equal_nan=True), name
+    assert bytes(sa) == bytes(sb)
+    xa, xb = a.dump(), b.dump()
+    assert xa.shape == xb.shape and np.allclose(xa, xb, rtol=1e-14, atol=1e-15)
+    # missing files raise like the reference interfaces do (std::invalid_argument -> RuntimeError through the C layer)
+    with pytest.raises(RuntimeError, match="not found"):
+        host_lib.HostModel(config=[root / "nope.urdf", files[1], files[2], files[3]])

@@ -3,6 +3,7 @@
 #include <cstring>
 #include <string>
 
+#include "model_from_config.hpp"
 #include "MpcPolicyMsg.hpp"
 #include "SqpLogging.hpp"
 #include "SqpSolver.hpp"
@@ -33,6 +34,33 @@ void* b200host_model_load(const char* path) {
     g_err = e.what();
     return nullptr;
   }
+}
+// the whole-body model straight from the reference's own config files (URDF + task.info + reference.info + gait.info; gait may be "")
+void* b200host_model_from_config(const char* urdf, const char* task, const char* reference, const char* gait) {
+  try {
+    return new HostModel(loadModelFromConfig(urdf, task, reference, gait ? gait : ""));
+  } catch (const std::exception& e) {
+    g_err = e.what();
+    return nullptr;
+  }
+}
+// everything of a HostModel that b200host_model_desc / _dims do not return, as one array (test hook): total mass, default base height, swing
+// config (8), dt, horizon, initial state (nx), default joint state (nj), then per gait in name order: count, modes, switching times
+int b200host_model_dump(void* m, double* out, int cap) {
+  const HostModel& M = *static_cast<HostModel*>(m);
+  std::vector<double> v{M.totalMass, M.defaultBaseHeight, M.swing.liftOffVelocity, M.swing.touchDownVelocity, M.swing.swingHeight,
+                        M.swing.touchDownHeightOffset, M.swing.swingTimeScale, M.swing.ipfLiftOffVelocity, M.swing.ipfTouchDownVelocity,
+                        M.swing.ipfMidPointValue, M.dt, M.timeHorizon};
+  v.insert(v.end(), M.initialState.begin(), M.initialState.end());
+  v.insert(v.end(), M.defaultJointState.begin(), M.defaultJointState.end());
+  for (const auto& g : M.gaits) {
+    v.push_back(static_cast<double>(g.second.modeSequence.size()));
+    for (int mode : g.second.modeSequence) v.push_back(mode);
+    v.insert(v.end(), g.second.switchingTimes.begin(), g.second.switchingTimes.end());
+  }
+  const int n = static_cast<int>(v.size());
+  for (int i = 0; i < n && i < cap; ++i) out[i] = v[i];
+  return n;
 }
 void b200host_model_free(void* m) { delete static_cast<HostModel*>(m); }
 int b200host_model_dims(void* m, int* nx, int* nu, double* dt, double* horizon) {

@@ -83,8 +83,15 @@ def _check(rc):
 
 
 class HostModel:
-    def __init__(self, path=MODEL_TXT):
-        self.h = lib().b200host_model_load(str(path).encode())
+    def __init__(self, path=MODEL_TXT, config=None):
+        """path: the flat model file; config = (urdf, task.info, reference.info, gait.info): the C++ loader of the reference's own files instead"""
+        L = lib()
+        if config is not None:
+            L.b200host_model_from_config.restype = C.c_void_p
+            L.b200host_model_from_config.argtypes = [C.c_char_p] * 4
+            self.h = L.b200host_model_from_config(*[str(c).encode() for c in config])
+        else:
+            self.h = L.b200host_model_load(str(path).encode())
         if not self.h:
             raise RuntimeError("b200sqp host: " + lib().b200host_last_error().decode())
         nx, nu, dt, hz = C.c_int(), C.c_int(), C.c_double(), C.c_double()
@@ -95,6 +102,15 @@ class HostModel:
         d, s = abi.ModelDesc(), abi.Settings()
         lib().b200host_model_desc(self.h, C.byref(d), C.byref(s))
         return d, s
+
+    def dump(self):
+        """everything else a HostModel holds, as one array (see b200host_model_dump)"""
+        L = lib()
+        L.b200host_model_dump.argtypes = [C.c_void_p, dp, C.c_int]
+        n = L.b200host_model_dump(self.h, None, 0)
+        out = np.zeros(n)
+        L.b200host_model_dump(self.h, out.ctypes.data_as(dp), n)
+        return out
 
     def cen_desc(self):
         """b200sqp_cen_desc of a centroidal model file, None for a whole-body one"""
