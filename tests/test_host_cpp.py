@@ -288,3 +288,22 @@ def test_cpp_config_loader_equals_the_flat_model_file():
     # missing files raise like the reference interfaces do (std::invalid_argument -> RuntimeError through the C layer)
     with pytest.raises(RuntimeError, match="not found"):
         host_lib.HostModel(config=[root / "nope.urdf", files[1], files[2], files[3]])
+    # the centroidal MPC: other state layout and weights, task-space link frame, ICP / leg-torque costs, nominal inertia of the SRBD model type
+    cfiles = [files[0], root / rel["centroidal_task"], root / rel["centroidal_reference"], files[3]]
+    ca, cb = host_lib.HostModel(host_lib.CEN_MODEL_TXT), host_lib.HostModel(config=cfiles, centroidal=True)
+    assert (ca.nx, ca.nu, ca.dt, ca.horizon) == (cb.nx, cb.nu, cb.dt, cb.horizon) and ca.nx == 35
+    (da, sa), (db, sb) = ca.desc_and_settings(), cb.desc_and_settings()
+    for name, _ in da._fields_:
+        va, vb = getattr(da, name), getattr(db, name)
+        if hasattr(va, "_length_"):
+            va, vb = np.ctypeslib.as_array(va), np.ctypeslib.as_array(vb)
+        assert np.allclose(va, vb, rtol=1e-13, atol=1e-15, equal_nan=True), name
+    assert bytes(sa) == bytes(sb)
+    xa, xb = ca.cen_desc(), cb.cen_desc()
+    assert xa is not None and xb is not None
+    for name, _ in xa._fields_:
+        va, vb = getattr(xa, name), getattr(xb, name)
+        if hasattr(va, "_length_"):
+            va, vb = np.ctypeslib.as_array(va), np.ctypeslib.as_array(vb)
+        assert np.allclose(va, vb, rtol=1e-12, atol=1e-14), name
+    assert np.allclose(ca.dump(), cb.dump(), rtol=1e-14, atol=1e-15)

@@ -35,10 +35,11 @@ void* b200host_model_load(const char* path) {
     return nullptr;
   }
 }
-// the whole-body model straight from the reference's own config files (URDF + task.info + reference.info + gait.info; gait may be "")
-void* b200host_model_from_config(const char* urdf, const char* task, const char* reference, const char* gait) {
+// the whole-body (centroidal = 0) or centroidal (1) model straight from the reference's own config files (URDF + task.info + reference.info +
+// gait.info; gait may be "")
+void* b200host_model_from_config(const char* urdf, const char* task, const char* reference, const char* gait, int centroidal) {
   try {
-    return new HostModel(loadModelFromConfig(urdf, task, reference, gait ? gait : ""));
+    return new HostModel(loadModelFromConfig(urdf, task, reference, gait ? gait : "", centroidal != 0));
   } catch (const std::exception& e) {
     g_err = e.what();
     return nullptr;

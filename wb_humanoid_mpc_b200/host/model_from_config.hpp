@@ -11,7 +11,8 @@
 //     by joint name (urdfdom keeps them in a std::map), contact / collision frames attached to their parent joint's frame;
 //   * the term constants of ModelSettings / HumanoidCostConstraintFactory / WBMpcInterface, field by field as
 //     wb_humanoid_mpc_b200/model_loader.py documents them (each with its reference source line).
-// The whole-body MPC only (the centroidal model also needs pinocchio::ccrba at the nominal posture: use the flat file).
+// Both MPCs: the whole-body one (WBMpcInterface) and, with centroidal = true, the centroidal one (CentroidalMpcInterface: other state layout and
+// weights, the task-space link cost, ICP and leg-torque costs, and the nominal inertia of the single-rigid-body model type).
 // tests/test_host_cpp.py compares every field with the flat model file derived by the Python loader.
 #pragma once
 #include <algorithm>
@@ -299,9 +300,9 @@ struct Body {
 
 }  // namespace cfg
 
-// the whole-body MPC of WBMpcInterface from its own files; gaitFile may be empty (no gait table)
+// the MPC of WBMpcInterface (or, centroidal = true, of CentroidalMpcInterface) from its own files; gaitFile may be empty (no gait table)
 inline HostModel loadModelFromConfig(const std::string& urdfFile, const std::string& taskFile, const std::string& referenceFile,
-                                     const std::string& gaitFile) {
+                                     const std::string& gaitFile, bool centroidal = false) {
   using namespace cfg;
   const Info task = parseInfo(taskFile);
   // ---- URDF -> links, joints -----------------------------------------------------------------------------------------------------------------
@@ -353,7 +354,14 @@ inline HostModel loadModelFromConfig(const std::string& urdfFile, const std::str
       rootLink = kv.first;
     }
   std::vector<Body> bodies{Body{"", -1, eye(), V3{0, 0, 0}, V3{0, 0, 0}, Inertia{}, 0.0, 0.0}};
+  struct LinkPlacement {
+    int body;
+    M3 R;
+    V3 p;
+  };
+  std::map<std::string, LinkPlacement> linkBody;   // link frame in the joint frame of the body it is welded to
   std::function<void(const std::string&, int, const M3&, V3)> visit = [&](const std::string& link, int bi, const M3& R, V3 p) {
+    linkBody[link] = LinkPlacement{bi, R, p};
     bodies[bi].inertia = bodies[bi].inertia + links.at(link).transformed(R, p);
     auto it = byParent.find(link);
     if (it == byParent.end()) return;
@@ -376,9 +384,10 @@ inline HostModel loadModelFromConfig(const std::string& urdfFile, const std::str
   visit(rootLink, 0, eye(), V3{0, 0, 0});
 
   HostModel m;
-  m.name = "g1_wb";
+  m.name = centroidal ? "g1_centroidal" : "g1_wb";
+  m.centroidal = centroidal;
   m.nj = static_cast<int>(bodies.size()) - 1;
-  m.nx = 2 * (6 + m.nj);
+  m.nx = centroidal ? 12 + m.nj : 2 * (6 + m.nj);   // CentroidalMpcRobotModel.h:52-160 / WBAccelMpcRobotModel.h:76-241
   m.nu = 12 + m.nj;
   if (m.nj + 1 > 32 || m.nx > 64 || m.nu > 40) throw std::invalid_argument("[b200sqp::host] model exceeds the sizes of b200sqp_model_desc");
   std::map<std::string, int> jidx;
@@ -459,13 +468,23 @@ inline HostModel loadModelFromConfig(const std::string& urdfFile, const std::str
   // the acceleration entries and leaves the acceleration weights at their defaults 0.01 (EndEffectorDynamicsCostHelpers.h:45-50): reproduced.
   const std::string w = "task_space_foot_cost_weights.";
   const char* axes[3] = {"x", "y", "z"};
-  for (int a = 0; a < 3; ++a) {
-    d.foot_cost_w[a] = task.num(w + "pos_" + axes[a]);
-    d.foot_cost_w[3 + a] = task.num(w + "orientation_" + axes[a]);
-    d.foot_cost_w[6 + a] = task.num(w + "lin_acceleration_" + axes[a]);
-    d.foot_cost_w[9 + a] = task.num(w + "ang_acceleration_" + axes[a]);
-    d.foot_cost_w[12 + a] = 0.01;
-    d.foot_cost_w[15 + a] = 0.01;
+  // EndEffectorKinematicsWeights::toVector (centroidal): position, orientation, linear velocity, angular velocity
+  auto kinematicsWeights = [&](const std::string& prefix, double* out) {
+    const char* kinds[4] = {"pos_", "orientation_", "lin_velocity_", "ang_velocity_"};
+    for (int k = 0; k < 4; ++k)
+      for (int a = 0; a < 3; ++a) out[3 * k + a] = task.num(prefix + kinds[k] + axes[a]);
+  };
+  if (centroidal) {
+    kinematicsWeights(w, d.foot_cost_w);   // entries 12..17 stay zero
+  } else {
+    for (int a = 0; a < 3; ++a) {
+      d.foot_cost_w[a] = task.num(w + "pos_" + axes[a]);
+      d.foot_cost_w[3 + a] = task.num(w + "orientation_" + axes[a]);
+      d.foot_cost_w[6 + a] = task.num(w + "lin_acceleration_" + axes[a]);
+      d.foot_cost_w[9 + a] = task.num(w + "ang_acceleration_" + axes[a]);
+      d.foot_cost_w[12 + a] = 0.01;
+      d.foot_cost_w[15 + a] = 0.01;
+    }
   }
   d.fric_coeff = task.num("contacts.frictionForceConeSoftConstraint.frictionCoefficient");
   d.fric_mu = task.num("contacts.frictionForceConeSoftConstraint.mu");
@@ -503,6 +522,67 @@ inline HostModel loadModelFromConfig(const std::string& urdfFile, const std::str
   const Info ref = parseInfo(referenceFile);
   m.defaultBaseHeight = ref.num("defaultBaseHeight");
   m.defaultJointState = ref.column("defaultJointState", m.nj);
+  if (centroidal) {
+    b200sqp_cen_desc& c = m.cen;
+    std::memset(&c, 0, sizeof(c));
+    // task_space_costs: one EndEffectorKinematicsQuadraticCost per listed link (CentroidalMpcInterface.cpp:331-362); the device path carries one
+    const Info& costs = task.at("task_space_costs");
+    if (costs.kids.size() != 1) throw std::invalid_argument("[b200sqp::host] exactly one task-space link cost is supported (G1: the torso)");
+    const std::string cname = costs.kids.front().first;
+    const auto lb = linkBody.find(costs.kids.front().second.at("link_name").value);
+    if (lb == linkBody.end()) throw std::invalid_argument("[b200sqp::host] task-space cost link not in the URDF");
+    if (d.n_frames >= 16) throw std::invalid_argument("[b200sqp::host] too many frames");
+    c.torso_frame = d.n_frames;   // the task-space link rides as the last frame of the table
+    d.frame_body[d.n_frames] = lb->second.body;
+    d.frame_p[d.n_frames][0] = lb->second.p.x;
+    d.frame_p[d.n_frames][1] = lb->second.p.y;
+    d.frame_p[d.n_frames][2] = lb->second.p.z;
+    d.n_frames += 1;
+    for (int k = 0; k < 9; ++k) c.torso_R[k] = lb->second.R.m[k];
+    kinematicsWeights("task_space_costs." + cname + ".weights.", c.torso_w);
+    c.icp_weight = task.num("icp_cost_weights.icpErrorWeight");
+    const char* sides[2] = {"left_leg_torque_cost", "right_leg_torque_cost"};   // ExternalTorqueQuadraticCostAD (HumanoidCostConstraintFactory.cpp:234-245)
+    for (int sd = 0; sd < 2; ++sd) {
+      const auto names = task.list(std::string(sides[sd]) + ".activeJointNames");
+      if (names.size() != 6) throw std::invalid_argument("[b200sqp::host] leg torque cost: six active joints expected");
+      const std::vector<double> wts = task.at(sides[sd]).column("weights", 6);
+      for (int k = 0; k < 6; ++k) {
+        c.torque_joint[sd][k] = jointIndex(names[k]);
+        c.torque_w[sd][k] = wts[k];
+      }
+    }
+    c.model_type = static_cast<int32_t>(task.num("centroidalModelType"));
+    // createCentroidalModelInfo, SingleRigidBodyDynamics (ocs2_centroidal_model/src/FactoryFunctions.cpp:113-121): pinocchio::ccrba at
+    // q = (0_6, nominal joint angles) -> rotational inertia about the centre of mass (base axes) and base - com
+    std::vector<M3> Rw{eye()};
+    std::vector<V3> pw{V3{0, 0, 0}};
+    for (int i = 1; i <= m.nj; ++i) {
+      const Body& b = bodies[i];
+      const double th = m.defaultJointState[i - 1], sn = std::sin(th), cs = 1.0 - std::cos(th);
+      const M3 K{{0, -b.axis.z, b.axis.y, b.axis.z, 0, -b.axis.x, -b.axis.y, b.axis.x, 0}};
+      const M3 KK = mul(K, K);
+      M3 Rq = eye();
+      for (int k = 0; k < 9; ++k) Rq.m[k] += sn * K.m[k] + cs * KK.m[k];
+      Rw.push_back(mul(mul(Rw[b.parent], b.R), Rq));
+      pw.push_back(add(pw[b.parent], mul(Rw[b.parent], b.p)));
+    }
+    std::vector<V3> cw;
+    V3 G{0, 0, 0};
+    for (int i = 0; i <= m.nj; ++i) {
+      cw.push_back(add(pw[i], mul(Rw[i], bodies[i].inertia.c)));
+      G = add(G, V3{bodies[i].inertia.m * cw[i].x, bodies[i].inertia.m * cw[i].y, bodies[i].inertia.m * cw[i].z});
+    }
+    G = V3{G.x / m.totalMass, G.y / m.totalMass, G.z / m.totalMass};
+    M3 Ig{{0, 0, 0, 0, 0, 0, 0, 0, 0}};
+    for (int i = 0; i <= m.nj; ++i) {
+      const M3 Iw = Inertia::shift(mul(mul(Rw[i], bodies[i].inertia.I), tr(Rw[i])), bodies[i].inertia.m, sub(cw[i], G));
+      for (int k = 0; k < 9; ++k) Ig.m[k] += Iw.m[k];
+    }
+    for (int k = 0; k < 9; ++k) c.inertia_nominal[k] = Ig.m[k];
+    c.com_to_base_nominal[0] = -G.x;
+    c.com_to_base_nominal[1] = -G.y;
+    c.com_to_base_nominal[2] = -G.z;
+  }
   if (!gaitFile.empty()) {
     const Info g = parseInfo(gaitFile);
     for (const std::string& name : g.list("list")) {

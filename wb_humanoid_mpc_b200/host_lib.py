@@ -83,13 +83,14 @@ def _check(rc):
 
 
 class HostModel:
-    def __init__(self, path=MODEL_TXT, config=None):
-        """path: the flat model file; config = (urdf, task.info, reference.info, gait.info): the C++ loader of the reference's own files instead"""
+    def __init__(self, path=MODEL_TXT, config=None, centroidal=False):
+        """path: the flat model file; config = (urdf, task.info, reference.info, gait.info): the C++ loader of the reference's own files instead
+        (centroidal: the centroidal MPC's task / reference files)"""
         L = lib()
         if config is not None:
             L.b200host_model_from_config.restype = C.c_void_p
-            L.b200host_model_from_config.argtypes = [C.c_char_p] * 4
-            self.h = L.b200host_model_from_config(*[str(c).encode() for c in config])
+            L.b200host_model_from_config.argtypes = [C.c_char_p] * 4 + [C.c_int]
+            self.h = L.b200host_model_from_config(*[str(c).encode() for c in config], int(centroidal))
         else:
             self.h = L.b200host_model_load(str(path).encode())
         if not self.h:
